@@ -1,0 +1,162 @@
+/* mtp_b200.h -- C ABI of the B200-native Moment Tensor Potential pair-style compute.
+ *
+ * This is the drop-in boundary for ONE path of RichardZJM/lammps-mtp-kokkos: the per-step
+ * energy / force / virial / extrapolation-grade evaluation that the reference performs in
+ *   PairMTP::compute                      LAMMPS/ML-MTP/pair_mtp.cpp:72-280          (semantics / oracle)
+ *   PairMTPExtrapolation::compute         LAMMPS/ML-MTP/pair_mtp_extrapolation.cpp:68-382
+ *   PairMTPKokkos<Dev>::compute           LAMMPS/KOKKOS/pair_mtp_kokkos.cpp:197-399   (mtp/kk)
+ *   PairMTPsKokkos<Dev>::compute          LAMMPS/KOKKOS/pair_mtps_kokkos.cpp:223-423  (mtp/small/kk)
+ *   PairMTP*ExtrapolationKokkos::compute  LAMMPS/KOKKOS/pair_mtp_extrapolation_kokkos.cpp:275-610,
+ *                                         pair_mtps_extrapolation_kokkos.cpp:305-639
+ * and the potential-file load the reference performs in
+ *   PairMTP::read_file                    pair_mtp.cpp:335-655
+ *   PairMTPExtrapolation::read_file       pair_mtp_extrapolation.cpp:528-619.
+ *
+ * The host side that binds these entry points is the LAMMPS PairStyle in
+ * lammps-mtp-kokkos_b200/lammps/pair_mtp_b200.{h,cpp}.
+ *
+ * Conventions: plain C, no torch / Kokkos / LAMMPS types.  Every function that returns int
+ * returns 0 on success or a negative MTP_ERR_* code; mtp_last_error() gives the text of the
+ * calling thread's last failure (the PairStyle turns it into error->all, the reference's
+ * fatal-error convention, pair_mtp.cpp:92,288,306,315,327).  All arithmetic is IEEE FP64.
+ * There is no CPU fallback: every compute entry point requires a CUDA device (sm_100a).
+ */
+#ifndef MTP_B200_H
+#define MTP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTP_B200_ABI_VERSION 1
+
+#define MTP_OK 0
+#define MTP_ERR_ARG (-1)      /* bad argument */
+#define MTP_ERR_FILE (-2)     /* potential file cannot be opened / parsed (message = reference wording) */
+#define MTP_ERR_CUDA (-3)     /* CUDA runtime failure or no sm_100 device */
+#define MTP_ERR_SPECIES (-4)  /* "Too few species count in the MTP potential!" (pair_mtp.cpp:91-93) */
+#define MTP_ERR_MODE (-5)     /* request incompatible with the potential's selection mode */
+#define MTP_ERR_TABLE (-6)    /* alpha_index_times is not a topologically ordered program */
+
+/* pair_style variants (README.md:36-40 of the reference) */
+#define MTP_VARIANT_LARGE 0   /* mtp/kk, mtp/extrapolation/kk              : throughput path */
+#define MTP_VARIANT_SMALL 1   /* mtp/small/kk, mtp/extrapolation/small/kk  : latency path   */
+
+typedef struct mtp_handle mtp_handle;
+
+/* Host-side description of a potential: the tables of pair_mtp.h:47-70 (+ pair_mtp_extrapolation.h:46-59).
+ * Used by mtp_create(); mtp_create_from_file() fills the same structure from an MLIP-3 .almtp file. */
+typedef struct {
+  int species_count;
+  int radial_func_count;          /* R */
+  int radial_basis_size;          /* B */
+  int alpha_moment_count;         /* M */
+  int alpha_index_basic_count;    /* K */
+  int alpha_index_times_count;    /* T */
+  int alpha_scalar_count;         /* A */
+  double min_cutoff, max_cutoff, scaling;
+  const double *radial_basis_coeffs;   /* [S][S][R][B]  index ((it*S+jt)*R+mu)*B+ri, pair_mtp.cpp:142-147 */
+  const int *alpha_index_basic;        /* [K][4] mu,ax,ay,az */
+  const int *alpha_index_times;        /* [T][4] a0,a1,mult,a3 */
+  const int *alpha_moment_mapping;     /* [A] */
+  const double *species_coeffs;        /* [S] */
+  const double *linear_coeffs;         /* [A] (moment_coeffs) */
+  /* selection state; inverse_active_set == NULL means "no extrapolation" */
+  int configuration_mode;              /* energy_weight == 1, pair_mtp_extrapolation.cpp:605 */
+  const double *inverse_active_set;    /* [Q][Q] row-major, Q = S*S*R*B + S + A */
+} mtp_params_host;
+
+typedef struct {
+  int abi_version;
+  int species_count, radial_func_count, radial_basis_size;
+  int alpha_moment_count, alpha_index_basic_count, alpha_index_times_count, alpha_scalar_count;
+  int max_alpha_index_basic;      /* P = 1 + max rank, pair_mtp.cpp:510-515 */
+  int coeff_count;                /* Q, 0 when no selection state is loaded */
+  int configuration_mode;
+  int has_selection_state;
+  int wave_count;                 /* dependency depth of the contraction program */
+  int chunksize;
+  int device;
+  double min_cutoff, max_cutoff, scaling;
+} mtp_info;
+
+/* One force evaluation = one call of Pair::compute(eflag, vflag).  All pointers are DEVICE pointers
+ * for mtp_compute() and HOST pointers for mtp_compute_host().
+ *
+ * Neighbor list (full list, pair_mtp.cpp:318): entry jj of atom i is
+ *     neighbors[(neigh_offsets ? neigh_offsets[i] : i * stride_i) + jj * stride_jj] & neighmask
+ * which covers both LAMMPS-KOKKOS's 2-D d_neighbors(i,jj) view (pair_mtp_kokkos.cpp:236-240,438) in
+ * either layout and a CSR / paged host list (list->firstneigh, pair_mtp.cpp:84-85,113).  numneigh is
+ * indexed by atom id, ilist (NULL = identity) lists the inum owned centres (pair_mtp.cpp:81-89). */
+typedef struct {
+  int variant;                    /* MTP_VARIANT_* */
+  int inum, nall;
+  const double *x;                /* [nall][3]  atom->x */
+  const int *type;                /* [nall]     atom->type, 1-based */
+  const int *ilist;               /* [inum] or NULL */
+  const int *numneigh;            /* [>= max listed id + 1] */
+  const int *neighbors;
+  const long long *neigh_offsets; /* [>= max listed id + 1] or NULL */
+  long long stride_i, stride_jj;
+  int neighmask;                  /* NEIGHMASK = 0x1FFFFFFF; 0 means "use 0x1FFFFFFF" */
+  int eflag;                      /* bit0 global energy, bit1 per-atom (LAMMPS ENERGY_GLOBAL/ATOM) */
+  int vflag;                      /* !=0: pairwise virial -sym(F (x) r) like pair_mtp.cpp:257-266; bit2: per-atom */
+  int want_grade;                 /* extrapolation_flag || mlip3_style (pair_mtp_extrapolation.cpp:71) */
+  long long natoms_total;         /* atom->natoms, configuration-mode normalisation (:373-376); 0 = inum */
+  double *f;                      /* [nall][3] accumulated into (ghost rows included) */
+  double *eatom;                  /* [nall] or NULL; eatom[i] ASSIGNED for listed i (pair_mtp.cpp:210) */
+  double *vatom;                  /* [nall][6] or NULL; accumulated on the centre atom (:268-276) */
+  double *ev_out;                 /* [8] overwritten: E, virial xx,yy,zz,xy,xz,yz, max grade */
+  double *grades;                 /* [nall] by atom id or NULL: neighbourhood grades (:335) */
+  double *cfg_candidate;          /* [Q] or NULL: configuration-mode candidate vector, overwritten */
+  unsigned char *within_cutoff;   /* optional: 1/0 per neighbor entry, same indexing as `neighbors` */
+  void *stream;                   /* cudaStream_t (mtp_compute only) */
+} mtp_compute_args;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* Parse an MLIP-3 .almtp potential (grammar of pair_mtp.cpp:345-570 + mtp_radial_basis.cpp:59-102);
+ * with want_selection_state != 0 also the MaxVol selection state that must follow it
+ * (pair_mtp_extrapolation.cpp:545-612).  device < 0 = current device.  NULL on failure. */
+mtp_handle *mtp_create_from_file(const char *path, int want_selection_state, int device);
+mtp_handle *mtp_create(const mtp_params_host *params, int device);
+void mtp_destroy(mtp_handle *h);
+const char *mtp_last_error(void);
+int mtp_get_info(const mtp_handle *h, mtp_info *out);
+/* Copy the parsed tables back out (sizes from mtp_get_info); any pointer may be NULL. */
+int mtp_get_tables(const mtp_handle *h, double *radial_basis_coeffs, int *alpha_index_basic,
+                   int *alpha_index_times, int *alpha_moment_mapping, double *species_coeffs,
+                   double *linear_coeffs, double *inverse_active_set);
+
+/* "chunksize n" keyword (pair_mtp_kokkos.cpp:113-117, README.md:44): upper bound on the rows of
+ * per-atom scratch that live in HBM at once (only the grade path keeps any; the force path keeps
+ * all per-atom state on chip).  Must be >= 1. */
+int mtp_set_chunksize(mtp_handle *h, int chunksize);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+/* Asynchronous on args->stream; results are valid after the stream is synchronised. */
+int mtp_compute(mtp_handle *h, const mtp_compute_args *device_args);
+/* Waits for the device and reports deferred errors (species bound check, pair_mtp.cpp:91-93). */
+int mtp_synchronize(mtp_handle *h);
+/* Same evaluation with HOST buffers: copies x/type (and the neighbor list when list_changed != 0,
+ * i.e. on LAMMPS re-neighboring steps, neighbor->ago == 0) to the device, runs mtp_compute, adds the
+ * result into the host f / eatom / vatom / grades and returns after the copies complete. */
+int mtp_compute_host(mtp_handle *h, const mtp_compute_args *host_args, int list_changed);
+
+/* ---- ghost-atom halo helpers (device) ---------------------------------------------------------- */
+/* forward: out[k][:] = x[sendlist[k]][:] + shift[:]   (LAMMPS Comm::forward_comm pack, on device) */
+int mtp_halo_pack_x(const double *x, const int *sendlist, int n, const double *shift3_host, double *out,
+                    void *stream);
+/* reverse: f[sendlist[k]][:] += buf[k][:]             (Comm::reverse_comm unpack, newton on) */
+int mtp_halo_unpack_add_f(double *f, const int *sendlist, int n, const double *buf, void *stream);
+
+/* ---- measured roofs ----------------------------------------------------------------------------- */
+/* FP64 vector (DFMA) and FP64 tensor (mma.sync.m8n8k4.f64, DMMA) peak of the device, in TFLOP/s. */
+int mtp_fp64_peak(int device, double *dfma_tflops, double *dmma_tflops);
+
+/* number of kernels launched by this library since load (bench.py's gpu_launches claim) */
+long long mtp_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,58 @@
+// Device-side view of a loaded potential and of one compute call (plain structs passed by value).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mtpb200 {
+
+struct DevPass {
+  const int *level_group_begin;    // [nlevels + 1]
+  const int *group_term_base;      // [ngroups]
+  const int *node;                 // [ngroups * 32]
+  const int *nterms;               // [ngroups * 32]
+  const uint2 *terms;              // [slot_rows * 32] {a | b << 16, float bits of mult}
+  int nlevels;
+};
+
+struct DevPotential {
+  int S, R, B, K, M, A, P, Q;
+  double rmin, rmax, scaling, cutsq;
+  const double *radial;      // [S][S][R][B]
+  const uint32_t *basic;     // [K] mu | ax << 8 | ay << 16 | az << 24
+  const double *species;     // [S]
+  const double *lin;         // [A]
+  const int *map;            // [A]
+  const double *ginit;       // [M]
+  DevPass fwd, rev;
+};
+
+// packed position + species record: one 32-byte sector per gathered neighbor
+struct __align__(32) AtomRec {
+  double x, y, z;
+  long long t;    // type - 1
+};
+
+struct SiteArgs {
+  int inum, nall;
+  const AtomRec *xt;
+  const int *ilist;
+  const int *numneigh;
+  const int *neighbors;
+  const long long *neigh_offsets;
+  long long stride_i, stride_jj;
+  int neighmask;
+  int eflag_global, eflag_atom, vflag_any, vflag_atom, want_grade;
+  double *f;
+  double *eatom;
+  double *vatom;
+  double *grades;
+  unsigned char *within;
+  double *partials;       // [gridDim.x][8] per-CTA energy/virial/max-grade
+  double *cand_rows;      // grade steps: [chunk rows][Qpad] candidate vectors
+  int cand_ld;            // Qpad
+  int first_ii;           // chunk offset into ilist (grade steps)
+  int *status;
+};
+
+}    // namespace mtpb200

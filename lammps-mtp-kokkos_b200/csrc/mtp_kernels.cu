@@ -1,0 +1,681 @@
+// Hand-written sm_100a kernels of the MTP hot path (FP64 throughout).
+//
+// One warp owns one centre atom at a time (persistent CTAs, grid-stride over ilist).  Everything the
+// reference keeps in HBM per atom -- the basic moments, the contraction-tree values, their adjoints and
+// above all the [neighbors][K][3] Jacobian (pair_mtp_kokkos.cpp:277-282,540-542,627) -- lives in shared
+// memory / registers here; the Jacobian is never formed: the backward pass re-evaluates the per-pair
+// monomials and applies dE/dm on the fly.
+//
+//   phase 1  gather + cutoff mask (pair_mtp.cpp:112-129) -> Chebyshev x cutoff (mtp_rb_chevbyshev_basis.cpp:29-54)
+//            -> radial contraction (pair_mtp.cpp:139-151) -> basic moments (pair_mtp.cpp:154-172)
+//   tree     contraction program forward (pair_mtp.cpp:196-201), site energy (:204-212),
+//            reverse mode (:217-233), both as atomic-free level-ordered gather lists
+//   phase 2  per-pair force from dE/dm (pair_mtp.cpp:236-254), ghost-inclusive scatter with red.f64,
+//            virial -sym(F (x) r) (:257-276); on grade steps also the candidate vector
+//            (pair_mtp_extrapolation.cpp:193-198,235-252,322-329)
+//
+// Unit-vector form used here (u = r/d, q = (a,b,c), rho = |q|):
+//   m_k       = sum_n f_mu(d_n) u_n^q                                  [= val*pow of pair_mtp.cpp:165-172]
+//   dm_k/dr_a = u_a u^q (f'_mu - rho f_mu/d) + (f_mu/d) q_a u^(q-e_a)  [= moment_jacobian of :175-191]
+#include "mtp_device.cuh"
+
+#include <cstdio>
+
+namespace mtpb200 {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int PEND = 64;    // pending in-cutoff neighbors per warp (two 32-lane gathers)
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+
+// x[nall][3] + type[nall] -> 32-byte records (one sector per gathered neighbor)
+__global__ void pack_xt_kernel(int nall, const double *__restrict__ x, const int *__restrict__ type,
+                               AtomRec *__restrict__ xt)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nall) return;
+  AtomRec r;
+  r.x = x[3 * (size_t) i];
+  r.y = x[3 * (size_t) i + 1];
+  r.z = x[3 * (size_t) i + 2];
+  r.t = (long long) type[i] - 1;
+  xt[i] = r;
+}
+
+// Per-warp shared-memory carve-up.  Row layout of the 32-slot staging area (doubles, odd stride so that
+// "same row, 32 slots" and "same slot, many rows" accesses are both bank-conflict free):
+//   [0,P) ux^p  [P,2P) uy^p  [2P,3P) uz^p  [3P,+R) f_mu  [+R) f'_mu  [+R) f_mu/d  [+3) ux,uy,uz  [+R) P_mu (grade)
+struct WarpSmem {
+  double *m, *g, *stage, *pr, *cand;
+  int *pj, *pt;
+};
+
+struct Layout {
+  int srow, o_fval, o_fder, o_fvi, o_u, o_pm;
+  size_t cta_bytes, warp_bytes;
+};
+
+__host__ __device__ inline Layout make_layout(int S, int R, int B, int K, int M, int P, int Q, bool grade)
+{
+  Layout L;
+  L.o_fval = 3 * P;
+  L.o_fder = L.o_fval + R;
+  L.o_fvi = L.o_fder + R;
+  L.o_u = L.o_fvi + R;
+  L.o_pm = L.o_u + 3;
+  int n = L.o_pm + (grade ? R : 0);
+  L.srow = n | 1;
+  size_t cta = (size_t) S * S * R * B * 8 + (size_t) K * 4;
+  L.cta_bytes = (cta + 15) & ~(size_t) 15;
+  size_t w = (size_t) (2 * M + 32 * L.srow + 3 * PEND + (grade ? Q : 0)) * 8 + (size_t) 2 * PEND * 4;
+  L.warp_bytes = (w + 15) & ~(size_t) 15;
+  return L;
+}
+
+struct Pending {
+  int cnt;
+};
+
+// ------------------------------------------------------------------------------------------------
+// staging: lane n < nb expands pending neighbor n into its row
+__device__ __forceinline__ void stage_rows(const DevPotential &pot, const Layout &L, const double *s_radial,
+                                           const WarpSmem &ws, int itype, int nb, int lane, bool grade)
+{
+  if (lane < nb) {
+    double *row = ws.stage + (size_t) lane * L.srow;
+    const double r0 = ws.pr[lane], r1 = ws.pr[PEND + lane], r2 = ws.pr[2 * PEND + lane];
+    const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2));
+    const double d = sqrt(rsq);
+    const double invd = 1.0 / d;
+    const double ux = r0 * invd, uy = r1 * invd, uz = r2 * invd;
+    const int P = pot.P, R = pot.R, B = pot.B;
+    row[0] = 1.0;
+    row[P] = 1.0;
+    row[2 * P] = 1.0;
+    for (int p = 1; p < P; p++) {
+      row[p] = row[p - 1] * ux;
+      row[P + p] = row[P + p - 1] * uy;
+      row[2 * P + p] = row[2 * P + p - 1] * uz;
+    }
+    row[L.o_u] = ux;
+    row[L.o_u + 1] = uy;
+    row[L.o_u + 2] = uz;
+    // Chebyshev recurrence, contracted with the radial coefficients as it is generated
+    const double t = d - pot.rmax;
+    const double ksi = (2 * d - (pot.rmin + pot.rmax)) / (pot.rmax - pot.rmin);
+    const double mult = 2.0 / (pot.rmax - pot.rmin);
+    double v_prev = 0, v_cur = pot.scaling * (1 * t * t);
+    double d_prev = 0, d_cur = pot.scaling * 2 * t;
+    for (int mu = 0; mu < R; mu++) {
+      row[L.o_fval + mu] = 0.0;
+      row[L.o_fder + mu] = 0.0;
+    }
+    const double *c = s_radial + (size_t) (itype * pot.S + ws.pt[lane]) * R * B;
+    for (int ri = 0; ri < B; ri++) {
+      if (ri == 1) {
+        v_prev = v_cur;
+        d_prev = d_cur;
+        v_cur = pot.scaling * (ksi * t * t);
+        d_cur = pot.scaling * (mult * t * t + 2 * ksi * t);
+      } else if (ri > 1) {
+        const double vn = 2 * ksi * v_cur - v_prev;
+        const double dn = 2 * (mult * v_cur + ksi * d_cur) - d_prev;
+        v_prev = v_cur;
+        d_prev = d_cur;
+        v_cur = vn;
+        d_cur = dn;
+      }
+      for (int mu = 0; mu < R; mu++) {
+        const double cc = c[mu * B + ri];
+        row[L.o_fval + mu] += cc * v_cur;
+        row[L.o_fder + mu] += cc * d_cur;
+      }
+    }
+    for (int mu = 0; mu < R; mu++) {
+      row[L.o_fvi + mu] = row[L.o_fval + mu] * invd;
+      if (grade) row[L.o_pm + mu] = 0.0;
+    }
+  }
+  __syncwarp();
+}
+
+// forward: lane owns basic moments k = lane, lane+32, ...; accumulates the staged neighbors
+__device__ __forceinline__ void forward_batch(const DevPotential &pot, const Layout &L, const uint32_t *s_basic,
+                                              const WarpSmem &ws, int nb, int lane)
+{
+  const int P = pot.P;
+  for (int k = lane; k < pot.K; k += 32) {
+    const uint32_t e = s_basic[k];
+    const int mu = e & 0xff, a = (e >> 8) & 0xff, b = (e >> 16) & 0xff, c = e >> 24;
+    double acc = 0.0;
+    for (int n = 0; n < nb; n++) {
+      const double *row = ws.stage + (size_t) n * L.srow;
+      acc += row[L.o_fval + mu] * (row[a] * row[P + b] * row[2 * P + c]);
+    }
+    ws.m[k] += acc;
+  }
+  __syncwarp();
+}
+
+struct AtomAcc {
+  double fx, fy, fz;       // force on the centre atom (per-lane partial)
+  double v[6];             // virial (per-lane partial)
+};
+
+// backward: lane owns staged neighbor n; loops over all basic moments
+template <bool GRADE>
+__device__ __forceinline__ void backward_batch(const DevPotential &pot, const Layout &L, const uint32_t *s_basic,
+                                               const WarpSmem &ws, const SiteArgs &a, int itype, int nb, int lane,
+                                               AtomAcc &acc)
+{
+  const int P = pot.P;
+  double Fx = 0, Fy = 0, Fz = 0;
+  if (lane < nb) {
+    double *row = ws.stage + (size_t) lane * L.srow;
+    double Sx = 0, Wx = 0, Wy = 0, Wz = 0;
+    for (int k = 0; k < pot.K; k++) {
+      const uint32_t e = s_basic[k];
+      const int mu = e & 0xff, qa = (e >> 8) & 0xff, qb = (e >> 16) & 0xff, qc = e >> 24;
+      const double gk = ws.g[k];
+      const double px = row[qa], py = row[P + qb], pz = row[2 * P + qc];
+      const double mono = px * py * pz;
+      const double fvi = row[L.o_fvi + mu];
+      const double gm = gk * mono;
+      Sx += gm * (row[L.o_fder + mu] - (double) (qa + qb + qc) * fvi);
+      if (GRADE) row[L.o_pm + mu] += gm;
+      const double gf = gk * fvi;
+      if (qa) Wx += gf * (double) qa * (row[qa - 1] * py * pz);
+      if (qb) Wy += gf * (double) qb * (px * row[P + qb - 1] * pz);
+      if (qc) Wz += gf * (double) qc * (px * py * row[2 * P + qc - 1]);
+    }
+    Fx = row[L.o_u] * Sx + Wx;
+    Fy = row[L.o_u + 1] * Sx + Wy;
+    Fz = row[L.o_u + 2] * Sx + Wz;
+    const int j = ws.pj[lane];
+    atomicAdd(&a.f[3 * (size_t) j], -Fx);
+    atomicAdd(&a.f[3 * (size_t) j + 1], -Fy);
+    atomicAdd(&a.f[3 * (size_t) j + 2], -Fz);
+    acc.fx += Fx;
+    acc.fy += Fy;
+    acc.fz += Fz;
+    if (a.vflag_any) {
+      const double r0 = ws.pr[lane], r1 = ws.pr[PEND + lane], r2 = ws.pr[2 * PEND + lane];
+      acc.v[0] -= Fx * r0;
+      acc.v[1] -= Fy * r1;
+      acc.v[2] -= Fz * r2;
+      acc.v[3] -= (Fx * r1 + Fy * r0) / 2;
+      acc.v[4] -= (Fx * r2 + Fz * r0) / 2;
+      acc.v[5] -= (Fy * r2 + Fz * r1) / 2;
+    }
+  }
+  if (GRADE) {
+    // radial block of the candidate vector: b[(it*S+jt)*RB + mu*B + ri] += phi_ri(d_n) * P_mu(u_n)
+    const int R = pot.R, B = pot.B;
+    double t = 0, ksi = 0, mult = 0;
+    int jt = -1;
+    const double *row = ws.stage + (size_t) lane * L.srow;
+    if (lane < nb) {
+      const double r0 = ws.pr[lane], r1 = ws.pr[PEND + lane], r2 = ws.pr[2 * PEND + lane];
+      const double d = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2)));
+      t = d - pot.rmax;
+      ksi = (2 * d - (pot.rmin + pot.rmax)) / (pot.rmax - pot.rmin);
+      mult = 2.0 / (pot.rmax - pot.rmin);
+      jt = ws.pt[lane];
+    }
+    (void) mult;
+    double v_prev = 0, v_cur = pot.scaling * (1 * t * t);
+    for (int ri = 0; ri < B; ri++) {
+      if (ri == 1) {
+        v_prev = v_cur;
+        v_cur = pot.scaling * (ksi * t * t);
+      } else if (ri > 1) {
+        const double vn = 2 * ksi * v_cur - v_prev;
+        v_prev = v_cur;
+        v_cur = vn;
+      }
+      for (int s = 0; s < pot.S; s++)
+        for (int mu = 0; mu < R; mu++) {
+          double c = (lane < nb && jt == s) ? v_cur * row[L.o_pm + mu] : 0.0;
+          c = warp_sum(c);
+          if (lane == 0) ws.cand[(size_t) (itype * pot.S + s) * R * B + mu * B + ri] += c;
+        }
+    }
+  }
+  __syncwarp();
+}
+
+// contraction program, forward and reverse (level-ordered gather lists, lane = node of the group)
+__device__ __forceinline__ void run_pass_forward(const DevPass &ps, int K, double *m, int lane)
+{
+  for (int lv = 0; lv < ps.nlevels; lv++) {
+    const int g0 = ps.level_group_begin[lv], g1 = ps.level_group_begin[lv + 1];
+    for (int g = g0; g < g1; g++) {
+      const int node = ps.node[g * 32 + lane];
+      const int nt = ps.nterms[g * 32 + lane];
+      const uint2 *tp = ps.terms + (size_t) ps.group_term_base[g] * 32 + lane;
+      if (node >= 0) {
+        double acc = node < K ? m[node] : 0.0;
+        for (int t = 0; t < nt; t++) {
+          const uint2 raw = tp[(size_t) t * 32];
+          const double mult = (double) __uint_as_float(raw.y);
+          acc += mult * m[raw.x & 0xffff] * m[raw.x >> 16];
+        }
+        m[node] = acc;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ void run_pass_reverse(const DevPass &ps, const double *m, double *g, int lane)
+{
+  for (int lv = 0; lv < ps.nlevels; lv++) {
+    const int g0 = ps.level_group_begin[lv], g1 = ps.level_group_begin[lv + 1];
+    for (int gi = g0; gi < g1; gi++) {
+      const int node = ps.node[gi * 32 + lane];
+      const int nt = ps.nterms[gi * 32 + lane];
+      const uint2 *tp = ps.terms + (size_t) ps.group_term_base[gi] * 32 + lane;
+      if (node >= 0) {
+        double acc = g[node];
+        for (int t = 0; t < nt; t++) {
+          const uint2 raw = tp[(size_t) t * 32];
+          const double mult = (double) __uint_as_float(raw.y);
+          acc += g[raw.x & 0xffff] * mult * m[raw.x >> 16];
+        }
+        g[node] = acc;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// gather + mask + compaction into the pending buffer; full batches are handed to PHASE's consumer
+template <int PHASE, bool GRADE>
+__device__ __forceinline__ void stream_neighbors(const DevPotential &pot, const Layout &L, const double *s_radial,
+                                                 const uint32_t *s_basic, const WarpSmem &ws, const SiteArgs &a,
+                                                 int i, int itype, double xi0, double xi1, double xi2, int lane,
+                                                 AtomAcc &acc)
+{
+  const int jnum = a.numneigh[i];
+  const long long row0 = a.neigh_offsets ? a.neigh_offsets[i] : (long long) i * a.stride_i;
+  int cnt = 0;
+  for (int base = 0; base < jnum; base += 32) {
+    const int jj = base + lane;
+    bool within = false;
+    int j = 0, jt = 0;
+    double r0 = 0, r1 = 0, r2 = 0;
+    if (jj < jnum) {
+      const long long at = row0 + (long long) jj * a.stride_jj;
+      j = a.neighbors[at] & a.neighmask;
+      const double2 *rec = reinterpret_cast<const double2 *>(a.xt + j);
+      const double2 xy = __ldg(rec);
+      const double2 zt = __ldg(rec + 1);
+      jt = (int) __double_as_longlong(zt.y);
+      r0 = xy.x - xi0;
+      r1 = xy.y - xi1;
+      r2 = zt.x - xi2;
+      // separately rounded, left to right, exactly pair_mtp.cpp:121-123 (no FMA contraction)
+      const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2));
+      within = !(rsq > pot.cutsq);
+      if (jt < 0 || jt >= pot.S) {    // pair_mtp.cpp:116-118
+        atomicOr(a.status, 1);
+        within = false;
+      }
+      if (PHASE == 0 && a.within) a.within[at] = within ? 1 : 0;
+    }
+    const unsigned bal = __ballot_sync(FULL, within);
+    if (within) {
+      const int slot = cnt + __popc(bal & ((1u << lane) - 1u));
+      ws.pr[slot] = r0;
+      ws.pr[PEND + slot] = r1;
+      ws.pr[2 * PEND + slot] = r2;
+      ws.pj[slot] = j;
+      ws.pt[slot] = jt;
+    }
+    cnt += __popc(bal);
+    __syncwarp();
+    if (cnt >= 32) {
+      stage_rows(pot, L, s_radial, ws, itype, 32, lane, GRADE && PHASE == 1);
+      if (PHASE == 0) forward_batch(pot, L, s_basic, ws, 32, lane);
+      else
+        backward_batch<GRADE>(pot, L, s_basic, ws, a, itype, 32, lane, acc);
+      // move the remainder (< 32 entries) to the front
+      const int rem = cnt - 32;
+      double t0 = 0, t1 = 0, t2 = 0;
+      int tj = 0, tt = 0;
+      if (lane < rem) {
+        t0 = ws.pr[32 + lane];
+        t1 = ws.pr[PEND + 32 + lane];
+        t2 = ws.pr[2 * PEND + 32 + lane];
+        tj = ws.pj[32 + lane];
+        tt = ws.pt[32 + lane];
+      }
+      __syncwarp();
+      if (lane < rem) {
+        ws.pr[lane] = t0;
+        ws.pr[PEND + lane] = t1;
+        ws.pr[2 * PEND + lane] = t2;
+        ws.pj[lane] = tj;
+        ws.pt[lane] = tt;
+      }
+      cnt = rem;
+      __syncwarp();
+    }
+  }
+  if (cnt > 0) {
+    stage_rows(pot, L, s_radial, ws, itype, cnt, lane, GRADE && PHASE == 1);
+    if (PHASE == 0) forward_batch(pot, L, s_basic, ws, cnt, lane);
+    else
+      backward_batch<GRADE>(pot, L, s_basic, ws, a, itype, cnt, lane, acc);
+  }
+}
+
+template <bool GRADE>
+__global__ void __launch_bounds__(256) mtp_site_kernel(DevPotential pot, SiteArgs a, int warps_per_cta)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Layout L = make_layout(pot.S, pot.R, pot.B, pot.K, pot.M, pot.P, pot.Q, GRADE);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  double *s_radial = reinterpret_cast<double *>(smem);
+  uint32_t *s_basic = reinterpret_cast<uint32_t *>(smem + (size_t) pot.S * pot.S * pot.R * pot.B * 8);
+  for (int t = threadIdx.x; t < pot.S * pot.S * pot.R * pot.B; t += blockDim.x) s_radial[t] = pot.radial[t];
+  for (int t = threadIdx.x; t < pot.K; t += blockDim.x) s_basic[t] = pot.basic[t];
+
+  WarpSmem ws;
+  {
+    unsigned char *base = smem + L.cta_bytes + (size_t) warp * L.warp_bytes;
+    double *d = reinterpret_cast<double *>(base);
+    ws.m = d;
+    ws.g = ws.m + pot.M;
+    ws.stage = ws.g + pot.M;
+    ws.pr = ws.stage + 32 * L.srow;
+    ws.cand = ws.pr + 3 * PEND;
+    ws.pj = reinterpret_cast<int *>(ws.cand + (GRADE ? pot.Q : 0));
+    ws.pt = ws.pj + PEND;
+  }
+  __syncthreads();
+
+  double e_warp = 0.0, grade_warp = 0.0;
+  double v_warp[6] = {0, 0, 0, 0, 0, 0};
+  const int total_warps = gridDim.x * warps_per_cta;
+  const int radial_count = pot.S * pot.S * pot.R * pot.B;
+
+  for (int ii = blockIdx.x * warps_per_cta + warp; ii < a.inum; ii += total_warps) {
+    const int i = a.ilist ? a.ilist[a.first_ii + ii] : a.first_ii + ii;
+    const double2 *rec = reinterpret_cast<const double2 *>(a.xt + i);
+    const double2 xy = __ldg(rec);
+    const double2 zt = __ldg(rec + 1);
+    int itype = (int) __double_as_longlong(zt.y);
+    if (itype < 0 || itype >= pot.S) {    // pair_mtp.cpp:91-93
+      if (lane == 0) atomicOr(a.status, 1);
+      itype = 0;
+    }
+    for (int k = lane; k < pot.K; k += 32) ws.m[k] = 0.0;
+    if (GRADE)
+      for (int q = lane; q < pot.Q; q += 32) ws.cand[q] = 0.0;
+    __syncwarp();
+
+    AtomAcc acc;
+    acc.fx = acc.fy = acc.fz = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; c++) acc.v[c] = 0.0;
+
+    // ---- phase 1: basic moments
+    stream_neighbors<0, GRADE>(pot, L, s_radial, s_basic, ws, a, i, itype, xy.x, xy.y, zt.x, lane, acc);
+
+    // ---- contraction program forward, energy, adjoint seed, reverse
+    run_pass_forward(pot.fwd, pot.K, ws.m, lane);
+    if (a.eflag_global || a.eflag_atom) {
+      double e = 0.0;
+      for (int s = lane; s < pot.A; s += 32) e += pot.lin[s] * ws.m[pot.map[s]];
+      e = warp_sum(e) + pot.species[itype];
+      if (a.eflag_atom && lane == 0) a.eatom[i] = e;
+      if (a.eflag_global) e_warp += e;
+    }
+    for (int n = lane; n < pot.M; n += 32) ws.g[n] = pot.ginit[n];
+    __syncwarp();
+    run_pass_reverse(pot.rev, ws.m, ws.g, lane);
+
+    // ---- phase 2: forces, virial (and the radial block of the candidate vector)
+    stream_neighbors<1, GRADE>(pot, L, s_radial, s_basic, ws, a, i, itype, xy.x, xy.y, zt.x, lane, acc);
+
+    const double fx = warp_sum(acc.fx), fy = warp_sum(acc.fy), fz = warp_sum(acc.fz);
+    if (lane == 0) {
+      atomicAdd(&a.f[3 * (size_t) i], fx);
+      atomicAdd(&a.f[3 * (size_t) i + 1], fy);
+      atomicAdd(&a.f[3 * (size_t) i + 2], fz);
+    }
+    if (a.vflag_any) {
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        const double vc = warp_sum(acc.v[c]);
+        v_warp[c] += vc;
+        if (a.vflag_atom && lane == 0) a.vatom[6 * (size_t) i + c] += vc;
+      }
+    }
+    if (GRADE) {
+      // species one-hot and linear block (pair_mtp_extrapolation.cpp:235-252), then hand the row over
+      if (lane == 0) ws.cand[radial_count + itype] += 1.0;
+      for (int s = lane; s < pot.A; s += 32) ws.cand[radial_count + pot.S + s] = ws.m[pot.map[s]];
+      __syncwarp();
+      double *dst = a.cand_rows + (size_t) ii * a.cand_ld;
+      for (int q = lane; q < a.cand_ld; q += 32) dst[q] = q < pot.Q ? ws.cand[q] : 0.0;
+    }
+    __syncwarp();
+  }
+  (void) grade_warp;
+
+  // ---- per-CTA partials, fixed order -> deterministic energy / virial
+  __shared__ double s_part[8][8];
+  if (lane == 0) {
+    s_part[warp][0] = e_warp;
+#pragma unroll
+    for (int c = 0; c < 6; c++) s_part[warp][1 + c] = v_warp[c];
+    s_part[warp][7] = 0.0;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double s = 0.0;
+    for (int w = 0; w < warps_per_cta; w++) s += s_part[w][threadIdx.x];
+    a.partials[(size_t) blockIdx.x * 8 + threadIdx.x] = s;
+  }
+}
+
+// sums the per-CTA partials in block order; ev[0..6] (+)= sum, ev[7] untouched here
+__global__ void finalize_ev_kernel(const double *partials, int nblocks, double *ev, int accumulate)
+{
+  const int c = threadIdx.x;
+  if (c >= 7) return;
+  double s = accumulate ? ev[c] : 0.0;
+  for (int b = 0; b < nblocks; b++) s += partials[(size_t) b * 8 + c];
+  ev[c] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Extrapolation grade: G = Bmat[n x Q] . Ainv^T, grade[row] = max_col |G|  (pair_mtp_extrapolation.cpp:347-358),
+// batched over the atoms of a chunk on the FP64 tensor cores: mma.sync.m8n8k4.f64 (DMMA.8x8x4 is the only native
+// FP64 MMA shape on sm_100a).  One warp owns 8 candidate rows and sweeps all column tiles of Ainv^T; |.| row-max
+// epilogue in registers, G is never written.
+//   A fragment (8x4, row-major):  a  = Bmat[row0 + lane/4][k0 + lane%4]
+//   B fragment (4x8, col-major):  b  = Ainv[col0 + lane/4][k0 + lane%4]        (B[k][n] = Ainv^T[k][n] = Ainv[n][k])
+//   C fragment: c0,c1 = G[row0 + lane/4][col0 + 2*(lane%4) + {0,1}]
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+constexpr int GRADE_WARPS = 4;      // warps per CTA; each warp owns 8 candidate rows
+constexpr int GRADE_COLS = 32;      // output columns (rows of Ainv) per pass = 4 DMMA column tiles
+constexpr int GRADE_KC = 64;        // k-extent staged in shared memory per step
+constexpr int GRADE_LDS = GRADE_KC + 4;    // smem row stride: 8 rows x 4 doubles land in distinct banks
+
+__global__ void __launch_bounds__(GRADE_WARPS * 32)
+grade_dmma_kernel(const double *__restrict__ bmat, int nrows, int ld /*Qpad, multiple of 8*/,
+                  const double *__restrict__ ainv_pad /*[Qpad][Qpad]*/, const int *__restrict__ ilist, int first_ii,
+                  double *__restrict__ grades, double *__restrict__ block_max)
+{
+  __shared__ __align__(16) double s_a[GRADE_WARPS * 8 * GRADE_LDS];
+  __shared__ __align__(16) double s_b[GRADE_COLS * GRADE_LDS];
+  __shared__ double s_w[GRADE_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row_base = blockIdx.x * GRADE_WARPS * 8;
+  const int ar = warp * 8 + (lane >> 2), kk = lane & 3;
+  double rmax0 = 0.0;
+  for (int col0 = 0; col0 < ld; col0 += GRADE_COLS) {
+    const int ncols = min(GRADE_COLS, ld - col0);
+    double acc[GRADE_COLS / 8][2];
+#pragma unroll
+    for (int ct = 0; ct < GRADE_COLS / 8; ct++) acc[ct][0] = acc[ct][1] = 0.0;
+    for (int kc = 0; kc < ld; kc += GRADE_KC) {
+      const int nk = min(GRADE_KC, ld - kc);    // multiple of 8
+      __syncthreads();
+      for (int t = threadIdx.x; t < GRADE_WARPS * 8 * nk; t += blockDim.x) {
+        const int r = t / nk, c = t - r * nk;
+        const int gr = row_base + r;
+        s_a[r * GRADE_LDS + c] = gr < nrows ? bmat[(size_t) gr * ld + kc + c] : 0.0;
+      }
+      for (int t = threadIdx.x; t < GRADE_COLS * nk; t += blockDim.x) {
+        const int r = t / nk, c = t - r * nk;
+        s_b[r * GRADE_LDS + c] = r < ncols ? ainv_pad[(size_t) (col0 + r) * ld + kc + c] : 0.0;
+      }
+      __syncthreads();
+      const double *pa = s_a + ar * GRADE_LDS + kk;
+      const double *pb = s_b + (lane >> 2) * GRADE_LDS + kk;
+      for (int k0 = 0; k0 < nk; k0 += 4) {
+        const double av = pa[k0];
+#pragma unroll
+        for (int ct = 0; ct < GRADE_COLS / 8; ct++) dmma884(acc[ct][0], acc[ct][1], av, pb[ct * 8 * GRADE_LDS + k0]);
+      }
+    }
+#pragma unroll
+    for (int ct = 0; ct < GRADE_COLS / 8; ct++) rmax0 = fmax(rmax0, fmax(fabs(acc[ct][0]), fabs(acc[ct][1])));
+  }
+  // reduce over the 4 lanes that share a row
+  rmax0 = fmax(rmax0, __shfl_xor_sync(FULL, rmax0, 1));
+  rmax0 = fmax(rmax0, __shfl_xor_sync(FULL, rmax0, 2));
+  const int grow = row_base + ar;
+  if (grades && kk == 0 && grow < nrows) {
+    const int i = ilist ? ilist[first_ii + grow] : first_ii + grow;
+    grades[i] = rmax0;
+  }
+  double wmax = (grow < nrows) ? rmax0 : 0.0;
+  wmax = warp_max(wmax);
+  if (lane == 0) s_w[warp] = wmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int w = 0; w < GRADE_WARPS; w++) m = fmax(m, s_w[w]);
+    block_max[blockIdx.x] = m;
+  }
+}
+
+__global__ void finalize_max_kernel(const double *block_max, int n, double *ev7, int accumulate)
+{
+  double m = accumulate ? *ev7 : 0.0;
+  for (int b = threadIdx.x; b < n; b += 32) m = fmax(m, block_max[b]);
+  m = warp_max(m);
+  if (threadIdx.x == 0) *ev7 = m;
+}
+
+// configuration mode: column sums of the candidate rows (pair_mtp_extrapolation.cpp:97-98,240,252,327)
+__global__ void cand_colsum_kernel(const double *bmat, int nrows, int ld, int q, double *cand, int accumulate)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= q) return;
+  double s = accumulate ? cand[c] : 0.0;
+  for (int r = 0; r < nrows; r++) s += bmat[(size_t) r * ld + c];
+  cand[c] = s;
+}
+
+// cfg grade: max_i |Ainv[i,:] . b| / natoms  (pair_mtp_extrapolation.cpp:366-376)
+__global__ void cfg_grade_kernel(const double *ainv_pad, int ld, int q, const double *cand, double inv_natoms,
+                                 double *ev7)
+{
+  __shared__ double s_w[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double best = 0.0;
+  for (int i = warp; i < q; i += nw) {
+    double acc = 0.0;
+    for (int j = lane; j < q; j += 32) acc += cand[j] * ainv_pad[(size_t) i * ld + j];
+    acc = warp_sum(acc);
+    best = fmax(best, fabs(acc));
+  }
+  if (lane == 0) s_w[warp] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int w = 0; w < nw; w++) m = fmax(m, s_w[w]);
+    *ev7 = m * inv_natoms;
+  }
+}
+
+// ---- halo helpers ---------------------------------------------------------------------------------
+__global__ void halo_pack_x_kernel(const double *__restrict__ x, const int *__restrict__ sendlist, int n, double sx,
+                                   double sy, double sz, double *__restrict__ out)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int i = sendlist[k];
+  out[3 * (size_t) k] = x[3 * (size_t) i] + sx;
+  out[3 * (size_t) k + 1] = x[3 * (size_t) i + 1] + sy;
+  out[3 * (size_t) k + 2] = x[3 * (size_t) i + 2] + sz;
+}
+
+__global__ void halo_unpack_add_f_kernel(double *__restrict__ f, const int *__restrict__ sendlist, int n,
+                                         const double *__restrict__ buf)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int i = sendlist[k];
+  // a send list may name the same owned atom more than once (several periodic images) -> atomic
+  atomicAdd(&f[3 * (size_t) i], buf[3 * (size_t) k]);
+  atomicAdd(&f[3 * (size_t) i + 1], buf[3 * (size_t) k + 1]);
+  atomicAdd(&f[3 * (size_t) i + 2], buf[3 * (size_t) k + 2]);
+}
+
+// ---- FP64 roofs ---------------------------------------------------------------------------------------
+__global__ void dfma_peak_kernel(double *out, int iters, double a, double b)
+{
+  double r[8];
+#pragma unroll
+  for (int u = 0; u < 8; u++) r[u] = a + u + threadIdx.x;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) r[u] = fma(r[u], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int u = 0; u < 8; u++) s += r[u];
+  if (s == 12345.678) out[0] = s;
+}
+
+__global__ void dmma_peak_kernel(double *out, int iters, double a, double b)
+{
+  double c[8][2];
+#pragma unroll
+  for (int u = 0; u < 8; u++) c[u][0] = c[u][1] = threadIdx.x * 1e-3;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) dmma884(c[u][0], c[u][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int u = 0; u < 8; u++) s += c[u][0] + c[u][1];
+  if (s == 12345.678) out[0] = s;
+}
+
+}    // namespace mtpb200

@@ -1,0 +1,457 @@
+// MLIP-3 .almtp parser + contraction-program compiler (host, plain C++17).
+// Grammar and messages follow the reference's loader so that a file the reference accepts loads to the
+// same tables and a file it rejects is rejected with the same text:
+//   PairMTP::read_file                  pair_mtp.cpp:345-570
+//   RadialMTPBasis::ReadBasisProperties mtp_radial_basis.cpp:59-102
+//   PairMTPExtrapolation::read_file     pair_mtp_extrapolation.cpp:545-612
+#include "mtp_potential.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+
+namespace mtpb200 {
+
+namespace {
+
+const char *const kBlank = " \t\r\n\f";    // LAMMPS TOKENIZER_DEFAULT_SEPARATORS
+
+struct Tokens {
+  std::vector<std::string> tok;
+  size_t pos = 0;
+  Tokens(const std::string &line, const std::string &seps)
+  {
+    size_t p = 0;
+    while ((p = line.find_first_not_of(seps, p)) != std::string::npos) {
+      size_t e = line.find_first_of(seps, p);
+      if (e == std::string::npos) e = line.size();
+      tok.emplace_back(line.substr(p, e - p));
+      p = e;
+    }
+  }
+  bool more() const { return pos < tok.size(); }
+  std::string word()
+  {
+    if (!more()) throw std::out_of_range("No more tokens");
+    return tok[pos++];
+  }
+  int integer()
+  {
+    std::string t = word();
+    char *end = nullptr;
+    long v = strtol(t.c_str(), &end, 10);
+    if (end == t.c_str() || *end) throw std::runtime_error("Not a valid integer number: '" + t + "'");
+    return (int) v;
+  }
+  double real()
+  {
+    std::string t = word();
+    char *end = nullptr;
+    double v = strtod(t.c_str(), &end);
+    if (end == t.c_str() || *end) throw std::runtime_error("Not a valid floating-point number: '" + t + "'");
+    return v;
+  }
+};
+
+// Line cursor over the whole file image.  Like LAMMPS's TextFileReader it returns the next physical line
+// that still holds at least one word after (optionally) cutting a '#' comment; blank lines are skipped.
+struct LineCursor {
+  const std::string &buf;
+  size_t pos = 0;
+  explicit LineCursor(const std::string &b) : buf(b) {}
+  bool raw_line(std::string &out)
+  {
+    if (pos >= buf.size()) return false;
+    size_t e = buf.find('\n', pos);
+    e = (e == std::string::npos) ? buf.size() : e + 1;
+    out.assign(buf, pos, e - pos);
+    pos = e;
+    return true;
+  }
+  bool next(std::string &out, bool strip_comments = true)
+  {
+    std::string ln;
+    while (raw_line(ln)) {
+      if (strip_comments) {
+        size_t h = ln.find('#');
+        if (h != std::string::npos) ln.erase(h);
+      }
+      if (ln.find_first_not_of(kBlank) != std::string::npos) {
+        out.swap(ln);
+        return true;
+      }
+    }
+    return false;
+  }
+  std::string must(const char *what_if_eof)
+  {
+    std::string ln;
+    if (!next(ln)) throw std::runtime_error(what_if_eof);
+    return ln;
+  }
+};
+
+std::string read_file_image(const std::string &path)
+{
+  FILE *fp = fopen(path.c_str(), "rb");
+  if (!fp) {
+    const char *dir = getenv("LAMMPS_POTENTIALS");    // utils::open_potential also searches this folder
+    if (dir) fp = fopen((std::string(dir) + "/" + path).c_str(), "rb");
+  }
+  if (!fp) throw std::runtime_error("Cannot open potential file " + path);
+  std::string img;
+  char chunk[1 << 16];
+  size_t n;
+  while ((n = fread(chunk, 1, sizeof(chunk), fp)) > 0) img.append(chunk, n);
+  fclose(fp);
+  return img;
+}
+
+}    // namespace
+
+void parse_almtp(const std::string &path, bool want_selection_state, Potential &p)
+{
+  const std::string img = read_file_image(path);
+  LineCursor cur(img);
+  const std::string seps = std::string(kBlank) + "=, ";
+  const std::string brace = seps + "{},";
+  const char *eof = "Error reading MTP file. Unexpected end of file.";
+
+  {
+    Tokens t(cur.must("Only MTP potential files are accepted."), seps);
+    if (t.word() != "MTP") throw std::runtime_error("Only MTP potential files are accepted.");
+  }
+  if (cur.must("MTP file must have version \"1.1.0\"") != "version = 1.1.0\n")
+    throw std::runtime_error("MTP file must have version \"1.1.0\"");
+
+  std::string line = cur.must(eof);
+  Tokens t(line, seps);
+  std::string key = t.word();
+  auto advance = [&]() {
+    line = cur.must(eof);
+    t = Tokens(line, seps);
+    key = t.word();
+  };
+
+  if (key == "potential_name") {
+    p.potential_name = t.more() ? t.word() : "";
+    advance();
+  }
+  if (key == "scaling") {
+    p.scaling = t.real();
+    advance();
+  } else
+    p.scaling = 1;
+  char fmtbuf[64];
+  snprintf(fmtbuf, sizeof(fmtbuf), "The scaling is : %.2e.\n", p.scaling);
+  p.log += fmtbuf;
+
+  if (key != "species_count") throw std::runtime_error("Error reading MTP file. Species count not found.");
+  p.species_count = t.integer();
+  p.log += "There are " + std::to_string(p.species_count) + " species.\n";
+  const int S = p.species_count;
+  if (S < 1) throw std::runtime_error("Error reading MTP file. Species count not found.");
+  p.setflag.assign((size_t) (S + 1) * (S + 1), 0);
+
+  advance();
+  if (key == "potential_tag") {
+    p.potential_tag = t.more() ? t.word() : "";
+    advance();
+  }
+
+  if (key != "radial_basis_type")
+    throw std::runtime_error("Error reading MTP file. No radial basis set type is specified.");
+  const std::string rb_type = t.word();
+  if (rb_type != "RBChebyshev")
+    throw std::runtime_error("Error reading MTP file. The specified radial basis set type, " + rb_type +
+                             ", was not found..");
+  // ---- basis properties block (mtp_radial_basis.cpp:59-102).  A "scaling" line placed here (MLIP-2
+  // style) is read and then overridden by the top-level value, as in the reference (pair_mtp.cpp:416).
+  advance();
+  if (key == "scaling") {
+    (void) t.real();
+    advance();
+  }
+  if (key != "min_val" && key != "min_dist")
+    throw std::runtime_error("Error in reading MTP file. Cannot read lower cutoff.");
+  p.min_cutoff = t.real();
+  advance();
+  if (key != "max_val" && key != "max_dist")
+    throw std::runtime_error("Error in reading MTP file. Cannot read upper cutoff.");
+  p.max_cutoff = t.real();
+  advance();
+  if (key != "radial_basis_size")
+    throw std::runtime_error("Error in reading MTP file. Cannot read radial basis set size.");
+  p.radial_basis_size = t.integer();
+  advance();
+  if (key != "radial_funcs_count")
+    throw std::runtime_error("Error in reading MTP file. Cannot read radial function count.");
+  p.radial_func_count = t.integer();
+  advance();
+  if (key != "radial_coeffs") {
+    if (key == "magnetic_basis_type") throw std::runtime_error("Magnetic basis is currently not supported.");
+    throw std::runtime_error("Error in reading MTP file. Cannot read radial coeffs count.");
+  }
+  const int R = p.radial_func_count, B = p.radial_basis_size;
+  if (R < 1 || B < 1) throw std::runtime_error("Error in reading MTP file. Cannot read radial function count.");
+  p.radial_basis_coeffs.assign((size_t) S * S * R * B, 0.0);
+  for (int n = 0; n < S * S; n++) {
+    Tokens hd(cur.must(eof), seps + "-");
+    const int t1 = hd.integer(), t2 = hd.integer();
+    if (t1 < 0 || t1 >= S || t2 < 0 || t2 >= S)
+      throw std::runtime_error("Error reading MTP file. Species pair out of range in radial_coeffs.");
+    p.setflag[(size_t) (t1 + 1) * (S + 1) + (t2 + 1)] = 1;
+    const size_t off = (size_t) (t1 * S + t2) * R * B;
+    for (int mu = 0; mu < R; mu++) {
+      Tokens row(cur.must(eof), brace);
+      for (int k = 0; k < B; k++) p.radial_basis_coeffs[off + (size_t) mu * B + k] = row.real();
+    }
+  }
+
+  advance();
+  if (key != "alpha_moments_count") throw std::runtime_error("Error reading MTP file. Alpha moment count not found.");
+  p.alpha_moment_count = t.integer();
+  advance();
+  if (key != "alpha_index_basic_count")
+    throw std::runtime_error("Error reading MTP file. Alpha moment count not found.");
+  p.alpha_index_basic_count = t.integer();
+  {
+    Tokens b(cur.must(eof), brace);
+    if (b.word() != "alpha_index_basic") throw std::runtime_error("Error reading MTP file. Alpha index basic not found.");
+    p.alpha_index_basic.resize((size_t) p.alpha_index_basic_count * 4);
+    for (auto &v : p.alpha_index_basic) v = b.integer();
+  }
+  advance();
+  if (key != "alpha_index_times_count")
+    throw std::runtime_error("Error reading MTP file. Alpha index times count not found.");
+  p.alpha_index_times_count = t.integer();
+  {
+    Tokens b(cur.must(eof), brace);
+    if (b.word() != "alpha_index_times") throw std::runtime_error("Error reading MTP file. Alpha index times not found.");
+    p.alpha_index_times.resize((size_t) p.alpha_index_times_count * 4);
+    for (auto &v : p.alpha_index_times) v = b.integer();
+  }
+  advance();
+  if (key != "alpha_scalar_moments")
+    throw std::runtime_error("Error reading MTP file. Alpha scalar moment count not found.");
+  p.alpha_scalar_count = t.integer();
+  {
+    Tokens b(cur.must(eof), brace);
+    if (b.word() != "alpha_moment_mapping")
+      throw std::runtime_error("Error reading MTP file. Alpha moment mappings not found.");
+    p.alpha_moment_mapping.resize((size_t) p.alpha_scalar_count);
+    for (auto &v : p.alpha_moment_mapping) v = b.integer();
+  }
+  {
+    Tokens b(cur.must("Error reading MTP file. Species coefficients not found."), brace);
+    if (b.word() != "species_coeffs") throw std::runtime_error("Error reading MTP file. Species coefficients not found.");
+    p.species_coeffs.resize((size_t) S);
+    for (auto &v : p.species_coeffs) v = b.real();
+  }
+  {
+    Tokens b(cur.must("Error reading MTP file. Moment coefficients not found."), brace);
+    if (b.word() != "moment_coeffs") throw std::runtime_error("Error reading MTP file. Moment coefficients not found.");
+    p.linear_coeffs.resize((size_t) p.alpha_scalar_count);
+    for (auto &v : p.linear_coeffs) v = b.real();
+  }
+  finalize_tables(p);
+
+  if (!want_selection_state) return;
+
+  // ---- MaxVol selection state (pair_mtp_extrapolation.cpp:545-612) ----
+  std::string ln;
+  if (!cur.next(ln, /*strip_comments=*/false))
+    throw std::runtime_error(
+        "No selection state found! Consider training/retraining or disabling extrapolation!\n");
+  {
+    Tokens v(ln, seps);
+    if (v.word() != "#MVS_v1.1")
+      throw std::runtime_error(
+          "Error in reading MTP file selection state. Please verify MVS version is #MVS_v1.1!");
+  }
+  int energy_weight = 0, site_en_weight = 0;    // the reference truncates the weights to int (:570,576,592)
+  const char *names[5] = {"energy_weight", "force_weight", "stress_weight", "site_en_weight", "weight_scaling"};
+  for (int n = 0; n < 5; n++) {
+    std::string l2;
+    if (!cur.next(l2)) throw std::runtime_error(std::string("Error in reading MTP file, ") + names[n]);
+    Tokens w(l2, seps);
+    if (w.word() != names[n]) throw std::runtime_error(std::string("Error in reading MTP file, ") + names[n]);
+    if (n == 0) energy_weight = (int) w.real();
+    if (n == 3) site_en_weight = (int) w.real();
+  }
+  if (energy_weight + site_en_weight > 1)
+    throw std::runtime_error(
+        "Error, the MTP currently only supports configuration mode (energy_weight=1) or neighbourhood mode "
+        "(site_en_weight=1). Please retrain the MTP with the correct modes!");
+  p.configuration_mode = (energy_weight == 1);
+  const size_t Q = (size_t) p.coeff_count, nd = Q * Q;
+  size_t at = cur.pos + 1;    // one '#' byte precedes the binary block (:607)
+  if (at + 2 * nd * sizeof(double) > img.size())
+    throw std::runtime_error("Unexpected end of file or read error while reading binary data");
+  p.active_set.resize(nd);
+  p.inverse_active_set.resize(nd);
+  memcpy(p.active_set.data(), img.data() + at, nd * sizeof(double));
+  memcpy(p.inverse_active_set.data(), img.data() + at + nd * sizeof(double), nd * sizeof(double));
+  p.has_selection_state = true;
+}
+
+void finalize_tables(Potential &p)
+{
+  const int S = p.species_count, R = p.radial_func_count, B = p.radial_basis_size;
+  const int K = p.alpha_index_basic_count, T = p.alpha_index_times_count, A = p.alpha_scalar_count;
+  const int M = p.alpha_moment_count;
+  if (S < 1 || R < 1 || B < 1 || K < 1 || T < 0 || A < 1 || M < K)
+    throw std::runtime_error("Error reading MTP file. Inconsistent table sizes.");
+  if (M > 65535) throw std::runtime_error("alpha_moments_count above 65535 is not supported.");
+  if ((int) p.radial_basis_coeffs.size() != S * S * R * B || (int) p.alpha_index_basic.size() != 4 * K ||
+      (int) p.alpha_index_times.size() != 4 * T || (int) p.alpha_moment_mapping.size() != A ||
+      (int) p.species_coeffs.size() != S || (int) p.linear_coeffs.size() != A)
+    throw std::runtime_error("Error reading MTP file. Inconsistent table sizes.");
+  int radial_func_max = 0, pmax = 0;
+  for (int k = 0; k < K; k++) {
+    const int *e = &p.alpha_index_basic[4 * (size_t) k];
+    if (e[0] < 0 || e[1] < 0 || e[2] < 0 || e[3] < 0)
+      throw std::runtime_error("Error reading MTP file. Negative alpha_index_basic entry.");
+    radial_func_max = std::max(radial_func_max, e[0]);
+    pmax = std::max(pmax, e[1] + e[2] + e[3]);
+  }
+  if (radial_func_max != R - 1) throw std::runtime_error("Wrong number of radial functions specified!");
+  if (pmax > 63) throw std::runtime_error("alpha_index_basic rank above 63 is not supported.");
+  p.max_alpha_index_basic = pmax + 1;
+  for (int e = 0; e < T; e++) {
+    const int *q = &p.alpha_index_times[4 * (size_t) e];
+    if (q[0] < 0 || q[0] >= M || q[1] < 0 || q[1] >= M || q[3] < 0 || q[3] >= M)
+      throw std::runtime_error("Error reading MTP file. alpha_index_times entry out of range.");
+    if (std::abs((long) q[2]) >= (1L << 24))
+      throw std::runtime_error("Error reading MTP file. alpha_index_times multiplicity too large.");
+  }
+  for (int s = 0; s < A; s++)
+    if (p.alpha_moment_mapping[s] < 0 || p.alpha_moment_mapping[s] >= M)
+      throw std::runtime_error("Error reading MTP file. alpha_moment_mapping entry out of range.");
+  if (p.setflag.empty()) {
+    p.setflag.assign((size_t) (S + 1) * (S + 1), 0);
+    for (int i = 1; i <= S; i++)
+      for (int j = 1; j <= S; j++) p.setflag[(size_t) i * (S + 1) + j] = 1;
+  }
+  p.coeff_count = S * S * R * B + S + A;
+}
+
+// --------------------------------------------------------------------------------------------------
+
+namespace {
+
+struct NodeList {
+  int node;
+  std::vector<ProgramTerm> terms;
+};
+
+void pack_pass(const std::vector<std::vector<NodeList>> &per_level, ProgramPass &out)
+{
+  out = ProgramPass();
+  out.level_group_begin.push_back(0);
+  int slot_rows = 0;
+  for (const auto &lists_in : per_level) {
+    std::vector<const NodeList *> lists;
+    for (const auto &l : lists_in) lists.push_back(&l);
+    // longest lists first so that the 32 lanes of a group have similar trip counts
+    std::stable_sort(lists.begin(), lists.end(),
+                     [](const NodeList *a, const NodeList *b) { return a->terms.size() > b->terms.size(); });
+    for (size_t g0 = 0; g0 < lists.size(); g0 += 32) {
+      const size_t g1 = std::min(lists.size(), g0 + 32);
+      int mx = 0;
+      for (size_t i = g0; i < g1; i++) mx = std::max(mx, (int) lists[i]->terms.size());
+      out.group_term_base.push_back(slot_rows);
+      out.group_max_terms.push_back(mx);
+      out.terms.resize((size_t) (slot_rows + mx) * 32, ProgramTerm{0, 0, 0.0f});
+      for (int lane = 0; lane < 32; lane++) {
+        const size_t i = g0 + lane;
+        if (i < g1) {
+          out.node.push_back(lists[i]->node);
+          out.nterms.push_back((int) lists[i]->terms.size());
+          for (size_t t = 0; t < lists[i]->terms.size(); t++)
+            out.terms[(size_t) (slot_rows + t) * 32 + lane] = lists[i]->terms[t];
+        } else {
+          out.node.push_back(-1);
+          out.nterms.push_back(0);
+        }
+      }
+      slot_rows += mx;
+    }
+    out.level_group_begin.push_back(out.ngroups());
+  }
+}
+
+}    // namespace
+
+void compile_program(const Potential &p, Program &prog)
+{
+  const int M = p.alpha_moment_count, T = p.alpha_index_times_count, A = p.alpha_scalar_count;
+  const int *times = p.alpha_index_times.data();
+  prog = Program();
+
+  // sequential-consistency check: every write to a node precedes every read of it
+  std::vector<int> last_write(M, -1), first_read(M, T);
+  for (int e = 0; e < T; e++) {
+    const int a0 = times[4 * e], a1 = times[4 * e + 1], a3 = times[4 * e + 3];
+    first_read[a0] = std::min(first_read[a0], e);
+    first_read[a1] = std::min(first_read[a1], e);
+    last_write[a3] = e;
+  }
+  for (int n = 0; n < M; n++)
+    if (last_write[n] >= first_read[n])
+      throw std::runtime_error(
+          "Error in the alpha times indicies! alpha_index_times is not a topologically ordered program.");
+
+  // dependency level of every node (0 = never a target)
+  prog.level.assign(M, 0);
+  for (int e = 0; e < T; e++) {
+    const int a0 = times[4 * e], a1 = times[4 * e + 1], a3 = times[4 * e + 3];
+    prog.level[a3] = std::max(prog.level[a3], 1 + std::max(prog.level[a0], prog.level[a1]));
+  }
+  // (levels of sources are final when an edge is visited because all their writes precede this read)
+  prog.depth = 0;
+  for (int n = 0; n < M; n++) prog.depth = std::max(prog.depth, prog.level[n]);
+
+  // forward: per target, terms in file order
+  std::vector<std::vector<NodeList>> fwd(prog.depth);
+  {
+    std::vector<int> slot(M, -1);
+    for (int e = 0; e < T; e++) {
+      const int a0 = times[4 * e], a1 = times[4 * e + 1], mult = times[4 * e + 2], a3 = times[4 * e + 3];
+      auto &lv = fwd[prog.level[a3] - 1];
+      if (slot[a3] < 0) {
+        slot[a3] = (int) lv.size();
+        lv.push_back(NodeList{a3, {}});
+      }
+      lv[slot[a3]].terms.push_back(ProgramTerm{(uint16_t) a0, (uint16_t) a1, (float) mult});
+    }
+  }
+  pack_pass(fwd, prog.fwd);
+
+  // reverse: per source, terms in reverse file order; levels visited from depth-1 down to 0
+  std::vector<std::vector<NodeList>> rev(prog.depth);
+  {
+    std::vector<int> slot(M, -1);
+    auto add = [&](int src, int a3, int other, int mult) {
+      auto &lv = rev[prog.depth - 1 - prog.level[src]];
+      if (slot[src] < 0) {
+        slot[src] = (int) lv.size();
+        lv.push_back(NodeList{src, {}});
+      }
+      lv[slot[src]].terms.push_back(ProgramTerm{(uint16_t) a3, (uint16_t) other, (float) mult});
+    };
+    for (int e = T - 1; e >= 0; e--) {
+      const int a0 = times[4 * e], a1 = times[4 * e + 1], mult = times[4 * e + 2], a3 = times[4 * e + 3];
+      add(a1, a3, a0, mult);    // g[a1] += g[a3]*mult*m[a0]   (pair_mtp.cpp:231)
+      add(a0, a3, a1, mult);    // g[a0] += g[a3]*mult*m[a1]   (pair_mtp.cpp:232)
+    }
+  }
+  pack_pass(rev, prog.rev);
+
+  prog.ginit.assign(M, 0.0);
+  for (int s = 0; s < A; s++) prog.ginit[p.alpha_moment_mapping[s]] = p.linear_coeffs[s];
+}
+
+}    // namespace mtpb200

@@ -1,0 +1,78 @@
+// Host-side potential model: MLIP-3 .almtp parser and the "compiled" contraction program.
+// Behavioural spec: PairMTP::read_file (pair_mtp.cpp:335-655), RadialMTPBasis::ReadBasisProperties
+// (mtp_radial_basis.cpp:59-102), PairMTPExtrapolation::read_file (pair_mtp_extrapolation.cpp:528-619).
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace mtpb200 {
+
+struct Potential {
+  int species_count = 0;
+  int radial_func_count = 0;      // R
+  int radial_basis_size = 0;      // B
+  int alpha_moment_count = 0;     // M
+  int alpha_index_basic_count = 0;
+  int alpha_index_times_count = 0;
+  int alpha_scalar_count = 0;
+  int max_alpha_index_basic = 0;  // P
+  double min_cutoff = 0, max_cutoff = 0, scaling = 1.0;
+  std::string potential_name = "Untitled", potential_tag;
+  std::vector<double> radial_basis_coeffs;   // [S][S][R][B]
+  std::vector<int> alpha_index_basic;        // [K][4]
+  std::vector<int> alpha_index_times;        // [T][4]
+  std::vector<int> alpha_moment_mapping;     // [A]
+  std::vector<double> species_coeffs, linear_coeffs;
+  std::vector<int> setflag;                  // [(S+1)^2], pair_mtp.cpp:455
+  // selection state
+  bool has_selection_state = false;
+  int configuration_mode = 0;
+  int coeff_count = 0;                       // Q
+  std::vector<double> active_set, inverse_active_set;
+  std::string log;                           // what the reference prints through utils::logmesg
+
+  int radial_coeff_count() const { return species_count * species_count * radial_func_count * radial_basis_size; }
+};
+
+// Throws std::runtime_error with the reference's message on any grammar violation.
+void parse_almtp(const std::string &path, bool want_selection_state, Potential &out);
+// Validates sizes / index ranges of tables handed in through mtp_create(); derives P and Q.
+void finalize_tables(Potential &p);
+
+// ---- contraction program ------------------------------------------------------------------------
+// alpha_index_times is a sequential program  m[a3] += mult*m[a0]*m[a1]  (pair_mtp.cpp:196-201) whose
+// reverse sweep gives dE/dm (pair_mtp.cpp:221-233).  At load it is re-expressed as atomic-free gather
+// lists grouped by dependency level (the reference's "waves", pair_mtps_kokkos.cpp:179-200, for any
+// depth): forward = per TARGET node the list of (a0,a1,mult) in file order; reverse = per SOURCE node
+// the list of (a3,other,mult) in reverse file order.  Nodes of one level are packed 32 to a group and
+// their lists are stored transposed (ELL, slot-major) so that lane l of a warp owns node l of the
+// group and reads term t at  terms[(term_base + t) * 32 + l]  (coalesced).
+struct ProgramTerm {
+  uint16_t a;     // forward: a0      reverse: a3
+  uint16_t b;     // forward: a1      reverse: the other factor
+  float mult;     // small integer multiplicity (exact in fp32)
+};
+
+struct ProgramPass {
+  std::vector<int> level_group_begin;   // [nlevels + 1] group index ranges per level (execution order)
+  std::vector<int> group_term_base;     // [ngroups] first slot row of the group
+  std::vector<int> group_max_terms;     // [ngroups]
+  std::vector<int> node;                // [ngroups * 32] node id or -1
+  std::vector<int> nterms;              // [ngroups * 32]
+  std::vector<ProgramTerm> terms;       // [slot_rows * 32]
+  int ngroups() const { return (int) group_term_base.size(); }
+};
+
+struct Program {
+  int depth = 0;                  // number of waves
+  std::vector<int> level;         // [M]
+  ProgramPass fwd, rev;
+  std::vector<double> ginit;      // [M]: dE/dm seed, g[map[s]] = xi_s (pair_mtp.cpp:217-218)
+};
+
+// Throws std::runtime_error if the table is not a topologically ordered program.
+void compile_program(const Potential &p, Program &out);
+
+}    // namespace mtpb200
