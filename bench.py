@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Headline benchmark: atom-steps/s of the MTP pair-style compute (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 2]
+
+A "step" is one full force evaluation (Pair::compute with eflag=1, vflag=1) over the workload:
+configs[1] of BASELINE.json by default (bcc W/Mo, 262,144 atoms, MTP level 16, 2 species, positions =
+lattice + 0.05 A jitter, full neighbor list at cutoff 5 A + 2 A skin, ghosts explicit like LAMMPS).
+N > 1 (torchrun, one rank per GPU): the global box is the per-GPU box replicated on a brick grid
+{2x1x1, 2x2x1, 2x2x2}; every step each rank packs its halo on the device, exchanges ghost positions
+and ghost forces with NCCL send/recv and runs the same kernels on its brick (weak scaling).
+
+One JSON line is printed by rank 0 (contract in the task statement): `value` = device-timed whole-job
+atom-steps/s with inputs resident in HBM, `e2e` = the same metric through the host-buffer C-ABI call
+(mtp_compute_host: H2D of x/type/f/neighbor list, compute, D2H of f and the energy/virial record),
+`roofline` for the dominant kernel against the FP64 peak measured in this run, `cpu_baseline` = the
+reference's own CPU `mtp` style timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "lammps-mtp-kokkos_b200"))
+
+METRIC = "atom-steps/sec (Matom·step/s) at 1/2/4/8 B200 vs CPU mtp; % of FP64/HBM roofline"
+UNIT = "Matom·step/s"
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+def algorithmic_flops_per_atom(pot, n_list, n_cut):
+    """flops counted as written in pair_mtp.cpp (add/mul/div/sqrt = 1, fma = 2)."""
+    B, R, P = pot.radial_basis_size, pot.radial_funcs_count, pot.max_alpha_index_basic
+    K, T, A = pot.K, pot.T, pot.A
+    nz = (np.asarray(pot.alpha_index_basic)[:, 1:] != 0).sum(axis=1)
+    per_pair = (8 * B + 19) + 4 * (P - 1) + 4 * R * B + float((15 + 5 * nz).sum()) + 6 * K + 6
+    return 9.0 * n_list + n_cut * per_pair + 9.0 * T + 2.0 * A
+
+
+def algorithmic_bytes_per_atom(n_list):
+    return 4.0 * n_list + 84.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc = None
+        self.index = index
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        busy = [s for s, p in zip(sm, pw) if p > 300] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def brick_grid(n):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n]
+
+
+def pinned_like(a):
+    import torch
+    t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].copy()).dtype, pin_memory=True)
+    v = t.numpy()
+    v[...] = a
+    return t, v
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, cfg, pot_path, pot):
+    """The reference's own CPU `mtp` (oracle/_ref, unmodified sources) on all host cores; falls back to
+    the C restatement (kind "port") only if the prebuilt reference library did not travel."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    from concurrent.futures import ThreadPoolExecutor
+    from mtp_b200 import harness
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cells = args.ref_cells
+    sysm = harness.make_config(args.config, cells=cells)
+    kind = "reference" if os.path.exists(oracle_py.REF_SO) else "port"
+    if kind == "port":
+        oracle_py.build(ref=False)
+    slabs = np.array_split(sysm.ilist, cores)
+
+    def make():
+        return oracle_py.ReferenceMTP("mtp", pot_path) if kind == "reference" else oracle_py.OracleMTP(pot)
+
+    workers = [make() for _ in range(cores)]
+
+    def one(k):
+        w, il = workers[k], slabs[k]
+        if kind == "reference":
+            r = w.compute(sysm.x, sysm.type, sysm.nlocal, il, sysm.numneigh, sysm.neigh, sysm.offsets, eflag=1, vflag=1)
+        else:
+            r = w.compute(sysm.x, sysm.type, il, sysm.numneigh, sysm.neigh, sysm.offsets, eflag=1, vflag=1)
+        return r.energy
+
+    times = []
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            es = list(ex.map(one, range(cores)))
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = sysm.nlocal / (ms * 1e-3) / 1e6
+    sample = (f"{sysm.nlocal}-atom sub-box ({cells[0]}x{cells[1]}x{cells[2]} cells) of the same lattice/potential, "
+              f"{cores} threads each owning a contiguous slab of ilist (PairMTP::compute, eflag=1 vflag=1), "
+              f"g++ -O2 -ffp-contract=off")
+    return dict(value=value, ms_per_step=ms, cores=cores, kind=kind, sample=sample, energy=float(sum(es)),
+                natoms=sysm.nlocal)
+
+
+# ----------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--cells", type=int, nargs=3, default=None, help="override the per-GPU cell counts")
+    ap.add_argument("--ref-cells", type=int, nargs=3, default=None, help="CPU-baseline sample box")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="large", choices=["large", "small"])
+    args = ap.parse_args()
+
+    from mtp_b200 import almtp, harness
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = harness.CONFIGS[args.config]
+    if args.ref_cells is None:
+        per_cell = {"sc": 1, "bcc": 2, "fcc": 4, "diamond": 8}[cfg["kind"]]
+        n = 2
+        while per_cell * (n + 2) ** 3 <= 28000:
+            n += 2
+        args.ref_cells = (n, n, n)
+
+    tmp = tempfile.mkdtemp(prefix="mtp_bench_")
+    pot_path = os.path.join(tmp, f"config{args.config}.almtp")
+    pot = almtp.random_potential(cfg["level"], cfg["species"], with_active_set=bool(cfg.get("active_set")))
+    if rank == 0 or args.impl == "b200":
+        almtp.write_almtp(pot_path if world == 1 else pot_path + f".{rank}", pot)
+        if world > 1:
+            pot_path = pot_path + f".{rank}"
+    pot = almtp.read_almtp(pot_path) if os.path.exists(pot_path) else pot
+    cells = tuple(args.cells) if args.cells else cfg["cells"]
+    workload = (f"config[{args.config - 1}]: {cfg['name']}; {cells[0]}x{cells[1]}x{cells[2]} {cfg['kind']} cells per GPU, "
+                f"jitter 0.05 A, cutoff 5.0 A + skin 2.0 A, random-init MLIP-3 coefficients (seed = level)")
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = run_reference(args, cfg, pot_path, pot)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload, "sample": r["sample"]},
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    from mtp_b200 import api
+    from mtp_b200.api import MTPB200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the MTP B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    variant = api.VARIANT_SMALL if args.variant == "small" else api.VARIANT_LARGE
+    mtp = MTPB200(pot_path, selection_state=bool(cfg.get("active_set")), device=local_rank)
+
+    if world == 1:
+        sysm = harness.make_config(args.config, cells=cells)
+        halo = None
+    else:
+        from mtp_b200 import decomp
+        sysm, halo = decomp.make_rank_system(args.config, cells, brick_grid(world), rank, dev, mtp)
+    nlocal, nall = sysm.nlocal, sysm.nall
+
+    # workload statistics for the roofline (listed / in-cutoff neighbors per atom)
+    n_list = float(sysm.numneigh[:nlocal].mean())
+    ii = np.repeat(np.arange(nlocal), sysm.numneigh[:nlocal])
+    d2 = ((sysm.x[sysm.neigh] - sysm.x[ii]) ** 2).sum(axis=1)
+    n_cut = float((d2 <= pot.max_dist ** 2).sum() / nlocal)
+    del ii, d2
+    flops_atom = algorithmic_flops_per_atom(pot, n_list, n_cut)
+    bytes_atom = algorithmic_bytes_per_atom(n_list)
+
+    # device-resident inputs
+    t_x = torch.from_numpy(sysm.x).to(dev)
+    t_type = torch.from_numpy(sysm.type).to(dev)
+    t_ilist = torch.from_numpy(sysm.ilist).to(dev)
+    t_nn = torch.from_numpy(sysm.numneigh).to(dev)
+    t_neigh = torch.from_numpy(sysm.neigh).to(dev)
+    t_off = torch.from_numpy(sysm.offsets).to(dev)
+    t_f = torch.zeros((nall, 3), dtype=torch.float64, device=dev)
+    t_ev = torch.zeros(8, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device():
+        t_f.zero_()
+        if halo is not None:
+            halo.forward(t_x)
+        mtp.compute_device(t_x, t_type, t_ilist, t_nn, t_neigh, t_off, t_f, t_ev, eflag=1, vflag=1,
+                           variant=variant, stream=stream)
+        if halo is not None:
+            halo.reverse(t_f)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    peaks = api.fp64_peaks(local_rank)       # measured DFMA / DMMA roofs (also warms the clocks)
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    launches0 = api.kernel_launch_count()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    for s in range(args.steps):
+        flush.fill_(s & 0xff)                  # L2 flush between timed iterations (not timed)
+        ev0[s].record()
+        step_device()
+        ev1[s].record()
+    barrier()
+    launches = api.kernel_launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    total_ms = float(sum(step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    mtp.synchronize()
+    clocks = sampler.stop()
+    ms_per_step = total_ms / args.steps
+    value = world * nlocal / (ms_per_step * 1e-3) / 1e6
+    energy = float(t_ev[0].item())
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
+    e2e = None
+    if world == 1:
+        keep, hx = pinned_like(sysm.x)
+        k2, htype = pinned_like(sysm.type)
+        k3, hnn = pinned_like(sysm.numneigh)
+        k4, hneigh = pinned_like(sysm.neigh)
+        k5, hoff = pinned_like(sysm.offsets)
+        k6, hil = pinned_like(sysm.ilist)
+        res = api.HostResult(nall, mtp.info.coeff_count)
+        k7, res.f = pinned_like(res.f)
+        k8, res.ev = pinned_like(res.ev)
+        for _ in range(2):
+            res.f[:] = 0.0
+            mtp.compute_host(hx, htype, hil, hnn, hneigh, hoff, eflag=1, vflag=1, variant=variant, out=res)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res.f[:] = 0.0
+            mtp.compute_host(hx, htype, hil, hnn, hneigh, hoff, eflag=1, vflag=1, variant=variant, out=res,
+                             list_changed=True)
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+        nid = nlocal
+        h2d = 24 * nall + 4 * nall + 24 * nall + 4 * sysm.neigh.size + 8 * nid + 4 * nid + 4 * nlocal
+        d2h = 24 * nall + 64
+        e2e = {"value": nlocal / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "note": "mtp_compute_host per step: H2D x,type,f and the full neighbor list (re-sent every step), "
+                       "kernels, D2H f + energy/virial record; host buffers pinned",
+               "energy_matches_device_path": bool(abs(res.ev[0] - energy) <= 1e-9 * abs(energy))}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    dfma, dmma = peaks
+    achieved_tf = flops_atom * nlocal / (ms_per_step * 1e-3) / 1e12
+    hbm_peak = 6555.5
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "MEASURED_PEAKS.json"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved_gbs = bytes_atom * nlocal / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": dfma, "unit": "TFLOP/s", "frac": achieved_tf / dfma,
+                "traffic": None, "kernel": "mtp_site_kernel (fused gather / moments / contraction tree / reverse / force)",
+                "peak_source": "FP64 DFMA peak measured in this run by mtp_fp64_peak (DMMA: %.2f TFLOP/s); "
+                               "MEASURED_PEAKS.json has no FP64 entry" % dmma,
+                "algorithmic_flops_per_atom": flops_atom, "algorithmic_bytes_per_atom": bytes_atom,
+                "neighbors_listed": n_list, "neighbors_in_cutoff": n_cut,
+                "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                        "peak_source": hbm_src},
+                "duration_ms": ms_per_step, "duration_note": "CUDA events around the whole step (pack + site kernel + "
+                                                             "finalize); the site kernel is >99% of it (profiles/)"}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        r = run_reference(argparse.Namespace(**{**vars(args), "steps": 8, "warmup": 1}), cfg, pot_path, pot)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload, "atoms_per_gpu": nlocal, "ghosts_per_gpu": nall - nlocal,
+                       "l2": "256 MiB write between timed iterations (L2 flush), per-step CUDA events summed",
+                       "variant": args.variant, "flags": "eflag=1 vflag=1"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "energy": energy}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
