@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <stdexcept>
@@ -84,18 +85,43 @@ struct PassBufs {
 
 }    // namespace
 
+struct ChunkBufs {
+  DevBuf<int> level_begin, node, term_begin;
+  DevBuf<uint32_t> term_idx;
+  DevBuf<double> term_coef, init;
+  DevChunkPass upload(const ChunkPass &c)
+  {
+    level_begin.upload(c.level_begin, 0);
+    node.upload(c.node, 0);
+    term_begin.upload(c.term_begin, 0);
+    term_idx.upload(c.term_idx, 0);
+    term_coef.upload(c.term_coef, 0);
+    init.upload(c.init, 0);
+    DevChunkPass d;
+    d.level_begin = level_begin.p;
+    d.node = node.p;
+    d.term_begin = term_begin.p;
+    d.term_idx = term_idx.p;
+    d.term_coef = term_coef.p;
+    d.init = init.p;
+    d.nlevels = (int) c.level_begin.size() - 1;
+    return d;
+  }
+};
+
 struct mtp_handle {
   Potential pot;
   Program prog;
   int device = 0;
   int sm_count = 0;
-  int chunksize = 1 << 30;
+  int chunksize = 32768;          // README.md:52-53 of the reference uses 32768 in every example
   int qpad = 0;
   // device copies of the potential
   DevBuf<double> d_radial, d_species, d_lin, d_ginit, d_ainv;
   DevBuf<uint32_t> d_basic;
   DevBuf<int> d_map;
   PassBufs d_fwd, d_rev;
+  ChunkBufs d_cfwd, d_crev;
   DevPotential dpot{};
   // work buffers (grow-only)
   DevBuf<AtomRec> d_xt;
@@ -108,15 +134,77 @@ struct mtp_handle {
   DevBuf<unsigned char> h_within;
   long long h_list_len = 0;
   cudaStream_t hstream = nullptr;
+  // register-resident kernel family (mtp_kernels_v1.cuh), -1 = generic kernel only
+  int v1_entry = -1;
+  DevBuf<short> d_fwd_slot, d_g_src;
+  V1Tables v1tab{};
   // launch configuration per kernel flavour
   int warps[2] = {0, 0};
   int grid_cap[2] = {0, 0};
+  // three-kernel pipeline (register-resident family)
+  DevBuf<double> d_mb, d_gb;      // [K][ld] basic moments / their adjoints of the current super-chunk
+  int pl_na_fit = 0;              // largest atoms-per-CTA of the program kernel that fits shared memory
+  int pl_grid_m = 0, pl_grid_p = 0, pl_grid_f[2] = {0, 0};
+  size_t pl_smem_m = 0, pl_smem_f[2] = {0, 0};
   size_t smem[2] = {0, 0};
 };
 
 namespace {
 
 void set_device(const mtp_handle *h) { CUDA_CHECK(cudaSetDevice(h->device)); }
+
+// dynamic shared memory a kernel may request: opt-in limit minus its static allocation
+size_t max_dynamic_smem(const void *fn, size_t optin)
+{
+  cudaFuncAttributes fa;
+  CUDA_CHECK(cudaFuncGetAttributes(&fa, fn));
+  return optin > fa.sharedSizeBytes ? optin - fa.sharedSizeBytes : 0;
+}
+
+// ---- instantiations of the register-resident kernel: (max tensor rank, padded radial function count) ----
+typedef void (*V1MomentsKernel)(DevPotential, V1Tables, SiteArgs, double *, int);
+typedef void (*V1ForcesKernel)(DevPotential, V1Tables, SiteArgs, const double *, int, double *);
+typedef V1Layout (*V1LayoutFn)(int, int, int, int, int, bool, int);
+struct V1Entry {
+  int deg, rp;
+  V1MomentsKernel moments;
+  V1ForcesKernel forces[2];
+  V1LayoutFn layout;
+};
+#define V1_ENTRY(D, R) \
+  {D, R, mtp_moments_kernel<D, R>, {mtp_forces_kernel<D, R, false>, mtp_forces_kernel<D, R, true>}, v1_layout<D, R>}
+const V1Entry kV1[] = {V1_ENTRY(2, 2), V1_ENTRY(3, 4), V1_ENTRY(4, 4), V1_ENTRY(6, 4), V1_ENTRY(8, 6), V1_ENTRY(9, 6)};
+constexpr int kV1Count = sizeof(kV1) / sizeof(kV1[0]);
+
+// canonical-slot tables for entry e; returns false if the basic table cannot be mapped (duplicates)
+bool build_v1_tables(mtp_handle *h, int e)
+{
+  const Potential &p = h->pot;
+  const int deg = kV1[e].deg, rp = kV1[e].rp, smax = deg / 2;
+  const int nb = tet(smax), nq = tet(deg);
+  std::vector<short> fwd((size_t) nb * 64, (short) -1), gsrc((size_t) nq * rp, (short) -1);
+  int rcnt[16] = {0};
+  for (int k = 0; k < p.alpha_index_basic_count; k++) {
+    const int *b = &p.alpha_index_basic[4 * (size_t) k];
+    const int mu = b[0], ax = b[1], ay = b[2], az = b[3], d = ax + ay + az;
+    if (mu >= rp || d > deg || k > 32767) return false;
+    const int t = block_index(smax, ax / 2, ay / 2, az / 2);
+    const int pcls = (ax & 1) | ((ay & 1) << 1) | ((az & 1) << 2);
+    const int lane = mu * 4 + (pcls >> 1), j = pcls & 1;
+    short &fs = fwd[((size_t) t * 32 + lane) * 2 + j];
+    short &gs = gsrc[(size_t) canon_index(deg, ax, ay, az) * rp + mu];
+    if (fs >= 0 || gs >= 0) return false;    // two basic moments with the same definition
+    fs = (short) k;
+    gs = (short) k;
+    rcnt[d] = std::max(rcnt[d], mu + 1);
+  }
+  h->d_fwd_slot.upload(fwd, 0);
+  h->d_g_src.upload(gsrc, 0);
+  h->v1tab.fwd_slot = h->d_fwd_slot.p;
+  h->v1tab.g_src = h->d_g_src.p;
+  for (int d = 0; d < 16; d++) h->v1tab.rcnt[d] = rcnt[d];
+  return true;
+}
 
 void upload_potential(mtp_handle *h)
 {
@@ -170,31 +258,85 @@ void upload_potential(mtp_handle *h)
   d.ginit = h->d_ginit.p;
   d.fwd = h->d_fwd.view(h->prog.fwd);
   d.rev = h->d_rev.view(h->prog.rev);
+  DevChunkPass cf = h->d_cfwd.upload(h->prog.cfwd), cr = h->d_crev.upload(h->prog.crev);
+  CUDA_CHECK(cudaDeviceSynchronize());
+  d.cfwd = cf;
+  d.crev = cr;
 
-  // launch configuration: as many warps per CTA (<= 8) as shared memory allows, then occupancy
+  // kernel family: register-resident kernel for standard shapes, generic kernel otherwise
+  h->v1_entry = -1;
+  if (!getenv("MTP_B200_FORCE_GENERIC")) {
+    for (int e = 0; e < kV1Count; e++)
+      if (kV1[e].deg >= d.P - 1 && kV1[e].rp >= d.R && d.P - 1 >= 0) {
+        if (build_v1_tables(h, e)) h->v1_entry = e;
+        break;
+      }
+  }
+
+  // launch configuration
   cudaDeviceProp prop;
   CUDA_CHECK(cudaGetDeviceProperties(&prop, h->device));
   h->sm_count = prop.multiProcessorCount;
   const size_t smem_max = prop.sharedMemPerBlockOptin;
+  if (h->v1_entry >= 0) {
+    const V1Entry &E = kV1[h->v1_entry];
+    const int W = 8;
+    bool ok = true;
+    {
+      const V1Layout L = E.layout(d.S, d.R, d.B, d.M, d.Q, false, 1);
+      h->pl_smem_m = L.radial_bytes + W * L.warp_bytes_moments;
+      ok = ok && h->pl_smem_m <= max_dynamic_smem((const void *) E.moments, smem_max);
+      if (ok) {
+        CUDA_CHECK(cudaFuncSetAttribute((const void *) E.moments, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->pl_smem_m));
+        int per_sm = 0;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.moments, W * 32, h->pl_smem_m));
+        h->pl_grid_m = std::max(1, per_sm) * h->sm_count;
+      }
+    }
+    for (int gflag = 0; gflag < 2 && ok; gflag++) {
+      if (gflag == 1 && !p.has_selection_state) continue;
+      const V1Layout L = E.layout(d.S, d.R, d.B, d.M, d.Q, gflag == 1, 1);
+      h->pl_smem_f[gflag] = L.radial_bytes + W * L.warp_bytes_forces;
+      ok = ok && h->pl_smem_f[gflag] <= max_dynamic_smem((const void *) E.forces[gflag], smem_max);
+      if (!ok) break;
+      CUDA_CHECK(cudaFuncSetAttribute((const void *) E.forces[gflag], cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->pl_smem_f[gflag]));
+      int per_sm = 0;
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.forces[gflag], W * 32, h->pl_smem_f[gflag]));
+      h->pl_grid_f[gflag] = std::max(1, per_sm) * h->sm_count;
+    }
+    // program kernel: largest power-of-two chunk whose moments + adjoints fit
+    h->pl_na_fit = 0;
+    const size_t prog_max = std::min(max_dynamic_smem((const void *) mtp_program_kernel<false>, smem_max),
+                                     max_dynamic_smem((const void *) mtp_program_kernel<true>, smem_max));
+    for (int na = 32; na >= 1; na >>= 1) {
+      const size_t nb = (((size_t) d.M * (na + 1) * 8 + 15) & ~(size_t) 15) * 2;
+      if (nb <= prog_max) {
+        h->pl_na_fit = na;
+        break;
+      }
+    }
+    ok = ok && h->pl_na_fit >= 1;
+    if (ok) {
+      CUDA_CHECK(cudaFuncSetAttribute((const void *) mtp_program_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) prog_max));
+      CUDA_CHECK(cudaFuncSetAttribute((const void *) mtp_program_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) prog_max));
+    }
+    if (!ok) h->v1_entry = -1;    // fall back to the generic kernel
+  }
   for (int gflag = 0; gflag < 2; gflag++) {
     if (gflag == 1 && !p.has_selection_state) continue;
     const Layout L = make_layout(d.S, d.R, d.B, d.K, d.M, d.P, d.Q, gflag == 1);
+    const void *fn = gflag ? (const void *) mtp_site_kernel<true> : (const void *) mtp_site_kernel<false>;
     int w = 4;
-    while (w > 1 && L.cta_bytes + (size_t) w * L.warp_bytes > smem_max) w--;
+    const size_t gen_max = max_dynamic_smem(fn, smem_max);
+    while (w > 1 && L.cta_bytes + (size_t) w * L.warp_bytes > gen_max) w--;
     const size_t bytes = L.cta_bytes + (size_t) w * L.warp_bytes;
-    if (bytes > smem_max)
+    if (bytes > gen_max) {
+      if (h->v1_entry >= 0) continue;
       throw std::runtime_error("potential too large for on-chip per-atom state (alpha_moments_count)");
-    if (gflag == 0) {
-      CUDA_CHECK(cudaFuncSetAttribute(mtp_site_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes));
-    } else {
-      CUDA_CHECK(cudaFuncSetAttribute(mtp_site_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes));
     }
+    CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes));
     int per_sm = 0;
-    if (gflag == 0) {
-      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mtp_site_kernel<false>, w * 32, bytes));
-    } else {
-      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mtp_site_kernel<true>, w * 32, bytes));
-    }
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, w * 32, bytes));
     if (per_sm < 1) per_sm = 1;
     h->warps[gflag] = w;
     h->smem[gflag] = bytes;
@@ -240,31 +382,78 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
   s.status = h->d_status.p;
 
   const int gi = grade ? 1 : 0;
-  const int w = h->warps[gi];
   const bool cfg = grade && h->pot.configuration_mode;
-  // chunking only bounds the candidate-row scratch of grade steps (README.md:44 "chunksize")
-  const int chunk = grade ? std::max(1, std::min(h->chunksize, a.inum > 0 ? a.inum : 1)) : (a.inum > 0 ? a.inum : 1);
+  const bool pipeline = h->v1_entry >= 0;
+  // super-chunk: bounded by the user's "chunksize"; the pipeline additionally keeps its two [K][chunk]
+  // intermediates within ~48 MB so that they stay L2-resident
+  int chunk = std::max(1, std::min(h->chunksize, a.inum > 0 ? a.inum : 1));
+  if (pipeline) {
+    const long long fit = std::max(8192LL, (48LL << 20) / (16LL * d.K) / 1024 * 1024);
+    chunk = (int) std::min<long long>(chunk, fit);
+  } else if (!grade) {
+    chunk = a.inum > 0 ? a.inum : 1;
+  }
+  const int ld = (chunk + 31) / 32 * 32;
   if (grade) h->d_cand.ensure((size_t) chunk * h->qpad);
+  if (pipeline) {
+    h->d_mb.ensure((size_t) d.K * ld);
+    h->d_gb.ensure((size_t) d.K * ld);
+  }
   if (cfg) CUDA_CHECK(cudaMemsetAsync(h->d_cfg.p, 0, sizeof(double) * h->qpad, st));
   CUDA_CHECK(cudaMemsetAsync(a.ev_out, 0, sizeof(double) * 8, st));
 
-  int nchunk = 0;
-  for (int first = 0; first < a.inum || (first == 0 && nchunk == 0); first += chunk, nchunk++) {
+  const int nsuper = a.inum > 0 ? (a.inum + chunk - 1) / chunk : 1;
+  const int W = 8;
+  // program kernel shape: atoms per CTA (power of two), smaller for small systems so that every SM gets work
+  int na = 1, grid_p_cap = 1;
+  size_t smem_p = 0;
+  if (pipeline) {
+    na = h->pl_na_fit;
+    const int nfirst = std::min(chunk, std::max(a.inum, 1));
+    while (na > 1 && (nfirst + na - 1) / na < h->sm_count) na >>= 1;
+    if (a.variant == MTP_VARIANT_SMALL && na > 8) na = 8;
+    smem_p = (((size_t) d.M * (na + 1) * 8 + 15) & ~(size_t) 15) * 2;
+    int per_sm = 0;
+    const void *pk = grade ? (const void *) mtp_program_kernel<true> : (const void *) mtp_program_kernel<false>;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, 512, smem_p));
+    grid_p_cap = std::max(1, per_sm) * h->sm_count;
+  }
+  const int rows_per_super = pipeline ? grid_p_cap + h->pl_grid_f[gi] : h->grid_cap[gi];
+  h->d_partials.ensure((size_t) nsuper * rows_per_super * 8);
+  int rows_used = 0;
+
+  for (int sc = 0; sc < nsuper; sc++) {
+    const int first = sc * chunk;
     const int n = std::max(0, std::min(chunk, a.inum - first));
-    int grid = std::min(h->grid_cap[gi], (n + w - 1) / w);
-    if (grid < 1) grid = 1;
-    h->d_partials.ensure((size_t) h->grid_cap[gi] * 8);
     s.inum = n;
     s.first_ii = first;
-    s.partials = h->d_partials.p;
     s.cand_rows = grade ? h->d_cand.p : nullptr;
     s.cand_ld = h->qpad;
-    if (grade) mtp_site_kernel<true><<<grid, w * 32, h->smem[1], st>>>(d, s, w);
-    else
-      mtp_site_kernel<false><<<grid, w * 32, h->smem[0], st>>>(d, s, w);
-    g_launches++;
-    finalize_ev_kernel<<<1, 32, 0, st>>>(h->d_partials.p, grid, a.ev_out, 1);
-    g_launches++;
+    if (pipeline) {
+      const V1Entry &E = kV1[h->v1_entry];
+      const int gm = std::max(1, std::min(h->pl_grid_m, (n + W - 1) / W));
+      E.moments<<<gm, W * 32, h->pl_smem_m, st>>>(d, h->v1tab, s, h->d_mb.p, ld);
+      const int gp = std::max(1, std::min(grid_p_cap, (n + na - 1) / na));
+      double *part_p = h->d_partials.p + (size_t) rows_used * 8;
+      if (grade) mtp_program_kernel<true><<<gp, 512, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, part_p);
+      else
+        mtp_program_kernel<false><<<gp, 512, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, part_p);
+      rows_used += gp;
+      const int gf = std::max(1, std::min(h->pl_grid_f[gi], (n + W - 1) / W));
+      double *part_f = h->d_partials.p + (size_t) rows_used * 8;
+      E.forces[gi]<<<gf, W * 32, h->pl_smem_f[gi], st>>>(d, h->v1tab, s, h->d_gb.p, ld, part_f);
+      rows_used += gf;
+      g_launches += 3;
+    } else {
+      const int w = h->warps[gi];
+      const int grid = std::max(1, std::min(h->grid_cap[gi], (n + w - 1) / w));
+      s.partials = h->d_partials.p + (size_t) rows_used * 8;
+      if (grade) mtp_site_kernel<true><<<grid, w * 32, h->smem[1], st>>>(d, s, w);
+      else
+        mtp_site_kernel<false><<<grid, w * 32, h->smem[0], st>>>(d, s, w);
+      rows_used += grid;
+      g_launches++;
+    }
     if (grade && n > 0) {
       if (cfg) {
         cand_colsum_kernel<<<(d.Q + 127) / 128, 128, 0, st>>>(h->d_cand.p, n, h->qpad, d.Q, h->d_cfg.p, 1);
@@ -279,8 +468,9 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
         g_launches++;
       }
     }
-    if (a.inum == 0) break;
   }
+  finalize_ev_kernel<<<1, 7 * 32, 0, st>>>(h->d_partials.p, rows_used, a.ev_out, 1);
+  g_launches++;
   if (cfg) {
     const long long nat = a.natoms_total > 0 ? a.natoms_total : a.inum;
     cfg_grade_kernel<<<1, 256, 0, st>>>(h->d_ainv.p, h->qpad, d.Q, h->d_cfg.p, nat > 0 ? 1.0 / (double) nat : 0.0,
@@ -335,6 +525,20 @@ extern "C" {
 const char *mtp_last_error(void) { return g_last_error.c_str(); }
 
 long long mtp_kernel_launch_count(void) { return g_launches.load(); }
+
+/* diagnostic builds only (-DMTP_PHASE_CLOCKS): per-phase SM clocks summed over warps, then reset */
+int mtp_debug_phase_clocks(unsigned long long *out8)
+{
+#ifdef MTP_PHASE_CLOCKS
+  unsigned long long z[8] = {0};
+  if (cudaMemcpyFromSymbol(out8, g_phase_clocks, sizeof(z)) != cudaSuccess) return MTP_ERR_CUDA;
+  if (cudaMemcpyToSymbol(g_phase_clocks, z, sizeof(z)) != cudaSuccess) return MTP_ERR_CUDA;
+  return MTP_OK;
+#else
+  (void) out8;
+  return MTP_ERR_ARG;
+#endif
+}
 
 mtp_handle *mtp_create_from_file(const char *path, int want_selection_state, int device)
 {

@@ -15,6 +15,16 @@ struct DevPass {
   int nlevels;
 };
 
+struct DevChunkPass {
+  const int *level_begin;      // [nlevels + 1]
+  const int *node;             // [nslots]
+  const int *term_begin;       // [nslots + 1]
+  const uint32_t *term_idx;    // packed operands
+  const double *term_coef;
+  const double *init;          // [nslots]
+  int nlevels;
+};
+
 struct DevPotential {
   int S, R, B, K, M, A, P, Q;
   double rmin, rmax, scaling, cutsq;
@@ -25,6 +35,7 @@ struct DevPotential {
   const int *map;            // [A]
   const double *ginit;       // [M]
   DevPass fwd, rev;
+  DevChunkPass cfwd, crev;
 };
 
 // packed position + species record: one 32-byte sector per gathered neighbor

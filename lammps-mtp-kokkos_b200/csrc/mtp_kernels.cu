@@ -493,15 +493,20 @@ __global__ void __launch_bounds__(256) mtp_site_kernel(DevPotential pot, SiteArg
   }
 }
 
-// sums the per-CTA partials in block order; ev[0..6] (+)= sum, ev[7] untouched here
-__global__ void finalize_ev_kernel(const double *partials, int nblocks, double *ev, int accumulate)
+// sums the per-CTA partial rows in a fixed order (lane-strided, then a shuffle tree) -> deterministic
+__global__ void finalize_ev_kernel(const double *partials, int nrows, double *ev, int accumulate)
 {
-  const int c = threadIdx.x;
+  const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;    // one warp per component, 7 warps
   if (c >= 7) return;
-  double s = accumulate ? ev[c] : 0.0;
-  for (int b = 0; b < nblocks; b++) s += partials[(size_t) b * 8 + c];
-  ev[c] = s;
+  double s = 0.0;
+  for (int b = lane; b < nrows; b += 32) s += partials[(size_t) b * 8 + c];
+  s = warp_sum(s);
+  if (lane == 0) ev[c] = (accumulate ? ev[c] : 0.0) + s;
 }
+
+}    // namespace mtpb200
+#include "mtp_kernels_v1.cuh"
+namespace mtpb200 {
 
 // ------------------------------------------------------------------------------------------------
 // Extrapolation grade: G = Bmat[n x Q] . Ainv^T, grade[row] = max_col |G|  (pair_mtp_extrapolation.cpp:347-358),

@@ -431,7 +431,7 @@ void compile_program(const Potential &p, Program &prog)
   pack_pass(fwd, prog.fwd);
 
   // reverse: per source, terms in reverse file order; levels visited from depth-1 down to 0
-  std::vector<std::vector<NodeList>> rev(prog.depth);
+  std::vector<std::vector<NodeList>> rev(std::max(prog.depth, 1));
   {
     std::vector<int> slot(M, -1);
     auto add = [&](int src, int a3, int other, int mult) {
@@ -447,11 +447,50 @@ void compile_program(const Potential &p, Program &prog)
       add(a1, a3, a0, mult);    // g[a1] += g[a3]*mult*m[a0]   (pair_mtp.cpp:231)
       add(a0, a3, a1, mult);    // g[a0] += g[a3]*mult*m[a1]   (pair_mtp.cpp:232)
     }
+    // basic moments that feed no product still need their adjoint (= the seed): give them an empty list
+    for (int k = 0; k < p.alpha_index_basic_count; k++)
+      if (slot[k] < 0) rev.back().push_back(NodeList{k, {}});
   }
   pack_pass(rev, prog.rev);
 
   prog.ginit.assign(M, 0.0);
   for (int s = 0; s < A; s++) prog.ginit[p.alpha_moment_mapping[s]] = p.linear_coeffs[s];
+
+  // ---- chunk form ----
+  std::vector<char> is_source(M, 0);
+  for (int e = 0; e < T; e++) is_source[times[4 * e]] = is_source[times[4 * e + 1]] = 1;
+  auto pack_chunk = [&](const std::vector<std::vector<NodeList>> &levels, bool reverse, ChunkPass &out) {
+    out = ChunkPass();
+    out.level_begin.push_back(0);
+    out.term_begin.push_back(0);
+    for (const auto &lv : levels) {
+      std::vector<const NodeList *> lists;
+      for (const auto &l : lv) lists.push_back(&l);
+      std::stable_sort(lists.begin(), lists.end(),
+                       [](const NodeList *a, const NodeList *b) { return a->terms.size() > b->terms.size(); });
+      for (const NodeList *l : lists) {
+        out.node.push_back(l->node);
+        out.init.push_back(reverse ? prog.ginit[l->node] : 0.0);
+        for (const ProgramTerm &t : l->terms) {
+          if (reverse && !is_source[t.a]) {
+            // g[a3] is never updated: it stays ginit[a3], fold it into the coefficient (drop exact zeros)
+            const double c = (double) t.mult * prog.ginit[t.a];
+            if (c == 0.0) continue;
+            out.term_idx.push_back(0xFFFFu | ((uint32_t) t.b << 16));
+            out.term_coef.push_back(c);
+          } else {
+            out.term_idx.push_back((uint32_t) t.a | ((uint32_t) t.b << 16));
+            out.term_coef.push_back((double) t.mult);
+          }
+        }
+        out.term_begin.push_back((int) out.term_idx.size());
+      }
+      out.level_begin.push_back((int) out.node.size());
+    }
+  };
+  if (M >= 0xFFFF) throw std::runtime_error("alpha_moments_count above 65534 is not supported.");
+  pack_chunk(fwd, false, prog.cfwd);
+  pack_chunk(rev, true, prog.crev);
 }
 
 }    // namespace mtpb200

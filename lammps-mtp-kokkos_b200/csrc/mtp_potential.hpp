@@ -65,8 +65,21 @@ struct ProgramPass {
   int ngroups() const { return (int) group_term_base.size(); }
 };
 
+// The same program in the form used by the CTA-per-atom-chunk kernel: the atoms of a chunk sit in the lanes
+// (moments stored [node][atom]), so every lane of a warp executes the SAME term and operand reads are
+// conflict-free rows; nodes of one level are dealt to the warps longest-list-first.
+struct ChunkPass {
+  std::vector<int> level_begin;     // [nlevels + 1] node-slot ranges, execution order
+  std::vector<int> node;            // [nslots]
+  std::vector<int> term_begin;      // [nslots + 1]
+  std::vector<uint32_t> term_idx;   // forward: a0 | a1 << 16;  reverse: a3 | other << 16, a3 == 0xFFFF: constant term
+  std::vector<double> term_coef;    // forward: mult;  reverse: mult, or mult * ginit[a3] for a constant term
+  std::vector<double> init;         // [nslots] reverse: ginit[node]; forward: unused (0)
+};
+
 struct Program {
   int depth = 0;                  // number of waves
+  ChunkPass cfwd, crev;
   std::vector<int> level;         // [M]
   ProgramPass fwd, rev;
   std::vector<double> ginit;      // [M]: dE/dm seed, g[map[s]] = xi_s (pair_mtp.cpp:217-218)
