@@ -122,6 +122,10 @@ mtp_handle *mtp_create(const mtp_params_host *params, int device);
 void mtp_destroy(mtp_handle *h);
 const char *mtp_last_error(void);
 int mtp_get_info(const mtp_handle *h, mtp_info *out);
+/* Host-only validation of a potential file: the same parser and contraction-program compiler as
+ * mtp_create_from_file(), no CUDA device touched (what PairMTP::coeff -> read_file does before any
+ * compute, pair_mtp.cpp:310,335-570).  out may be NULL; out->device = -1, out->chunksize = 0. */
+int mtp_potential_check(const char *path, int want_selection_state, mtp_info *out);
 /* Copy the parsed tables back out (sizes from mtp_get_info); any pointer may be NULL. */
 int mtp_get_tables(const mtp_handle *h, double *radial_basis_coeffs, int *alpha_index_basic,
                    int *alpha_index_times, int *alpha_moment_mapping, double *species_coeffs,

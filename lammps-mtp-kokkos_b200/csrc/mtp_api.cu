@@ -559,6 +559,37 @@ mtp_handle *mtp_create_from_file(const char *path, int want_selection_state, int
   return h;
 }
 
+int mtp_potential_check(const char *path, int want_selection_state, mtp_info *o)
+{
+  if (!path) return fail(MTP_ERR_ARG, "null path");
+  return guarded([&] {
+    Potential p;
+    Program prog;
+    parse_almtp(path, want_selection_state != 0, p);
+    compile_program(p, prog);
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->abi_version = MTP_B200_ABI_VERSION;
+    o->species_count = p.species_count;
+    o->radial_func_count = p.radial_func_count;
+    o->radial_basis_size = p.radial_basis_size;
+    o->alpha_moment_count = p.alpha_moment_count;
+    o->alpha_index_basic_count = p.alpha_index_basic_count;
+    o->alpha_index_times_count = p.alpha_index_times_count;
+    o->alpha_scalar_count = p.alpha_scalar_count;
+    o->max_alpha_index_basic = p.max_alpha_index_basic;
+    o->coeff_count = p.has_selection_state ? p.coeff_count : 0;
+    o->configuration_mode = p.configuration_mode;
+    o->has_selection_state = p.has_selection_state ? 1 : 0;
+    o->wave_count = prog.depth;
+    o->chunksize = 0;
+    o->device = -1;
+    o->min_cutoff = p.min_cutoff;
+    o->max_cutoff = p.max_cutoff;
+    o->scaling = p.scaling;
+  });
+}
+
 mtp_handle *mtp_create(const mtp_params_host *q, int device)
 {
   if (!q) {

@@ -74,6 +74,7 @@ def load_library():
     lib.mtp_destroy.argtypes = [C.c_void_p]
     lib.mtp_destroy.restype = None
     lib.mtp_last_error.restype = C.c_char_p
+    lib.mtp_potential_check.argtypes = [C.c_char_p, C.c_int, C.POINTER(MTPInfo)]
     lib.mtp_get_info.argtypes = [C.c_void_p, C.POINTER(MTPInfo)]
     lib.mtp_get_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 7
     lib.mtp_set_chunksize.argtypes = [C.c_void_p, C.c_int]
@@ -236,6 +237,14 @@ class MTPB200:
             self.close()
         except Exception:
             pass
+
+
+def potential_check(path: str, selection_state: bool = False) -> MTPInfo:
+    """Host-only parse + program compile of a potential file (no CUDA device needed)."""
+    lib = load_library()
+    info = MTPInfo()
+    _check(lib, lib.mtp_potential_check(os.fsencode(path), int(selection_state), C.byref(info)))
+    return info
 
 
 def fp64_peaks(device: int = -1):

@@ -233,12 +233,16 @@ int mtpref_compute(void *hv, int nlocal, int nghost, const double *x, const int 
     memcpy(f, h->fbuf.data(), sizeof(double) * 3 * (size_t) nall);
     ev[0] = h->pair->eng_vdwl;
     for (int k = 0; k < 6; k++) ev[1 + k] = h->pair->virial[k];
-    ev[7] = h->pair->pvector ? h->pair->pvector[0] : 0.0;
+    // pvector[0] is only written on grade steps (pair_mtp_extrapolation.cpp:381); report 0 otherwise
+    ev[7] = (h->extrap && extrapolation_flag) ? h->pair->pvector[0] : 0.0;
     if (eatom && h->pair->eflag_atom) memcpy(eatom, h->pair->eatom, sizeof(double) * nall);
     if (vatom && h->pair->vflag_atom)
       for (int i = 0; i < nall; i++)
         for (int k = 0; k < 6; k++) vatom[6 * (size_t) i + k] = h->pair->vatom[i][k];
-    if (grades && h->extrap) {
+    int iv_[10];
+    double dv_[3];
+    if (h->extrap) h->extrap->info(iv_, dv_);
+    if (grades && h->extrap && !iv_[9]) {    // extract_peratom is a fatal error in configuration mode (:644-645)
       int ncol;
       double *g = (double *) h->extrap->extract_peratom("extrapolation", ncol);
       if (g)
