@@ -46,6 +46,20 @@ def algorithmic_flops_per_atom(pot, n_list, n_cut):
     return 9.0 * n_list + n_cut * per_pair + 9.0 * T + 2.0 * A
 
 
+def algorithmic_flops_split(pot, n_list, n_cut):
+    """The same count apportioned to the kernels of the pipeline: the moment kernel owns
+    gather/cutoff, radial basis, powers, radial contraction and the m[k] accumulation (6 flop per k: nf, val, pw x2,
+    fma); the force kernel owns the Jacobian part (9 + 5 nz_k) and the contraction with dE/dm (6K + 6); the program
+    kernel owns the contraction tree forward/reverse and the energy."""
+    B, R, P = pot.radial_basis_size, pot.radial_funcs_count, pot.max_alpha_index_basic
+    K, T, A = pot.K, pot.T, pot.A
+    nz = (np.asarray(pot.alpha_index_basic)[:, 1:] != 0).sum(axis=1)
+    moments = 9.0 * n_list + n_cut * ((8 * B + 19) + 4 * (P - 1) + 4 * R * B + 6.0 * K)
+    forces = n_cut * (float((9 + 5 * nz).sum()) + 6 * K + 6)
+    program = 9.0 * T + 2.0 * A
+    return {"moments": moments, "forces": forces, "program": program}
+
+
 def algorithmic_bytes_per_atom(n_list):
     return 4.0 * n_list + 84.0
 
@@ -233,12 +247,9 @@ def main():
     variant = api.VARIANT_SMALL if args.variant == "small" else api.VARIANT_LARGE
     mtp = MTPB200(pot_path, selection_state=bool(cfg.get("active_set")), device=local_rank)
 
-    if world == 1:
-        sysm = harness.make_config(args.config, cells=cells)
-        halo = None
-    else:
-        from mtp_b200 import decomp
-        sysm, halo = decomp.make_rank_system(args.config, cells, brick_grid(world), rank, dev, mtp)
+    # one brick per rank on the grid {1, 2x1x1, 2x2x1, 2x2x2}; at N = 1 all six swaps are periodic self-images
+    from mtp_b200 import decomp
+    sysm, halo = decomp.make_rank_system(args.config, cells, brick_grid(world), rank, dev, mtp.lib)
     nlocal, nall = sysm.nlocal, sysm.nall
 
     # workload statistics for the roofline (listed / in-cutoff neighbors per atom)
@@ -263,13 +274,14 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
 
     def step_device():
+        # what LAMMPS does around Pair::compute every step: forward comm of x, zero f, compute, reverse comm of f,
+        # and the energy/virial all-reduce
+        halo.forward(t_x)
         t_f.zero_()
-        if halo is not None:
-            halo.forward(t_x)
         mtp.compute_device(t_x, t_type, t_ilist, t_nn, t_neigh, t_off, t_f, t_ev, eflag=1, vflag=1,
                            variant=variant, stream=stream)
-        if halo is not None:
-            halo.reverse(t_f)
+        halo.reverse(t_f)
+        halo.allreduce_ev(t_ev)
 
     def barrier():
         if world > 1:
@@ -282,7 +294,8 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    launches0 = api.kernel_launch_count()
+    launches0 = api.kernel_launch_count() + halo.launches
+    mtp.profile_enable(True)
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
@@ -292,7 +305,9 @@ def main():
         step_device()
         ev1[s].record()
     barrier()
-    launches = api.kernel_launch_count() - launches0
+    launches = api.kernel_launch_count() + halo.launches - launches0
+    prof = mtp.profile_read()
+    mtp.profile_enable(False)
     step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
     total_ms = float(sum(step_ms))
     if world > 1:
@@ -308,6 +323,7 @@ def main():
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
     e2e = None
     if world == 1:
+        # N = 1: the reference-facing C-ABI call with HOST buffers (what a host-resident LAMMPS hands the pair style)
         keep, hx = pinned_like(sysm.x)
         k2, htype = pinned_like(sysm.type)
         k3, hnn = pinned_like(sysm.numneigh)
@@ -329,11 +345,51 @@ def main():
         nid = nlocal
         h2d = 24 * nall + 4 * nall + 24 * nall + 4 * sysm.neigh.size + 8 * nid + 4 * nid + 4 * nlocal
         d2h = 24 * nall + 64
-        e2e = {"value": nlocal / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "note": "mtp_compute_host per step: H2D x,type,f and the full neighbor list (re-sent every step), "
-                       "kernels, D2H f + energy/virial record; host buffers pinned",
-               "energy_matches_device_path": bool(abs(res.ev[0] - energy) <= 1e-9 * abs(energy))}
+        e2e_energy = float(res.ev[0])
+        note = ("mtp_compute_host per step: H2D x,type,f and the full neighbor list (re-sent every step), kernels, "
+                "D2H f + energy/virial record; host buffers pinned; wall clock around the blocking call")
+    else:
+        # N > 1: same metric through the public Python API: per step H2D of the owned positions, types and the
+        # neighbor list from pinned host memory, device halo exchange, kernels, D2H of the owned forces + EV record
+        hx_t, _ = pinned_like(sysm.x[:nlocal])
+        ht_t, _ = pinned_like(sysm.type)
+        hnn_t, _ = pinned_like(sysm.numneigh)
+        hne_t, _ = pinned_like(sysm.neigh)
+        hof_t, _ = pinned_like(sysm.offsets)
+        hf_t = torch.empty((nlocal, 3), dtype=torch.float64, pin_memory=True)
+        hev_t = torch.empty(8, dtype=torch.float64, pin_memory=True)
+
+        def step_e2e():
+            t_x[:nlocal].copy_(hx_t, non_blocking=True)
+            t_type.copy_(ht_t, non_blocking=True)
+            t_nn.copy_(hnn_t, non_blocking=True)
+            t_neigh.copy_(hne_t, non_blocking=True)
+            t_off.copy_(hof_t, non_blocking=True)
+            step_device()
+            hf_t.copy_(t_f[:nlocal], non_blocking=True)
+            hev_t.copy_(t_ev, non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        h2d = 24 * nlocal + 4 * nall + 4 * nall + 4 * sysm.neigh.size + 8 * (nall + 1)
+        d2h = 24 * nlocal + 64
+        e2e_energy = float(hev_t[0])
+        note = ("per rank and step: H2D owned x, type, numneigh/offsets/neighbor list from pinned memory, device halo "
+                "forward (NCCL send/recv), kernels, halo reverse, EV all-reduce, D2H owned f + EV record; wall clock, "
+                "max over ranks; bytes are per rank")
+    e2e = {"value": world * nlocal / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "note": note,
+           "energy_matches_device_path": bool(abs(e2e_energy - energy) <= 1e-9 * abs(energy))}
 
     if rank != 0:
         if world > 1:
@@ -341,24 +397,42 @@ def main():
         return
 
     dfma, dmma = peaks
-    achieved_tf = flops_atom * nlocal / (ms_per_step * 1e-3) / 1e12
-    hbm_peak = 6555.5
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         hbm_src = "MEASURED_PEAKS.json"
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    split = algorithmic_flops_split(pot, n_list, n_cut)
+    kernels = {}
+    for cls, (ms, spans) in prof.items():
+        if spans == 0:
+            continue
+        k = {"ms_per_step": ms / args.steps, "launches_per_step": spans / args.steps}
+        if cls in split:
+            k["algorithmic_flops_per_atom"] = split[cls]
+            k["achieved_tflops"] = split[cls] * nlocal / (ms / args.steps * 1e-3) / 1e12
+            k["frac_of_fp64_peak"] = k["achieved_tflops"] / dfma
+        kernels[cls] = k
+    dom = max((c for c in kernels if c in split), key=lambda c: kernels[c]["ms_per_step"], default=None)
+    pipe_ms = sum(k["ms_per_step"] for k in kernels.values())
+    achieved_tf = flops_atom * nlocal / (pipe_ms * 1e-3) / 1e12 if pipe_ms else 0.0
     achieved_gbs = bytes_atom * nlocal / (ms_per_step * 1e-3) / 1e9
-    roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": dfma, "unit": "TFLOP/s", "frac": achieved_tf / dfma,
-                "traffic": None, "kernel": "mtp_site_kernel (fused gather / moments / contraction tree / reverse / force)",
-                "peak_source": "FP64 DFMA peak measured in this run by mtp_fp64_peak (DMMA: %.2f TFLOP/s); "
+    roofline = {"bound": "fp64", "unit": "TFLOP/s", "peak": dfma,
+                "peak_source": "FP64 DFMA peak measured in this run by mtp_fp64_peak (DMMA m8n8k4: %.2f TFLOP/s); "
                                "MEASURED_PEAKS.json has no FP64 entry" % dmma,
-                "algorithmic_flops_per_atom": flops_atom, "algorithmic_bytes_per_atom": bytes_atom,
-                "neighbors_listed": n_list, "neighbors_in_cutoff": n_cut,
+                "kernel": dom, "achieved": kernels[dom]["achieved_tflops"] if dom else None,
+                "frac": kernels[dom]["frac_of_fp64_peak"] if dom else None, "traffic": None,
+                "duration_ms": kernels[dom]["ms_per_step"] / kernels[dom]["launches_per_step"] if dom else None,
+                "duration_note": "average launch duration of the dominant kernel: CUDA events recorded by the library on "
+                                 "the launch stream around every launch of the timed region (mtp_profile_read)",
+                "kernels": kernels,
+                "pipeline": {"ms_per_step_kernels": pipe_ms, "algorithmic_flops_per_atom": flops_atom,
+                             "achieved": achieved_tf, "frac": achieved_tf / dfma,
+                             "note": "all kernels of one force evaluation; flops counted as written in pair_mtp.cpp "
+                                     "(SURVEY.md 8d), i.e. including the Jacobian the reference forms and this design never does"},
+                "algorithmic_bytes_per_atom": bytes_atom, "neighbors_listed": n_list, "neighbors_in_cutoff": n_cut,
                 "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                        "peak_source": hbm_src},
-                "duration_ms": ms_per_step, "duration_note": "CUDA events around the whole step (pack + site kernel + "
-                                                             "finalize); the site kernel is >99% of it (profiles/)"}
+                        "peak_source": hbm_src}}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -369,6 +443,8 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload, "atoms_per_gpu": nlocal, "ghosts_per_gpu": nall - nlocal,
+                       "parallelism": "brick grid %dx%dx%d, one rank per GPU, NCCL send/recv halo (%d B/rank/step)" % (
+                           *brick_grid(world), halo.bytes_per_step),
                        "l2": "256 MiB write between timed iterations (L2 flush), per-step CUDA events summed",
                        "variant": args.variant, "flags": "eflag=1 vflag=1"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

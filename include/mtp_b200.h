@@ -157,6 +157,21 @@ int mtp_halo_unpack_add_f(double *f, const int *sendlist, int n, const double *b
 /* FP64 vector (DFMA) and FP64 tensor (mma.sync.m8n8k4.f64, DMMA) peak of the device, in TFLOP/s. */
 int mtp_fp64_peak(int device, double *dfma_tflops, double *dmma_tflops);
 
+/* Per-kernel-class device timing for bench.py's roofline: when enabled, mtp_compute() brackets the launches
+ * of each class with CUDA events on the launch stream; mtp_profile_read() synchronises the device, returns
+ * the accumulated milliseconds and span counts per class since the previous read, and resets them. */
+#define MTP_PROF_PACK 0      /* x/type -> 32-byte records */
+#define MTP_PROF_GATHER 1    /* neighbor gather + cutoff mask + radial basis */
+#define MTP_PROF_MOMENTS 2   /* basic moments */
+#define MTP_PROF_PROGRAM 3   /* contraction program forward, site energy, reverse mode */
+#define MTP_PROF_FORCES 4    /* per-pair forces, scatter, virial, candidate vector */
+#define MTP_PROF_GRADE 5     /* extrapolation grade (DMMA) */
+#define MTP_PROF_FINALIZE 6  /* energy / virial reduction */
+#define MTP_PROF_SITE 7      /* generic fused site kernel (non-standard potentials) */
+#define MTP_PROF_CLASSES 8
+int mtp_profile_enable(mtp_handle *h, int on);
+int mtp_profile_read(mtp_handle *h, double *ms /*[MTP_PROF_CLASSES]*/, long long *count /*[MTP_PROF_CLASSES]*/);
+
 /* number of kernels launched by this library since load (bench.py's gpu_launches claim) */
 long long mtp_kernel_launch_count(void);
 

@@ -147,6 +147,15 @@ struct mtp_handle {
   int pl_grid_m = 0, pl_grid_p = 0, pl_grid_f[2] = {0, 0};
   size_t pl_smem_m = 0, pl_smem_f[2] = {0, 0};
   size_t smem[2] = {0, 0};
+  // optional per-kernel-class device timing (mtp_profile_enable): CUDA events recorded on the launch stream
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span {
+    int cls;
+    size_t e0, e1;
+  };
+  std::vector<Span> spans;
 };
 
 namespace {
@@ -344,6 +353,36 @@ void upload_potential(mtp_handle *h)
   }
 }
 
+// RAII span: records an event pair around the launches of one kernel class when profiling is on
+struct ProfSpan {
+  mtp_handle *h;
+  cudaStream_t st;
+  size_t e0 = 0;
+  int cls;
+  static size_t grab(mtp_handle *h)
+  {
+    if (h->ev_used == h->ev_pool.size()) {
+      cudaEvent_t e;
+      CUDA_CHECK(cudaEventCreate(&e));
+      h->ev_pool.push_back(e);
+    }
+    return h->ev_used++;
+  }
+  ProfSpan(mtp_handle *h_, int cls_, cudaStream_t st_) : h(h_), st(st_), cls(cls_)
+  {
+    if (!h->profile) return;
+    e0 = grab(h);
+    CUDA_CHECK(cudaEventRecord(h->ev_pool[e0], st));
+  }
+  ~ProfSpan()
+  {
+    if (!h->profile) return;
+    const size_t e1 = grab(h);
+    cudaEventRecord(h->ev_pool[e1], st);
+    h->spans.push_back({cls, e0, e1});
+  }
+};
+
 void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
 {
   const DevPotential &d = h->dpot;
@@ -355,6 +394,7 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
   // pack positions + species into 32-byte records
   h->d_xt.ensure((size_t) (a.nall > 0 ? a.nall : 1));
   if (a.nall > 0) {
+    ProfSpan sp(h, MTP_PROF_PACK, st);
     pack_xt_kernel<<<(a.nall + 255) / 256, 256, 0, st>>>(a.nall, a.x, a.type, h->d_xt.p);
     g_launches++;
   }
@@ -432,22 +472,32 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
     if (pipeline) {
       const V1Entry &E = kV1[h->v1_entry];
       const int gm = std::max(1, std::min(h->pl_grid_m, (n + W - 1) / W));
-      E.moments<<<gm, W * 32, h->pl_smem_m, st>>>(d, h->v1tab, s, h->d_mb.p, ld);
+      {
+        ProfSpan sp(h, MTP_PROF_MOMENTS, st);
+        E.moments<<<gm, W * 32, h->pl_smem_m, st>>>(d, h->v1tab, s, h->d_mb.p, ld);
+      }
       const int gp = std::max(1, std::min(grid_p_cap, (n + na - 1) / na));
       double *part_p = h->d_partials.p + (size_t) rows_used * 8;
-      if (grade) mtp_program_kernel<true><<<gp, 512, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, part_p);
-      else
-        mtp_program_kernel<false><<<gp, 512, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, part_p);
+      {
+        ProfSpan sp(h, MTP_PROF_PROGRAM, st);
+        if (grade) mtp_program_kernel<true><<<gp, 512, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, part_p);
+        else
+          mtp_program_kernel<false><<<gp, 512, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, part_p);
+      }
       rows_used += gp;
       const int gf = std::max(1, std::min(h->pl_grid_f[gi], (n + W - 1) / W));
       double *part_f = h->d_partials.p + (size_t) rows_used * 8;
-      E.forces[gi]<<<gf, W * 32, h->pl_smem_f[gi], st>>>(d, h->v1tab, s, h->d_gb.p, ld, part_f);
+      {
+        ProfSpan sp(h, MTP_PROF_FORCES, st);
+        E.forces[gi]<<<gf, W * 32, h->pl_smem_f[gi], st>>>(d, h->v1tab, s, h->d_gb.p, ld, part_f);
+      }
       rows_used += gf;
       g_launches += 3;
     } else {
       const int w = h->warps[gi];
       const int grid = std::max(1, std::min(h->grid_cap[gi], (n + w - 1) / w));
       s.partials = h->d_partials.p + (size_t) rows_used * 8;
+      ProfSpan sp(h, MTP_PROF_SITE, st);
       if (grade) mtp_site_kernel<true><<<grid, w * 32, h->smem[1], st>>>(d, s, w);
       else
         mtp_site_kernel<false><<<grid, w * 32, h->smem[0], st>>>(d, s, w);
@@ -455,6 +505,7 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
       g_launches++;
     }
     if (grade && n > 0) {
+      ProfSpan sp(h, MTP_PROF_GRADE, st);
       if (cfg) {
         cand_colsum_kernel<<<(d.Q + 127) / 128, 128, 0, st>>>(h->d_cand.p, n, h->qpad, d.Q, h->d_cfg.p, 1);
         g_launches++;
@@ -469,8 +520,11 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
       }
     }
   }
-  finalize_ev_kernel<<<1, 7 * 32, 0, st>>>(h->d_partials.p, rows_used, a.ev_out, 1);
-  g_launches++;
+  {
+    ProfSpan sp(h, MTP_PROF_FINALIZE, st);
+    finalize_ev_kernel<<<1, 7 * 32, 0, st>>>(h->d_partials.p, rows_used, a.ev_out, 1);
+    g_launches++;
+  }
   if (cfg) {
     const long long nat = a.natoms_total > 0 ? a.natoms_total : a.inum;
     cfg_grade_kernel<<<1, 256, 0, st>>>(h->d_ainv.p, h->qpad, d.Q, h->d_cfg.p, nat > 0 ? 1.0 / (double) nat : 0.0,
@@ -641,6 +695,7 @@ void mtp_destroy(mtp_handle *h)
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->hstream) cudaStreamDestroy(h->hstream);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   delete h;
 }
 
@@ -693,6 +748,34 @@ int mtp_set_chunksize(mtp_handle *h, int chunksize)
   if (!h || chunksize < 1) return fail(MTP_ERR_ARG, "chunksize must be >= 1");
   h->chunksize = chunksize;
   return MTP_OK;
+}
+
+int mtp_profile_enable(mtp_handle *h, int on)
+{
+  if (!h) return fail(MTP_ERR_ARG, "null handle");
+  h->profile = on != 0;
+  return MTP_OK;
+}
+
+int mtp_profile_read(mtp_handle *h, double *ms, long long *count)
+{
+  if (!h || !ms || !count) return fail(MTP_ERR_ARG, "null argument");
+  return guarded([&] {
+    set_device(h);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    for (int c = 0; c < MTP_PROF_CLASSES; c++) {
+      ms[c] = 0.0;
+      count[c] = 0;
+    }
+    for (const auto &sp : h->spans) {
+      float t = 0;
+      CUDA_CHECK(cudaEventElapsedTime(&t, h->ev_pool[sp.e0], h->ev_pool[sp.e1]));
+      ms[sp.cls] += t;
+      count[sp.cls]++;
+    }
+    h->spans.clear();
+    h->ev_used = 0;
+  });
 }
 
 int mtp_compute(mtp_handle *h, const mtp_compute_args *a)

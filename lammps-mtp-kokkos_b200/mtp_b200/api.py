@@ -83,6 +83,8 @@ def load_library():
     lib.mtp_compute_host.argtypes = [C.c_void_p, C.POINTER(MTPComputeArgs), C.c_int]
     lib.mtp_halo_pack_x.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _dp, C.c_void_p, C.c_void_p]
     lib.mtp_halo_unpack_add_f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.mtp_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    lib.mtp_profile_read.argtypes = [C.c_void_p, _dp, _llp]
     lib.mtp_fp64_peak.argtypes = [C.c_int, _dp, _dp]
     lib.mtp_kernel_launch_count.restype = C.c_longlong
     _lib = lib
@@ -223,6 +225,18 @@ class MTPB200:
         a.grades, a.cfg_candidate, a.within_cutoff = ptr(grades), ptr(cfg_candidate), ptr(within)
         a.stream = stream
         _check(self.lib, self.lib.mtp_compute(self.h, C.byref(a)))
+
+    PROF_CLASSES = ("pack", "gather", "moments", "program", "forces", "grade", "finalize", "site")
+
+    def profile_enable(self, on: bool = True):
+        _check(self.lib, self.lib.mtp_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """{class: (ms, spans)} of device time per kernel class since the last read."""
+        ms = (C.c_double * 8)()
+        cnt = (C.c_longlong * 8)()
+        _check(self.lib, self.lib.mtp_profile_read(self.h, ms, cnt))
+        return {n: (ms[i], cnt[i]) for i, n in enumerate(self.PROF_CLASSES)}
 
     def synchronize(self):
         _check(self.lib, self.lib.mtp_synchronize(self.h))

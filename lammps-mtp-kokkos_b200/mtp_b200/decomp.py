@@ -1,0 +1,227 @@
+"""Brick spatial decomposition + ghost-atom halo exchange, one rank per GPU.
+
+Stands in for what upstream LAMMPS's ``Comm`` does around the pair style (pair_mtp.cpp:81-88,113,315
+rely on it: only ``inum`` owned centres are evaluated, ghosts are reached through the neighbor list and
+their forces are returned with ``newton on``):
+
+* setup: LAMMPS's six-swap scheme -- per dimension, atoms within ``r_cut + skin`` of the low / high face
+  (including ghosts received in earlier dimensions, so edges and corners come for free) are sent to the
+  minus / plus neighbor brick, shifted by the global box length when they cross the periodic boundary;
+* every step: ``forward`` packs ghost-source positions on the device (``mtp_halo_pack_x``), exchanges
+  them with grouped NCCL send/recv over NVLink and lands them directly in the ghost rows of ``x``;
+  ``reverse`` sends the ghost rows of ``f`` back and scatter-adds them (``mtp_halo_unpack_add_f``);
+  energies/virials need one 7-double all-reduce (``allreduce_ev``).
+
+The transport is ``torch.distributed`` (NCCL on GPUs; gloo in the CPU tests, where pack/unpack run as
+torch index ops -- host-logic coverage only, the product path is the CUDA one).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import harness
+
+
+def brick_grid(n: int):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n]
+
+
+def rank_coords(rank: int, grid):
+    return (rank % grid[0], (rank // grid[0]) % grid[1], rank // (grid[0] * grid[1]))
+
+
+def coords_rank(c, grid):
+    return (c[0] % grid[0]) + grid[0] * ((c[1] % grid[1]) + grid[1] * (c[2] % grid[2]))
+
+
+@dataclass
+class Swap:
+    dim: int
+    peer_send: int            # rank the packed rows go to
+    peer_recv: int            # rank the ghost rows come from
+    sendlist: torch.Tensor    # int32 [n_send] rows of x to pack
+    shift: np.ndarray         # [3] periodic shift added while packing
+    recv_first: int           # first ghost row filled by this swap
+    recv_n: int
+    sendbuf: torch.Tensor | None = None     # [n_send, 3] f64
+    recvbuf: torch.Tensor | None = None     # [recv_n, 3] f64 (reverse direction)
+
+
+class Halo:
+    """Per-step forward (x) / reverse (f) ghost exchange for one rank."""
+
+    def __init__(self, swaps, rank, world, device, lib=None):
+        self.swaps = swaps
+        self.rank, self.world, self.device = rank, world, device
+        self.lib = lib            # ctypes handle of libmtp_b200.so when on CUDA
+        self.cuda = device.type == "cuda"
+        for s in swaps:
+            s.sendbuf = torch.empty((len(s.sendlist), 3), dtype=torch.float64, device=device)
+            s.recvbuf = torch.empty((len(s.sendlist), 3), dtype=torch.float64, device=device)
+        self.bytes_per_step = sum(2 * 24 * len(s.sendlist) for s in swaps if s.peer_send != rank)
+        self.launches = 0
+
+    # -- pack / unpack: CUDA kernels of the C ABI on the GPU, index ops on the CPU (tests only)
+    def _pack(self, x, s: Swap, out):
+        n = len(s.sendlist)
+        if n == 0:
+            return
+        if self.cuda:
+            import ctypes as C
+            sh = (C.c_double * 3)(*s.shift)
+            rc = self.lib.mtp_halo_pack_x(x.data_ptr(), s.sendlist.data_ptr(), n, sh, out.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream)
+            assert rc == 0
+            self.launches += 1
+        else:
+            out.copy_(x.index_select(0, s.sendlist.long()) + torch.from_numpy(s.shift))
+
+    def _unpack_add(self, f, s: Swap, buf):
+        n = len(s.sendlist)
+        if n == 0:
+            return
+        if self.cuda:
+            rc = self.lib.mtp_halo_unpack_add_f(f.data_ptr(), s.sendlist.data_ptr(), n, buf.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream)
+            assert rc == 0
+            self.launches += 1
+        else:
+            f.index_add_(0, s.sendlist.long(), buf.clone())
+
+    def _by_dim(self):
+        for d in range(3):
+            grp = [s for s in self.swaps if s.dim == d]
+            if grp:
+                yield grp
+
+    def forward(self, x: torch.Tensor):
+        """Ghost rows of x <- owners' current positions (LAMMPS Comm::forward_comm)."""
+        for grp in self._by_dim():
+            ops, reqs = [], []
+            for s in grp:
+                ghost = x[s.recv_first: s.recv_first + s.recv_n]
+                if s.peer_send == self.rank:
+                    self._pack(x, s, ghost)           # periodic self-image: pack straight into the ghost rows
+                else:
+                    self._pack(x, s, s.sendbuf)
+            for s in grp:
+                if s.peer_send != self.rank and len(s.sendlist):
+                    ops.append(dist.P2POp(dist.isend, s.sendbuf, s.peer_send))
+            for s in grp:
+                if s.peer_recv != self.rank and s.recv_n:
+                    ops.append(dist.P2POp(dist.irecv, x[s.recv_first: s.recv_first + s.recv_n], s.peer_recv))
+            if ops:
+                reqs = dist.batch_isend_irecv(ops)
+                for r in reqs:
+                    r.wait()
+
+    def reverse(self, f: torch.Tensor):
+        """Owners' f += ghost rows of f (LAMMPS Comm::reverse_comm, newton on), swaps in reverse order."""
+        for grp in reversed(list(self._by_dim())):
+            ops = []
+            for s in grp:
+                if s.peer_recv != self.rank and s.recv_n:
+                    ops.append(dist.P2POp(dist.isend, f[s.recv_first: s.recv_first + s.recv_n], s.peer_recv))
+            for s in grp:
+                if s.peer_send != self.rank and len(s.sendlist):
+                    ops.append(dist.P2POp(dist.irecv, s.recvbuf, s.peer_send))
+            if ops:
+                for r in dist.batch_isend_irecv(ops):
+                    r.wait()
+            for s in grp:
+                if s.peer_send == self.rank:
+                    self._unpack_add(f, s, f[s.recv_first: s.recv_first + s.recv_n])
+                else:
+                    self._unpack_add(f, s, s.recvbuf)
+
+    def allreduce_ev(self, ev: torch.Tensor):
+        """E + 6 virial components: SUM over ranks; ev[7] (max grade): MAX (pair_mtp_extrapolation.cpp:369)."""
+        if self.world > 1:
+            dist.all_reduce(ev[:7], op=dist.ReduceOp.SUM)
+            dist.all_reduce(ev[7:8], op=dist.ReduceOp.MAX)
+
+
+def _exchange_arrays(send_to, recv_from, arrays, device, rank):
+    """Setup-time exchange of numpy arrays with two peers (one op group): returns what recv_from sent."""
+    metas = [(a.shape, str(a.dtype)) for a in arrays]
+    gathered = [None] * dist.get_world_size()
+    dist.all_gather_object(gathered, (rank, send_to, metas))
+    peer_metas = None
+    for (r, dst, m) in gathered:
+        if r == recv_from and dst == rank:
+            peer_metas = m
+    assert peer_metas is not None
+    sends = [torch.from_numpy(np.ascontiguousarray(a)).to(device) for a in arrays]
+    recvs = [torch.empty(shape, dtype=getattr(torch, {"float64": "float64", "int32": "int32"}[dt]), device=device)
+             for (shape, dt) in peer_metas]
+    ops = [dist.P2POp(dist.isend, t, send_to) for t in sends if t.numel()]
+    ops += [dist.P2POp(dist.irecv, t, recv_from) for t in recvs if t.numel()]
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    return [t.cpu().numpy() for t in recvs]
+
+
+def build_rank_system(x_own, types_own, sublo, subhi, grid, rank, gbox, cutoff, skin, device, lib=None):
+    """Ghost shell + send lists for this rank's brick [sublo, subhi) of the periodic global box ``gbox``."""
+    world = grid[0] * grid[1] * grid[2]
+    me = rank_coords(rank, grid)
+    rghost = cutoff + skin
+    x = np.ascontiguousarray(x_own, dtype=np.float64)
+    t = np.ascontiguousarray(types_own, dtype=np.int32)
+    nlocal = len(x)
+    swaps = []
+    for d in range(3):
+        if rghost >= (subhi[d] - sublo[d]):
+            raise ValueError("ghost cutoff exceeds the brick length; use a larger per-GPU box")
+        lo = np.nonzero(x[:, d] < sublo[d] + rghost)[0].astype(np.int32)
+        hi = np.nonzero(x[:, d] >= subhi[d] - rghost)[0].astype(np.int32)
+        sh_lo, sh_hi = np.zeros(3), np.zeros(3)
+        if me[d] == 0:
+            sh_lo[d] = gbox[d]
+        if me[d] == grid[d] - 1:
+            sh_hi[d] = -gbox[d]
+        cm, cp = list(me), list(me)
+        cm[d] -= 1
+        cp[d] += 1
+        minus, plus = coords_rank(cm, grid), coords_rank(cp, grid)
+        first = len(x)
+        # this rank's lo-send lands on `minus`; what lands here first comes from `plus` (its lo-send), then
+        # from `minus` (its hi-send)
+        if grid[d] == 1:
+            got = [(x[lo] + sh_lo, t[lo]), (x[hi] + sh_hi, t[hi])]
+        else:
+            a = _exchange_arrays(minus, plus, [x[lo] + sh_lo, t[lo]], device, rank)
+            b = _exchange_arrays(plus, minus, [x[hi] + sh_hi, t[hi]], device, rank)
+            got = [(a[0].reshape(-1, 3), a[1]), (b[0].reshape(-1, 3), b[1])]
+        n_a, n_b = len(got[0][0]), len(got[1][0])
+        swaps.append(Swap(d, minus, plus, torch.from_numpy(lo).to(device), sh_lo, first, n_a))
+        swaps.append(Swap(d, plus, minus, torch.from_numpy(hi).to(device), sh_hi, first + n_a, n_b))
+        x = np.concatenate([x, got[0][0], got[1][0]])
+        t = np.concatenate([t, got[0][1], got[1][1]])
+    x = np.ascontiguousarray(x)
+    t = np.ascontiguousarray(t.astype(np.int32))
+    numneigh, offsets, flat = harness.neighbor_list(x, nlocal, rghost)
+    owner = np.full(len(x), -1, dtype=np.int32)
+    owner[:nlocal] = np.arange(nlocal, dtype=np.int32)
+    sysm = harness.System(box=np.asarray(gbox, dtype=np.float64), nlocal=nlocal, x=x, type=t, owner=owner,
+                          ilist=np.arange(nlocal, dtype=np.int32), numneigh=numneigh, offsets=offsets, neigh=flat,
+                          rlist=rghost)
+    return sysm, Halo(swaps, rank, world, device, lib)
+
+
+def make_rank_system(config, cells, grid, rank, device, lib=None, cutoff=5.0, skin=2.0, jitter=0.05):
+    """BASELINE.json weak-scaling layout: the per-GPU box of ``config`` replicated on the brick grid."""
+    cfg = harness.CONFIGS[config]
+    x, box = harness.lattice(cfg["kind"], cfg["a"], cells or cfg["cells"], jitter=jitter, seed=2024)
+    types = harness.random_types(x.shape[0], cfg["fractions"], cfg["type_seed"])
+    me = np.array(rank_coords(rank, grid), dtype=np.float64)
+    sublo = me * box
+    return build_rank_system(x + sublo, types, sublo, sublo + box, grid, rank, box * np.array(grid), cutoff, skin,
+                             device, lib)

@@ -1,0 +1,64 @@
+"""Worker of tests/test_decomp_gloo.py (run under torch.distributed.run, gloo, CPU).
+
+Every rank builds its brick + halo, displaces its owned atoms, runs forward halo -> pair compute (the CPU
+oracle stands in for the CUDA kernels: tests may use it as the checker) -> reverse halo -> all-reduce, and
+rank 0 compares against the same global system evaluated in one piece.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "lammps-mtp-kokkos_b200"), os.path.join(ROOT, "oracle")):
+    sys.path.insert(0, p)
+
+from mtp_b200 import almtp, decomp, harness  # noqa: E402
+from oracle_py import OracleMTP  # noqa: E402
+
+
+def main():
+    out = sys.argv[1]
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    grid = decomp.brick_grid(world)
+    dev = torch.device("cpu")
+    cells = (5, 5, 5)
+    pot = almtp.random_potential(10, 2)
+    sysm, halo = decomp.make_rank_system(2, cells, grid, rank, dev)
+    nlocal = sysm.nlocal
+    # move the owned atoms after setup (same displacement field in every brick keeps the global reference simple)
+    disp = np.random.default_rng(99).uniform(-0.05, 0.05, size=(nlocal, 3))
+    x = torch.from_numpy(sysm.x.copy())
+    x[:nlocal] += torch.from_numpy(disp)
+    stale_ghosts = x[nlocal:].clone()
+    halo.forward(x)
+    assert not torch.equal(stale_ghosts, x[nlocal:])
+    orc = OracleMTP(pot)
+    r = orc.compute(x.numpy(), sysm.type, sysm.ilist, sysm.numneigh, sysm.neigh, sysm.offsets, eflag=3, vflag=5)
+    f = torch.from_numpy(r.f.copy())
+    halo.reverse(f)
+    ev = torch.from_numpy(r.ev.copy())
+    halo.allreduce_ev(ev)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (x[:nlocal].numpy(), sysm.type[:nlocal], f[:nlocal].numpy(), r.eatom[:nlocal]))
+    if rank == 0:
+        cfg = harness.CONFIGS[2]
+        _, box = harness.lattice(cfg["kind"], cfg["a"], cells)
+        gbox = box * np.array(grid)
+        gx = np.concatenate([g[0] for g in gathered])
+        gt = np.concatenate([g[1] for g in gathered])
+        gs = harness.make_system(np.mod(gx, gbox), gt, gbox, 5.0, 2.0)
+        ref = orc.compute(gs.x, gs.type, gs.ilist, gs.numneigh, gs.neigh, gs.offsets, eflag=3, vflag=5)
+        fref = gs.reverse_comm(ref.f)
+        np.savez(out, f=np.concatenate([g[2] for g in gathered]), fref=fref, ev=ev.numpy(), evref=ref.ev,
+                 eatom=np.concatenate([g[3] for g in gathered]), eatomref=ref.eatom[: gs.nlocal],
+                 ghosts=np.array([sysm.nall - nlocal]), halo_bytes=np.array([halo.bytes_per_step]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
