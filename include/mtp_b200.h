@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MTP_B200_ABI_VERSION 1
+#define MTP_B200_ABI_VERSION 2
 
 #define MTP_OK 0
 #define MTP_ERR_ARG (-1)      /* bad argument */
@@ -111,6 +111,9 @@ typedef struct {
   double *cfg_candidate;          /* [Q] or NULL: configuration-mode candidate vector, overwritten */
   unsigned char *within_cutoff;   /* optional: 1/0 per neighbor entry, same indexing as `neighbors` */
   void *stream;                   /* cudaStream_t (mtp_compute only) */
+  int max_numneigh;               /* upper bound of numneigh[] over the listed centres, e.g. d_neighbors.extent(1)
+                                     of the LAMMPS-KOKKOS list; 0 = unknown (mtp_compute then reduces numneigh on the
+                                     device and waits for that one integer) */
 } mtp_compute_args;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */

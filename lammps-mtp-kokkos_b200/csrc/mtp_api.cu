@@ -109,6 +109,23 @@ struct ChunkBufs {
   }
 };
 
+struct FlatBufs {
+  DevBuf<int> begin;
+  DevBuf<uint4> terms;
+  DevFlatPass upload(const FlatPass &f)
+  {
+    begin.upload(f.stream_begin, 0);
+    static_assert(sizeof(FlatTerm) == sizeof(uint4), "FlatTerm packing");
+    terms.upload(reinterpret_cast<const uint4 *>(f.terms.data()), f.terms.size(), 0);
+    DevFlatPass d;
+    d.stream_begin = begin.p;
+    d.terms = terms.p;
+    d.nlevels = f.nlevels;
+    d.vw = f.vw;
+    return d;
+  }
+};
+
 struct mtp_handle {
   Potential pot;
   Program prog;
@@ -122,6 +139,8 @@ struct mtp_handle {
   DevBuf<int> d_map;
   PassBufs d_fwd, d_rev;
   ChunkBufs d_cfwd, d_crev;
+  FlatBufs d_ffwd[2], d_frev[2];
+  int pl_na[2] = {0, 0};          // atoms per CTA of the program kernel: throughput shape, latency shape
   DevPotential dpot{};
   // work buffers (grow-only)
   DevBuf<AtomRec> d_xt;
@@ -133,6 +152,7 @@ struct mtp_handle {
   DevBuf<long long> h_offsets;
   DevBuf<unsigned char> h_within;
   long long h_list_len = 0;
+  int h_maxnn = 0;
   cudaStream_t hstream = nullptr;
   // register-resident kernel family (mtp_kernels_v1.cuh), -1 = generic kernel only
   int v1_entry = -1;
@@ -147,6 +167,14 @@ struct mtp_handle {
   int pl_grid_m = 0, pl_grid_p = 0, pl_grid_f[2] = {0, 0};
   size_t pl_smem_m = 0, pl_smem_f[2] = {0, 0};
   size_t smem[2] = {0, 0};
+  // register-resident pair stages for standard basic-moment sets (mtp_kernels_v2.cuh), -1 = not applicable
+  int v2_entry = -1;
+  DevBuf<short> d_slot_to_k;
+  DevBuf<double> d_pfld;
+  DevBuf<int> d_pj, d_pjt, d_pcnt, d_maxnn;
+  int v2_grid_g = 0, v2_grid_m = 0, v2_grid_f = 0, v2_ab = 0;
+  size_t v2_smem_g = 0, v2_smem_f = 0;
+  int v2_chunk = 0;
   // optional per-kernel-class device timing (mtp_profile_enable): CUDA events recorded on the launch stream
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -163,6 +191,8 @@ namespace {
 void set_device(const mtp_handle *h) { CUDA_CHECK(cudaSetDevice(h->device)); }
 
 // dynamic shared memory a kernel may request: opt-in limit minus its static allocation
+size_t program_smem_bytes(int M, int na) { return ((((size_t) M + 1) * (na + 1) * 8 + 15) & ~(size_t) 15) * 2; }
+
 size_t max_dynamic_smem(const void *fn, size_t optin)
 {
   cudaFuncAttributes fa;
@@ -215,10 +245,77 @@ bool build_v1_tables(mtp_handle *h, int e)
   return true;
 }
 
+// ---- instantiations of the v2 pair stages, one per D0 (MLIP levels 2..24) ----
+typedef void (*V2GatherKernel)(DevPotential, SiteArgs, PairBuf);
+typedef void (*V2MomentsKernel)(SiteArgs, PairBuf, const short *, double *, int);
+typedef void (*V2ForcesKernel)(SiteArgs, PairBuf, const short *, const double *, int, int, double *);
+struct V2Entry {
+  int d0, R, KF, NP;
+  V2GatherKernel gather;
+  V2MomentsKernel moments;
+  V2ForcesKernel forces;
+};
+#define V2_ENTRY(D) \
+  {D, V2Shape<D>::R, V2Shape<D>::KF, V2Shape<D>::NP, mtp_gather_kernel<V2Shape<D>::R>, mtp_moments_v2<D>, mtp_forces_v2<D>}
+const V2Entry kV2[] = {V2_ENTRY(0), V2_ENTRY(1), V2_ENTRY(2), V2_ENTRY(3), V2_ENTRY(4), V2_ENTRY(5),
+                       V2_ENTRY(6), V2_ENTRY(7), V2_ENTRY(8), V2_ENTRY(9), V2_ENTRY(10)};
+constexpr int kV2Count = sizeof(kV2) / sizeof(kV2[0]);
+
+// canonical slot (q lexicographic in (a,b,c), then mu) -> basic moment index of the file, -1 = absent
+bool build_v2_tables(mtp_handle *h, int e)
+{
+  const Potential &p = h->pot;
+  const int D0 = kV2[e].d0, R = kV2[e].R;
+  if (p.radial_func_count != R) return false;
+  auto dmu = [&](int mu) { return std::max(D0 - 2 * mu, 0); };
+  auto rcnt = [&](int d) { return d == 0 ? R : (d > D0 ? 0 : (D0 - d) / 2 + 1); };
+  std::vector<short> s2k((size_t) kV2[e].KF, (short) -1);
+  // slot prefix per monomial
+  std::vector<int> prefix((size_t) tet(D0) + 1, 0);
+  {
+    int q = 0, s = 0;
+    for (int a = 0; a <= D0; a++)
+      for (int b = 0; b <= D0 - a; b++)
+        for (int c = 0; c <= D0 - a - b; c++) {
+          prefix[q++] = s;
+          s += rcnt(a + b + c);
+        }
+    prefix[q] = s;
+    if (s != kV2[e].KF) return false;
+  }
+  for (int k = 0; k < p.alpha_index_basic_count; k++) {
+    const int *b = &p.alpha_index_basic[4 * (size_t) k];
+    const int mu = b[0], d = b[1] + b[2] + b[3];
+    if (mu >= R || d > dmu(mu) || k > 32767) return false;
+    short &slot = s2k[(size_t) prefix[canon_index(D0, b[1], b[2], b[3])] + mu];
+    if (slot >= 0) return false;    // two basic moments with the same definition
+    slot = (short) k;
+  }
+  h->d_slot_to_k.upload(s2k, 0);
+  return true;
+}
+
 void upload_potential(mtp_handle *h)
 {
   Potential &p = h->pot;
-  compile_program(p, h->prog);
+  {
+    // program kernel shape: largest power-of-two atoms-per-CTA whose moments + adjoints ((M+1) rows each) fit
+    cudaDeviceProp prop0;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop0, h->device));
+    const size_t prog_max = std::min(max_dynamic_smem((const void *) mtp_program_kernel<false>, prop0.sharedMemPerBlockOptin),
+                                     max_dynamic_smem((const void *) mtp_program_kernel<true>, prop0.sharedMemPerBlockOptin));
+    h->pl_na_fit = 0;
+    for (int na = 32; na >= 1; na >>= 1)
+      if (program_smem_bytes(p.alpha_moment_count, na) <= prog_max) {
+        h->pl_na_fit = na;
+        break;
+      }
+    h->pl_na[0] = std::max(1, h->pl_na_fit);
+    h->pl_na[1] = std::min(h->pl_na[0], 8);
+    compile_program(p, h->prog, 16 * 32 / h->pl_na[0], 16 * 32 / h->pl_na[1]);
+    CUDA_CHECK(cudaFuncSetAttribute((const void *) mtp_program_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) prog_max));
+    CUDA_CHECK(cudaFuncSetAttribute((const void *) mtp_program_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) prog_max));
+  }
   std::vector<uint32_t> basic(p.alpha_index_basic_count);
   for (int k = 0; k < p.alpha_index_basic_count; k++) {
     const int *e = &p.alpha_index_basic[4 * (size_t) k];
@@ -271,6 +368,11 @@ void upload_potential(mtp_handle *h)
   CUDA_CHECK(cudaDeviceSynchronize());
   d.cfwd = cf;
   d.crev = cr;
+  for (int v = 0; v < 2; v++) {
+    d.ffwd[v] = h->d_ffwd[v].upload(h->prog.ffwd[v]);
+    d.frev[v] = h->d_frev[v].upload(h->prog.frev[v]);
+  }
+  CUDA_CHECK(cudaDeviceSynchronize());
 
   // kernel family: register-resident kernel for standard shapes, generic kernel otherwise
   h->v1_entry = -1;
@@ -287,6 +389,49 @@ void upload_potential(mtp_handle *h)
   CUDA_CHECK(cudaGetDeviceProperties(&prop, h->device));
   h->sm_count = prop.multiProcessorCount;
   const size_t smem_max = prop.sharedMemPerBlockOptin;
+
+  h->v2_entry = -1;
+  if (!getenv("MTP_B200_FORCE_GENERIC") && !getenv("MTP_B200_NO_V2") && h->pl_na_fit >= 1) {
+    int pmax = d.P - 1;
+    for (int e = 0; e < kV2Count; e++)
+      if (kV2[e].d0 == pmax) {
+        if (build_v2_tables(h, e)) h->v2_entry = e;
+        break;
+      }
+  }
+  if (h->v2_entry >= 0) {
+    const V2Entry &E = kV2[h->v2_entry];
+    const int nrad = d.S * d.S * d.R * d.B;
+    h->v2_smem_g = (size_t) ((nrad + 1) & ~1) * 8 + 8 * (size_t) (3 * V2_PEND * 8 + 2 * V2_PEND * 4);
+    bool ok = h->v2_smem_g <= max_dynamic_smem((const void *) E.gather, smem_max);
+    if (ok) {
+      CUDA_CHECK(cudaFuncSetAttribute((const void *) E.gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->v2_smem_g));
+      int per_sm = 0;
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.gather, 256, h->v2_smem_g));
+      h->v2_grid_g = std::max(1, per_sm) * h->sm_count;
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.moments, 32 * E.NP, 0));
+      h->v2_grid_m = std::max(1, per_sm) * h->sm_count;
+      // forces: atoms per CTA so that the canonical adjoints stay below ~72 KB of shared memory
+      const size_t ks = (size_t) (E.KF | 1);
+      h->v2_ab = 0;
+      for (int ab = 64; ab >= 8; ab >>= 1)
+        if (ab * ks * 8 + (ab + 1) * 4 <= std::min<size_t>(72 * 1024, max_dynamic_smem((const void *) E.forces, smem_max))) {
+          h->v2_ab = ab;
+          break;
+        }
+      ok = h->v2_ab > 0;
+      if (ok) {
+        h->v2_smem_f = h->v2_ab * ks * 8 + (h->v2_ab + 1) * 4;
+        CUDA_CHECK(cudaFuncSetAttribute((const void *) E.forces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->v2_smem_f));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.forces, 256, h->v2_smem_f));
+        h->v2_grid_f = std::max(1, per_sm) * h->sm_count;
+      }
+    }
+    if (!ok) h->v2_entry = -1;
+    const char *ce = getenv("MTP_B200_CHUNK");
+    h->v2_chunk = ce ? std::max(1024, atoi(ce)) : 0;
+    h->d_maxnn.ensure(1);
+  }
   if (h->v1_entry >= 0) {
     const V1Entry &E = kV1[h->v1_entry];
     const int W = 8;
@@ -313,22 +458,7 @@ void upload_potential(mtp_handle *h)
       CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.forces[gflag], W * 32, h->pl_smem_f[gflag]));
       h->pl_grid_f[gflag] = std::max(1, per_sm) * h->sm_count;
     }
-    // program kernel: largest power-of-two chunk whose moments + adjoints fit
-    h->pl_na_fit = 0;
-    const size_t prog_max = std::min(max_dynamic_smem((const void *) mtp_program_kernel<false>, smem_max),
-                                     max_dynamic_smem((const void *) mtp_program_kernel<true>, smem_max));
-    for (int na = 32; na >= 1; na >>= 1) {
-      const size_t nb = (((size_t) d.M * (na + 1) * 8 + 15) & ~(size_t) 15) * 2;
-      if (nb <= prog_max) {
-        h->pl_na_fit = na;
-        break;
-      }
-    }
     ok = ok && h->pl_na_fit >= 1;
-    if (ok) {
-      CUDA_CHECK(cudaFuncSetAttribute((const void *) mtp_program_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) prog_max));
-      CUDA_CHECK(cudaFuncSetAttribute((const void *) mtp_program_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) prog_max));
-    }
     if (!ok) h->v1_entry = -1;    // fall back to the generic kernel
   }
   for (int gflag = 0; gflag < 2; gflag++) {
@@ -423,13 +553,40 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
 
   const int gi = grade ? 1 : 0;
   const bool cfg = grade && h->pot.configuration_mode;
-  const bool pipeline = h->v1_entry >= 0;
+  const bool use_v2 = h->v2_entry >= 0 && !grade;
+  const bool pipeline = use_v2 || h->v1_entry >= 0;
   // super-chunk: bounded by the user's "chunksize"; the pipeline additionally keeps its two [K][chunk]
   // intermediates within ~48 MB so that they stay L2-resident
   int chunk = std::max(1, std::min(h->chunksize, a.inum > 0 ? a.inum : 1));
   if (pipeline) {
-    const long long fit = std::max(8192LL, (48LL << 20) / (16LL * d.K) / 1024 * 1024);
+    long long fit = std::max(8192LL, (48LL << 20) / (16LL * d.K) / 1024 * 1024);
+    if (use_v2 && h->v2_chunk > 0) fit = h->v2_chunk;
     chunk = (int) std::min<long long>(chunk, fit);
+  }
+  PairBuf pb{};
+  if (use_v2) {
+    int maxnn = a.max_numneigh;
+    if (maxnn <= 0) {    // unknown bound: one small reduction + a 4-byte read-back
+      CUDA_CHECK(cudaMemsetAsync(h->d_maxnn.p, 0, sizeof(int), st));
+      if (a.inum > 0) {
+        max_numneigh_kernel<<<std::min(h->sm_count * 4, (a.inum + 255) / 256), 256, 0, st>>>(a.inum, a.ilist, a.numneigh,
+                                                                                            h->d_maxnn.p);
+        g_launches++;
+      }
+      CUDA_CHECK(cudaMemcpyAsync(&maxnn, h->d_maxnn.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    const V2Entry &E = kV2[h->v2_entry];
+    pb.ncap = std::max(4, (maxnn + 3) / 4 * 4);
+    pb.cap = (long long) chunk * pb.ncap;
+    h->d_pfld.ensure((size_t) (4 + 2 * E.R) * pb.cap);
+    h->d_pj.ensure((size_t) pb.cap);
+    h->d_pjt.ensure((size_t) pb.cap);
+    h->d_pcnt.ensure((size_t) chunk);
+    pb.fld = h->d_pfld.p;
+    pb.pj = h->d_pj.p;
+    pb.pjt = h->d_pjt.p;
+    pb.pcnt = h->d_pcnt.p;
   } else if (!grade) {
     chunk = a.inum > 0 ? a.inum : 1;
   }
@@ -448,17 +605,18 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
   int na = 1, grid_p_cap = 1;
   size_t smem_p = 0;
   if (pipeline) {
-    na = h->pl_na_fit;
+    // throughput shape unless the system is too small to give every SM a chunk (or the latency variant is asked for)
     const int nfirst = std::min(chunk, std::max(a.inum, 1));
-    while (na > 1 && (nfirst + na - 1) / na < h->sm_count) na >>= 1;
-    if (a.variant == MTP_VARIANT_SMALL && na > 8) na = 8;
-    smem_p = (((size_t) d.M * (na + 1) * 8 + 15) & ~(size_t) 15) * 2;
+    const bool small = a.variant == MTP_VARIANT_SMALL || (nfirst + h->pl_na[0] - 1) / h->pl_na[0] < h->sm_count;
+    na = h->pl_na[small ? 1 : 0];
+    s.prog_shape = small ? 1 : 0;
+    smem_p = program_smem_bytes(d.M, na);
     int per_sm = 0;
     const void *pk = grade ? (const void *) mtp_program_kernel<true> : (const void *) mtp_program_kernel<false>;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, 512, smem_p));
     grid_p_cap = std::max(1, per_sm) * h->sm_count;
   }
-  const int rows_per_super = pipeline ? grid_p_cap + h->pl_grid_f[gi] : h->grid_cap[gi];
+  const int rows_per_super = pipeline ? grid_p_cap + std::max(h->pl_grid_f[gi], h->v2_grid_f) : h->grid_cap[gi];
   h->d_partials.ensure((size_t) nsuper * rows_per_super * 8);
   int rows_used = 0;
 
@@ -469,7 +627,34 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
     s.first_ii = first;
     s.cand_rows = grade ? h->d_cand.p : nullptr;
     s.cand_ld = h->qpad;
-    if (pipeline) {
+    if (use_v2) {
+      const V2Entry &E = kV2[h->v2_entry];
+      {
+        ProfSpan sp(h, MTP_PROF_GATHER, st);
+        const int gg = std::max(1, std::min(h->v2_grid_g, (n + 7) / 8));
+        E.gather<<<gg, 256, h->v2_smem_g, st>>>(d, s, pb);
+      }
+      {
+        ProfSpan sp(h, MTP_PROF_MOMENTS, st);
+        const int gm = std::max(1, std::min(h->v2_grid_m, (n + 31) / 32));
+        E.moments<<<gm, 32 * E.NP, 0, st>>>(s, pb, h->d_slot_to_k.p, h->d_mb.p, ld);
+      }
+      const int gp = std::max(1, std::min(grid_p_cap, (n + na - 1) / na));
+      double *part_p = h->d_partials.p + (size_t) rows_used * 8;
+      {
+        ProfSpan sp(h, MTP_PROF_PROGRAM, st);
+        mtp_program_kernel<false><<<gp, 512, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, part_p);
+      }
+      rows_used += gp;
+      const int gf = std::max(1, std::min(h->v2_grid_f, (n + h->v2_ab - 1) / h->v2_ab));
+      double *part_f = h->d_partials.p + (size_t) rows_used * 8;
+      {
+        ProfSpan sp(h, MTP_PROF_FORCES, st);
+        E.forces<<<gf, 256, h->v2_smem_f, st>>>(s, pb, h->d_slot_to_k.p, h->d_gb.p, ld, h->v2_ab, part_f);
+      }
+      rows_used += gf;
+      g_launches += 4;
+    } else if (pipeline) {
       const V1Entry &E = kV1[h->v1_entry];
       const int gm = std::max(1, std::min(h->pl_grid_m, (n + W - 1) / W));
       {
@@ -843,7 +1028,11 @@ int mtp_compute_host(mtp_handle *h, const mtp_compute_args *a, int list_changed)
       h->h_numneigh.upload(a->numneigh, nid, st);
       if (a->ilist) h->h_ilist.upload(a->ilist, inum, st);
       h->h_list_len = len;
+      int mx = 0;
+      for (size_t k = 0; k < inum; k++) mx = std::max(mx, a->numneigh[a->ilist ? (size_t) a->ilist[k] : k]);
+      h->h_maxnn = mx;
     }
+    d.max_numneigh = h->h_maxnn;
     d.x = h->h_x.p;
     d.type = h->h_type.p;
     d.f = h->h_f.p;

@@ -25,6 +25,13 @@ struct DevChunkPass {
   int nlevels;
 };
 
+// flat predicated term streams (mtp_potential.hpp: FlatPass)
+struct DevFlatPass {
+  const int *stream_begin;     // [nlevels * vw + 1]
+  const uint4 *terms;          // {a | b << 16, node | store << 16, coef lo, coef hi}
+  int nlevels, vw;
+};
+
 struct DevPotential {
   int S, R, B, K, M, A, P, Q;
   double rmin, rmax, scaling, cutsq;
@@ -36,6 +43,7 @@ struct DevPotential {
   const double *ginit;       // [M]
   DevPass fwd, rev;
   DevChunkPass cfwd, crev;
+  DevFlatPass ffwd[2], frev[2];    // [0]: 32 atoms per CTA, [1]: 8 atoms per CTA
 };
 
 // packed position + species record: one 32-byte sector per gathered neighbor
@@ -63,6 +71,7 @@ struct SiteArgs {
   double *cand_rows;      // grade steps: [chunk rows][Qpad] candidate vectors
   int cand_ld;            // Qpad
   int first_ii;           // chunk offset into ilist (grade steps)
+  int prog_shape;         // which flat-stream table set the program kernel uses (0 throughput, 1 latency)
   int *status;
 };
 

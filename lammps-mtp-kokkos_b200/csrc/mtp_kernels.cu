@@ -506,7 +506,20 @@ __global__ void finalize_ev_kernel(const double *partials, int nrows, double *ev
 
 }    // namespace mtpb200
 #include "mtp_kernels_v1.cuh"
+#include "mtp_kernels_v2.cuh"
 namespace mtpb200 {
+
+// max of numneigh over the listed centres (only when the caller does not know an upper bound)
+__global__ void max_numneigh_kernel(int inum, const int *__restrict__ ilist, const int *__restrict__ numneigh, int *out)
+{
+  int m = 0;
+  for (int ii = blockIdx.x * blockDim.x + threadIdx.x; ii < inum; ii += gridDim.x * blockDim.x)
+    m = max(m, numneigh[ilist ? ilist[ii] : ii]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(FULL, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // Extrapolation grade: G = Bmat[n x Q] . Ainv^T, grade[row] = max_col |G|  (pair_mtp_extrapolation.cpp:347-358),

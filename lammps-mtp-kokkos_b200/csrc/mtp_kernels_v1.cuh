@@ -489,6 +489,45 @@ mtp_moments_kernel(DevPotential pot, V1Tables tb, SiteArgs a, double *__restrict
 }
 
 // contraction program forward (pair_mtp.cpp:196-201), site energy (:204-212), reverse mode (:217-233)
+//
+// CTA per chunk of NA atoms (NA = 32 or 8), lane = atom: moments cm[node][atom] and adjoints cg[node][atom] of the
+// chunk live in shared memory (row stride NA+1, row M = 1.0).  The program is executed as flat predicated term
+// streams (mtp_potential.hpp: FlatPass): one stream per (dependency level, virtual warp); every term is
+//     acc += coef * A[a] * B[b];  if (store) { dst[node] = acc; acc = 0; }
+// so the inner loop has no data-dependent branch and the descriptor + operand loads of FLAT_UNROLL terms are all
+// independent (the only serial chain is the accumulator).
+template <bool REVERSE>
+__device__ __forceinline__ void run_flat_pass(const DevFlatPass &ps, double *cm, double *cg, int NAp, int al, int vwarp)
+{
+  const double *A = REVERSE ? cg : cm;
+  double *dst = REVERSE ? cg : cm;
+  for (int lv = 0; lv < ps.nlevels; lv++) {
+    const int t0 = ps.stream_begin[lv * ps.vw + vwarp], t1 = ps.stream_begin[lv * ps.vw + vwarp + 1];
+    double acc = 0.0;
+    for (int t = t0; t < t1; t += 4) {
+      uint4 d[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) d[u] = __ldg(ps.terms + t + u);
+      double va[4], vb[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        va[u] = A[(d[u].x & 0xffffu) * NAp + al];
+        vb[u] = cm[(d[u].x >> 16) * NAp + al];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const double coef = __hiloint2double((int) d[u].w, (int) d[u].z);
+        acc += coef * va[u] * vb[u];
+        if (d[u].y >> 16) {
+          dst[(d[u].y & 0xffffu) * NAp + al] = acc;
+          acc = 0.0;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 template <bool GRADE>
 __global__ void __launch_bounds__(512)
 mtp_program_kernel(DevPotential pot, SiteArgs a, const double *__restrict__ mb, double *__restrict__ gb, int ld,
@@ -497,14 +536,16 @@ mtp_program_kernel(DevPotential pot, SiteArgs a, const double *__restrict__ mb, 
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
   const int NAp = NA + 1;
-  const size_t node_bytes = ((size_t) pot.M * NAp * 8 + 15) & ~(size_t) 15;
+  const size_t node_bytes = ((size_t) (pot.M + 1) * NAp * 8 + 15) & ~(size_t) 15;
   double *cm = reinterpret_cast<double *>(smem);
   double *cg = reinterpret_cast<double *>(smem + node_bytes);
-  const int NS = 32 / NA;                   // term slots per warp
   const int al_t = lane & (NA - 1);         // atom of this lane
-  const int slot_t = lane / NA;
+  const int vwarp = warp * (32 / NA) + lane / NA;
+  const int fi = a.prog_shape;
   const int radial_count = pot.S * pot.S * pot.R * pot.B;
   double e_thread = 0.0;
+
+  for (int t = threadIdx.x; t < NAp; t += blockDim.x) cm[pot.M * NAp + t] = cg[pot.M * NAp + t] = 1.0;
 
   for (int chunk0 = blockIdx.x * NA; chunk0 < a.inum; chunk0 += gridDim.x * NA) {
     const int na = min(NA, a.inum - chunk0);
@@ -514,24 +555,8 @@ mtp_program_kernel(DevPotential pot, SiteArgs a, const double *__restrict__ mb, 
       cm[k * NAp + al] = al < na ? mb[(size_t) k * ld + chunk0 + al] : 0.0;
     }
     __syncthreads();
-    {
-      const DevChunkPass &ps = pot.cfwd;
-      for (int lv = 0; lv < ps.nlevels; lv++) {
-        const int t1 = ps.level_begin[lv + 1];
-        for (int t = ps.level_begin[lv] + warp * NS + slot_t; t < t1; t += W * NS) {
-          const int node = ps.node[t];
-          const int e1 = ps.term_begin[t + 1];
-          double acc = node < pot.K ? cm[node * NAp + al_t] : 0.0;
-          for (int e = ps.term_begin[t]; e < e1; e++) {
-            const uint32_t idx = ps.term_idx[e];
-            acc += ps.term_coef[e] * cm[(idx & 0xffffu) * NAp + al_t] * cm[(idx >> 16) * NAp + al_t];
-          }
-          cm[node * NAp + al_t] = acc;
-        }
-        __syncthreads();
-      }
-    }
-    // site energies: thread (al, part) sums a strided share of the basis functions
+    run_flat_pass<false>(pot.ffwd[fi], cm, cg, NAp, al_t, vwarp);
+    // site energies: one warp per atom, lanes stride the basis functions
     if (a.eflag_global || a.eflag_atom || GRADE) {
       for (int al = warp; al < na; al += W) {
         const int i = a.ilist ? a.ilist[a.first_ii + chunk0 + al] : a.first_ii + chunk0 + al;
@@ -548,26 +573,7 @@ mtp_program_kernel(DevPotential pot, SiteArgs a, const double *__restrict__ mb, 
         if (a.eflag_global && lane == 0) e_thread += e;
       }
     }
-    {
-      const DevChunkPass &ps = pot.crev;
-      for (int lv = 0; lv < ps.nlevels; lv++) {
-        const int t1 = ps.level_begin[lv + 1];
-        for (int t = ps.level_begin[lv] + warp * NS + slot_t; t < t1; t += W * NS) {
-          const int node = ps.node[t];
-          const int e1 = ps.term_begin[t + 1];
-          double acc = ps.init[t];
-          for (int e = ps.term_begin[t]; e < e1; e++) {
-            const uint32_t idx = ps.term_idx[e];
-            const uint32_t a3 = idx & 0xffffu;
-            const double c = ps.term_coef[e];
-            const double ga = a3 == 0xffffu ? c : cg[a3 * NAp + al_t] * c;
-            acc += ga * cm[(idx >> 16) * NAp + al_t];
-          }
-          cg[node * NAp + al_t] = acc;
-        }
-        __syncthreads();
-      }
-    }
+    run_flat_pass<true>(pot.frev[fi], cm, cg, NAp, al_t, vwarp);
     // adjoints of the basic moments -> gb
     for (int t = threadIdx.x; t < pot.K * NA; t += blockDim.x) {
       const int k = t / NA, al = t - k * NA;

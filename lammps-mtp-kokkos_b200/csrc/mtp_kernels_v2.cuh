@@ -1,0 +1,539 @@
+// Pair stages of the per-step pipeline for standard MTP basic-moment sets (template <D0>).
+//
+// A level-L MLIP potential uses the basic moments M_{mu,nu} with nu <= D_mu = D0 - 2 mu (D0 = (L-4)/2, plus a
+// trailing scalar M_{mu,0} when D0 is odd), i.e. for every monomial q = x^a y^b z^c of degree d the radial
+// indices mu < rcnt(d).  With D0 a compile-time constant every loop over (a, b, c, mu) below unrolls into
+// straight-line FP64 code on registers.  Canonical slot order: q lexicographic in (a, b, c), then mu.
+//
+//   mtp_gather_kernel    warp per centre atom: neighbor gather (32-byte position records), cutoff mask exactly as
+//                        pair_mtp.cpp:112-129, compaction, then lane = in-cutoff pair: Chebyshev x cutoff and the
+//                        radial contraction (mtp_rb_chevbyshev_basis.cpp:29-54, pair_mtp.cpp:139-151).  Writes one
+//                        record per pair {u, d, f_mu, f'_mu, j} into the pair buffer, field-major, atom ii owning
+//                        the slots [ii * ncap, ii * ncap + pcnt[ii]).
+//   mtp_moments_v2       CTA = 32 atoms x NP warps, lane = atom, warp = "pass" (a contiguous range of canonical
+//                        slots, <= ~48 accumulators held in registers).  Pair records are staged through shared
+//                        memory (coalesced read, transposed so that lane = atom reads are conflict free);
+//                        m[mu][q] += f_mu u^q is one DFMA per (pair, moment), monomials by running products.
+//   mtp_forces_v2        CTA = AB atoms, lane = pair (all lanes busy whatever the neighbor counts): the adjoints
+//                        dE/dm of the CTA's atoms sit in shared memory in canonical order, the per-pair force is
+//                        the gradient of sum_mu f_mu(d) P_mu(u) evaluated by a fully unrolled three-level Horner
+//                        scheme (pair_mtp.cpp:175-191,236-254 without ever forming the Jacobian), red.f64 scatter to
+//                        the neighbor, segmented warp reduction for the centre atom, virial -sym(F (x) r) (:257-276).
+#pragma once
+
+#include "mtp_device.cuh"
+
+namespace mtpb200 {
+
+struct PairBuf {
+  double *fld;        // [4 + 2R][cap]: ux, uy, uz, d, f_0..f_{R-1}, f'_0..f'_{R-1}
+  int *pj;            // [cap] neighbor atom index (ghosts included)
+  int *pjt;           // [cap] neighbor species (0-based)
+  int *pcnt;          // [chunk] in-cutoff pairs per centre
+  long long cap;      // chunk * ncap
+  int ncap;           // slots per centre (>= max numneigh)
+};
+
+template <int D0> struct V2Shape {
+  static constexpr int R = D0 / 2 + 1 + (D0 & 1);
+  __host__ __device__ static constexpr int dmu(int mu) { return D0 - 2 * mu > 0 ? D0 - 2 * mu : 0; }
+  __host__ __device__ static constexpr int rcnt(int d) { return d == 0 ? R : (d > D0 ? 0 : (D0 - d) / 2 + 1); }
+  __host__ __device__ static constexpr int kfull()
+  {
+    int s = 0;
+    for (int mu = 0; mu < R; mu++) s += tet(dmu(mu));
+    return s;
+  }
+  static constexpr int NQ = tet(D0);
+  static constexpr int KF = kfull();
+  static constexpr int NF = 3 + R;                 // fields the moment kernel stages: u, f
+  static constexpr int NFLD = 4 + 2 * R;           // fields of a pair record
+  // ---- forward passes: columns (a, b) in lexicographic order, greedily packed under a register budget
+  __host__ __device__ static constexpr int col_count(int a, int b)
+  {
+    int s = 0;
+    for (int c = 0; c <= D0 - a - b; c++) s += rcnt(a + b + c);
+    return s;
+  }
+  static constexpr int BUDGET = (KF + ((KF + 47) / 48) - 1) / ((KF + 47) / 48) + 2;
+  // pass of column (a, b); with (a, b) = (D0 + 1, 0) returns the number of passes
+  __host__ __device__ static constexpr int pass_of(int qa, int qb)
+  {
+    int pass = 0, fill = 0;
+    for (int a = 0; a <= D0; a++)
+      for (int b = 0; b <= D0 - a; b++) {
+        const int n = col_count(a, b);
+        if (fill + n > BUDGET && fill > 0) {
+          pass++;
+          fill = 0;
+        }
+        if (a == qa && b == qb) return pass;
+        fill += n;
+      }
+    return pass + 1;
+  }
+  static constexpr int NP = pass_of(D0 + 1, 0);
+  __host__ __device__ static constexpr int col_begin(int qa, int qb)    // canonical slot of (qa, qb, c = 0)
+  {
+    int s = 0;
+    for (int a = 0; a <= D0; a++)
+      for (int b = 0; b <= D0 - a; b++) {
+        if (a == qa && b == qb) return s;
+        s += col_count(a, b);
+      }
+    return s;
+  }
+  __host__ __device__ static constexpr int pass_begin(int p)    // first canonical slot of pass p
+  {
+    int s = 0;
+    for (int a = 0; a <= D0; a++)
+      for (int b = 0; b <= D0 - a; b++) {
+        if (pass_of(a, b) >= p) return s;
+        s += col_count(a, b);
+      }
+    return s;
+  }
+  __host__ __device__ static constexpr int amax()
+  {
+    int m = 0;
+    for (int p = 0; p < NP; p++) {
+      const int n = pass_begin(p + 1) - pass_begin(p);
+      m = n > m ? n : m;
+    }
+    return m;
+  }
+  static constexpr int AMAX = amax();
+};
+
+constexpr int V2_PEND = 64;
+constexpr int V2_NT = 16;      // pairs per staged tile of the moment kernel
+
+// ===================================================================================================== gather
+template <int R>
+__global__ void __launch_bounds__(256)
+mtp_gather_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  double *s_radial = reinterpret_cast<double *>(smem);
+  const int nrad = pot.S * pot.S * pot.R * pot.B;
+  for (int t = threadIdx.x; t < nrad; t += blockDim.x) s_radial[t] = pot.radial[t];
+  double *pr = s_radial + ((nrad + 1) & ~1) + (size_t) warp * (3 * V2_PEND + V2_PEND);
+  int *pj = reinterpret_cast<int *>(pr + 3 * V2_PEND);
+  int *pt = pj + V2_PEND;
+  __syncthreads();
+
+  for (int ii = blockIdx.x * W + warp; ii < a.inum; ii += gridDim.x * W) {
+    V1Atom at;
+    v1_load_atom(pot, a, ii, lane, at);
+    const long long slot0 = (long long) ii * pb.ncap;
+    int pend = 0, done = 0;
+    for (int base = 0; base < at.jnum || pend > 0; base += 32) {
+      if (base < at.jnum) {
+        const int jj = base + lane;
+        bool within = false;
+        int j = 0, jt = 0;
+        double r0 = 0, r1 = 0, r2 = 0;
+        if (jj < at.jnum) {
+          const long long pos = at.row0 + (long long) jj * a.stride_jj;
+          j = a.neighbors[pos] & a.neighmask;
+          const double2 *nrec = reinterpret_cast<const double2 *>(a.xt + j);
+          const double2 nxy = __ldg(nrec);
+          const double2 nzt = __ldg(nrec + 1);
+          jt = (int) __double_as_longlong(nzt.y);
+          r0 = nxy.x - at.xi0;
+          r1 = nxy.y - at.xi1;
+          r2 = nzt.x - at.xi2;
+          // separately rounded, left to right, exactly pair_mtp.cpp:121-123 (no FMA contraction)
+          const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2));
+          within = !(rsq > pot.cutsq);
+          if (jt < 0 || jt >= pot.S) {    // pair_mtp.cpp:116-118
+            atomicOr(a.status, 1);
+            within = false;
+          }
+          if (a.within) a.within[pos] = within ? 1 : 0;
+        }
+        const unsigned bal = __ballot_sync(FULL, within);
+        if (within) {
+          const int slot = pend + __popc(bal & ((1u << lane) - 1u));
+          pr[slot] = r0;
+          pr[V2_PEND + slot] = r1;
+          pr[2 * V2_PEND + slot] = r2;
+          pj[slot] = j;
+          pt[slot] = jt;
+        }
+        pend += __popc(bal);
+        __syncwarp();
+        if (pend < 32 && base + 32 < at.jnum) continue;    // keep filling the batch
+      }
+      const int nb = pend < 32 ? pend : 32;
+      if (nb == 0) break;
+      if (lane < nb) {
+        const double r0 = pr[lane], r1 = pr[V2_PEND + lane], r2 = pr[2 * V2_PEND + lane];
+        const int jt = pt[lane];
+        const double dist = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2)));
+        const double invd = 1.0 / dist;
+        double F[R], Fd[R];
+        radial_functions<R>(pot, s_radial + (size_t) (at.itype * pot.S + jt) * pot.R * pot.B, dist, F, Fd);
+        const long long s = slot0 + done + lane;
+        pb.fld[s] = r0 * invd;
+        pb.fld[pb.cap + s] = r1 * invd;
+        pb.fld[2 * pb.cap + s] = r2 * invd;
+        pb.fld[3 * pb.cap + s] = dist;
+#pragma unroll
+        for (int mu = 0; mu < R; mu++) {
+          pb.fld[(4 + mu) * pb.cap + s] = F[mu];
+          pb.fld[(4 + R + mu) * pb.cap + s] = Fd[mu];
+        }
+        pb.pj[s] = pj[lane];
+        pb.pjt[s] = jt;
+      }
+      done += nb;
+      // drop the consumed batch, keep the remainder (< 32 entries)
+      const int rem = pend - nb;
+      double t0 = 0, t1 = 0, t2 = 0;
+      int tj = 0, tt = 0;
+      __syncwarp();
+      if (lane < rem) {
+        t0 = pr[32 + lane];
+        t1 = pr[V2_PEND + 32 + lane];
+        t2 = pr[2 * V2_PEND + 32 + lane];
+        tj = pj[32 + lane];
+        tt = pt[32 + lane];
+      }
+      __syncwarp();
+      if (lane < rem) {
+        pr[lane] = t0;
+        pr[V2_PEND + lane] = t1;
+        pr[2 * V2_PEND + lane] = t2;
+        pj[lane] = tj;
+        pt[lane] = tt;
+      }
+      pend = rem;
+      __syncwarp();
+    }
+    if (lane == 0) pb.pcnt[ii] = done;
+  }
+}
+
+// ===================================================================================================== moments
+// accumulate one pair into the accumulators of pass P:  acc[slot - pass_begin(P)] += f[mu] * x^a y^b z^c.
+// The (a, b) loops are template recursion so that pass_of / col_begin are evaluated by the constexpr evaluator.
+template <int D0, int P, int A, int B> struct V2FwdB {
+  __device__ __forceinline__ static void run(double xy, double uy, double uz, const double (&f)[V2Shape<D0>::R],
+                                             double (&acc)[V2Shape<D0>::AMAX])
+  {
+    using Sh = V2Shape<D0>;
+    if constexpr (B <= D0 - A) {
+      if constexpr (Sh::pass_of(A, B) == P) {
+        constexpr int base = Sh::col_begin(A, B) - Sh::pass_begin(P);
+        int idx = base;
+        double m = xy;
+#pragma unroll
+        for (int c = 0; c <= D0 - A - B; c++) {
+#pragma unroll
+          for (int mu = 0; mu < Sh::rcnt(A + B + c); mu++) {
+            acc[idx] = fma(f[mu], m, acc[idx]);
+            idx++;
+          }
+          m *= uz;
+        }
+      }
+      V2FwdB<D0, P, A, B + 1>::run(xy * uy, uy, uz, f, acc);
+    }
+  }
+};
+template <int D0, int P, int A> struct V2FwdA {
+  __device__ __forceinline__ static void run(double xa, double ux, double uy, double uz,
+                                             const double (&f)[V2Shape<D0>::R], double (&acc)[V2Shape<D0>::AMAX])
+  {
+    if constexpr (A <= D0) {
+      V2FwdB<D0, P, A, 0>::run(xa, uy, uz, f, acc);
+      V2FwdA<D0, P, A + 1>::run(xa * ux, ux, uy, uz, f, acc);
+    }
+  }
+};
+template <int D0, int P>
+__device__ __forceinline__ void v2_fwd_accumulate(double ux, double uy, double uz,
+                                                  const double (&f)[V2Shape<D0>::R], double (&acc)[V2Shape<D0>::AMAX])
+{
+  V2FwdA<D0, P, 0>::run(1.0, ux, uy, uz, f, acc);
+}
+
+template <int D0, int P>
+__device__ __forceinline__ void v2_moments_body(const SiteArgs &a, const PairBuf &pb, const short *__restrict__ slot_to_k,
+                                                double *__restrict__ mb, int ld, double *tile)
+{
+  using Sh = V2Shape<D0>;
+  constexpr int R = Sh::R, NF = Sh::NF, NW = Sh::NP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nblk = (a.inum + 31) >> 5;
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int ii = blk * 32 + lane;
+    const int cnt_l = ii < a.inum ? pb.pcnt[ii] : 0;
+    int nmax = cnt_l;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
+    double acc[Sh::AMAX];
+#pragma unroll
+    for (int t = 0; t < Sh::AMAX; t++) acc[t] = 0.0;
+    for (int n0 = 0; n0 < nmax; n0 += V2_NT) {
+      __syncthreads();    // previous tile fully consumed
+      // stage: the warps split the 32 atoms; 16 lanes cover the tile's pairs of one field (coalesced 128 B)
+      for (int al = warp; al < 32; al += NW) {
+        const int cnt_al = __shfl_sync(FULL, cnt_l, al);
+        const long long base = (long long) (blk * 32 + al) * pb.ncap + n0;
+        for (int e = lane; e < V2_NT * NF; e += 32) {
+          const int fi = e / V2_NT, n = e - fi * V2_NT;
+          const int gf = fi < 3 ? fi : fi + 1;    // skip the distance field
+          const double v = (n0 + n < cnt_al) ? pb.fld[(size_t) gf * pb.cap + base + n] : 0.0;
+          tile[(n * NF + fi) * 33 + al] = v;
+        }
+      }
+      __syncthreads();
+      const int nt = min(V2_NT, nmax - n0);
+      for (int n = 0; n < nt; n++) {
+        const double *rec = tile + (size_t) n * NF * 33 + lane;
+        const double ux = rec[0], uy = rec[33], uz = rec[66];
+        double f[R];
+#pragma unroll
+        for (int mu = 0; mu < R; mu++) f[mu] = rec[(3 + mu) * 33];
+        v2_fwd_accumulate<D0, P>(ux, uy, uz, f, acc);    // padded records have f = 0
+      }
+    }
+    if (ii < a.inum) {
+      constexpr int beg = Sh::pass_begin(P), cnt = Sh::pass_begin(P + 1) - Sh::pass_begin(P);
+#pragma unroll
+      for (int t = 0; t < cnt; t++) {
+        const int k = slot_to_k[beg + t];
+        if (k >= 0) mb[(size_t) k * ld + ii] = acc[t];
+      }
+    }
+  }
+}
+
+template <int D0, int P> struct V2PassDispatch {
+  __device__ __forceinline__ static void run(int pass, const SiteArgs &a, const PairBuf &pb, const short *slot_to_k,
+                                             double *mb, int ld, double *tile)
+  {
+    if (pass == P) v2_moments_body<D0, P>(a, pb, slot_to_k, mb, ld, tile);
+    else
+      V2PassDispatch<D0, P + 1>::run(pass, a, pb, slot_to_k, mb, ld, tile);
+  }
+};
+template <int D0> struct V2PassDispatch<D0, V2Shape<D0>::NP> {
+  __device__ __forceinline__ static void run(int, const SiteArgs &, const PairBuf &, const short *, double *, int, double *) {}
+};
+
+template <int D0>
+__global__ void __launch_bounds__(32 * V2Shape<D0>::NP)
+mtp_moments_v2(SiteArgs a, PairBuf pb, const short *__restrict__ slot_to_k, double *__restrict__ mb, int ld)
+{
+  __shared__ double tile[V2_NT * V2Shape<D0>::NF * 33];
+  V2PassDispatch<D0, 0>::run(threadIdx.x >> 5, a, pb, slot_to_k, mb, ld, tile);
+}
+
+// ===================================================================================================== forces
+// gradient of sum_mu f_mu(d) P_mu(u), P_mu(u) = sum_q g[q][mu] u^q, by three nested Horner sweeps; g = canonical row
+template <int D0>
+__device__ __forceinline__ void v2_pair_force(const double *__restrict__ gr, double ux, double uy, double uz,
+                                              const double (&fvi)[V2Shape<D0>::R], const double (&fder)[V2Shape<D0>::R],
+                                              double &Fx, double &Fy, double &Fz)
+{
+  using Sh = V2Shape<D0>;
+  double Pv = 0, Px = 0, Py = 0, Pz = 0, Pd = 0;
+  int sl = Sh::KF;
+#pragma unroll
+  for (int a = D0; a >= 0; a--) {
+    double Q = 0, Qy = 0, Qz = 0, Qd = 0;
+#pragma unroll
+    for (int b = D0 - a; b >= 0; b--) {
+      double T = 0, Tz = 0, Td = 0;
+#pragma unroll
+      for (int c = D0 - a - b; c >= 0; c--) {
+        constexpr int dummy = 0;
+        (void) dummy;
+        const int rc = Sh::rcnt(a + b + c);
+        sl -= rc;
+        double W = 0, Wd = 0;
+#pragma unroll
+        for (int mu = 0; mu < rc; mu++) {
+          const double g = gr[sl + mu];
+          if (mu == 0) {
+            W = fvi[0] * g;
+            Wd = fder[0] * g;
+          } else {
+            W = fma(fvi[mu], g, W);
+            Wd = fma(fder[mu], g, Wd);
+          }
+        }
+        if (c == D0 - a - b) {    // top of the z sweep: T = Tz = Td = 0
+          T = W;
+          Td = Wd;
+        } else {
+          Tz = fma(Tz, uz, T);
+          T = fma(T, uz, W);
+          Td = fma(Td, uz, Wd);
+        }
+      }
+      if (b == D0 - a) {
+        Q = T;
+        Qz = Tz;
+        Qd = Td;
+      } else {
+        Qy = fma(Qy, uy, Q);
+        Q = fma(Q, uy, T);
+        Qz = fma(Qz, uy, Tz);
+        Qd = fma(Qd, uy, Td);
+      }
+    }
+    if (a == D0) {
+      Pv = Q;
+      Py = Qy;
+      Pz = Qz;
+      Pd = Qd;
+    } else {
+      Px = fma(Px, ux, Pv);
+      Pv = fma(Pv, ux, Q);
+      Py = fma(Py, ux, Qy);
+      Pz = fma(Pz, ux, Qz);
+      Pd = fma(Pd, ux, Qd);
+    }
+  }
+  const double S = Pd - (ux * Px + uy * Py + uz * Pz);
+  Fx = fma(ux, S, Px);
+  Fy = fma(uy, S, Py);
+  Fz = fma(uz, S, Pz);
+}
+
+template <int D0>
+__global__ void __launch_bounds__(256)
+mtp_forces_v2(SiteArgs a, PairBuf pb, const short *__restrict__ slot_to_k, const double *__restrict__ gb, int ld,
+              int AB, double *__restrict__ partials)
+{
+  using Sh = V2Shape<D0>;
+  constexpr int R = Sh::R, KS = Sh::KF | 1;
+  extern __shared__ __align__(16) unsigned char smem[];
+  double *g = reinterpret_cast<double *>(smem);               // [AB][KS] canonical adjoints
+  int *pre = reinterpret_cast<int *>(g + (size_t) AB * KS);   // [AB + 1] exclusive prefix of pcnt
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double vloc[6] = {0, 0, 0, 0, 0, 0};
+
+  const int nblk = (a.inum + AB - 1) / AB;
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int ii0 = blk * AB, na = min(AB, a.inum - ii0);
+    __syncthreads();    // previous block's g / pre no longer in use
+    for (int t = threadIdx.x; t < AB * Sh::KF; t += blockDim.x) {
+      const int s = t / AB, al = t - s * AB;    // atom fastest: coalesced rows of gb
+      const int k = slot_to_k[s];
+      g[(size_t) al * KS + s] = (k >= 0 && al < na) ? gb[(size_t) k * ld + ii0 + al] : 0.0;
+    }
+    if (warp == 0) {    // exclusive scan of the block's pair counts (AB <= 128: 4 values per lane)
+      int run = 0;
+      for (int b0 = 0; b0 < AB; b0 += 32) {
+        const int al = b0 + lane;
+        const int c = (al < na) ? pb.pcnt[ii0 + al] : 0;
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(FULL, inc, o);
+          if (lane >= o) inc += v;
+        }
+        if (al < AB) pre[al] = run + inc - c;
+        run += __shfl_sync(FULL, inc, 31);
+      }
+      if (lane == 0) pre[AB] = run;
+    }
+    __syncthreads();
+    const int total = pre[AB];
+    for (int p0 = 0; p0 < total; p0 += blockDim.x) {
+      const int p = p0 + threadIdx.x;
+      const bool live = p < total;
+      int al = 0;
+      if (live) {    // largest al with pre[al] <= p
+        int lo = 0, hi = AB;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (pre[mid] <= p) lo = mid;
+          else
+            hi = mid;
+        }
+        al = lo;
+      }
+      double Fx = 0, Fy = 0, Fz = 0;
+      const int i = a.ilist ? a.ilist[a.first_ii + ii0 + al] : a.first_ii + ii0 + al;
+      if (live) {
+        const size_t s = (size_t) (ii0 + al) * pb.ncap + (p - pre[al]);
+        const double ux = pb.fld[s], uy = pb.fld[pb.cap + s], uz = pb.fld[2 * pb.cap + s], d = pb.fld[3 * pb.cap + s];
+        const double invd = 1.0 / d;
+        double fvi[R], fder[R];
+#pragma unroll
+        for (int mu = 0; mu < R; mu++) {
+          fvi[mu] = pb.fld[(4 + mu) * pb.cap + s] * invd;
+          fder[mu] = pb.fld[(4 + R + mu) * pb.cap + s];
+        }
+        v2_pair_force<D0>(g + (size_t) al * KS, ux, uy, uz, fvi, fder, Fx, Fy, Fz);
+        const int j = pb.pj[s];
+        atomicAdd(&a.f[3 * (size_t) j], -Fx);
+        atomicAdd(&a.f[3 * (size_t) j + 1], -Fy);
+        atomicAdd(&a.f[3 * (size_t) j + 2], -Fz);
+        if (a.vflag_any) {
+          const double r0 = ux * d, r1 = uy * d, r2 = uz * d;
+          const double v0 = Fx * r0, v1 = Fy * r1, v2 = Fz * r2;
+          const double v3 = (Fx * r1 + Fy * r0) / 2, v4 = (Fx * r2 + Fz * r0) / 2, v5 = (Fy * r2 + Fz * r1) / 2;
+          vloc[0] -= v0;
+          vloc[1] -= v1;
+          vloc[2] -= v2;
+          vloc[3] -= v3;
+          vloc[4] -= v4;
+          vloc[5] -= v5;
+          if (a.vflag_atom) {    // pair_mtp.cpp:268-276: all on the centre atom
+            atomicAdd(&a.vatom[6 * (size_t) i], -v0);
+            atomicAdd(&a.vatom[6 * (size_t) i + 1], -v1);
+            atomicAdd(&a.vatom[6 * (size_t) i + 2], -v2);
+            atomicAdd(&a.vatom[6 * (size_t) i + 3], -v3);
+            atomicAdd(&a.vatom[6 * (size_t) i + 4], -v4);
+            atomicAdd(&a.vatom[6 * (size_t) i + 5], -v5);
+          }
+        }
+      }
+      // centre atom: segmented sum over the lanes that share it (lanes are sorted by atom)
+      const int key = live ? al : -1 - lane;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ko = __shfl_down_sync(FULL, key, o);
+        const double x = __shfl_down_sync(FULL, Fx, o), y = __shfl_down_sync(FULL, Fy, o), z = __shfl_down_sync(FULL, Fz, o);
+        if (lane + o < 32 && ko == key) {
+          Fx += x;
+          Fy += y;
+          Fz += z;
+        }
+      }
+      const int kprev = __shfl_up_sync(FULL, key, 1);
+      if (live && (lane == 0 || kprev != key)) {
+        atomicAdd(&a.f[3 * (size_t) i], Fx);
+        atomicAdd(&a.f[3 * (size_t) i + 1], Fy);
+        atomicAdd(&a.f[3 * (size_t) i + 2], Fz);
+      }
+    }
+  }
+
+  // per-CTA virial partial, fixed order
+  __shared__ double s_part[8][8];
+#pragma unroll
+  for (int c = 0; c < 6; c++) vloc[c] = warp_sum(vloc[c]);
+  if (lane == 0) {
+    s_part[warp][0] = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; c++) s_part[warp][1 + c] = vloc[c];
+    s_part[warp][7] = 0.0;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double s = 0.0;
+    for (int w = 0; w < (int) (blockDim.x >> 5); w++) s += s_part[w][threadIdx.x];
+    partials[(size_t) blockIdx.x * 8 + threadIdx.x] = s;
+  }
+}
+
+}    // namespace mtpb200

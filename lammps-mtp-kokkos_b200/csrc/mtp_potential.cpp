@@ -385,7 +385,7 @@ void pack_pass(const std::vector<std::vector<NodeList>> &per_level, ProgramPass 
 
 }    // namespace
 
-void compile_program(const Potential &p, Program &prog)
+void compile_program(const Potential &p, Program &prog, int vw_large, int vw_small)
 {
   const int M = p.alpha_moment_count, T = p.alpha_index_times_count, A = p.alpha_scalar_count;
   const int *times = p.alpha_index_times.data();
@@ -491,6 +491,60 @@ void compile_program(const Potential &p, Program &prog)
   if (M >= 0xFFFF) throw std::runtime_error("alpha_moments_count above 65534 is not supported.");
   pack_chunk(fwd, false, prog.cfwd);
   pack_chunk(rev, true, prog.crev);
+
+  // ---- flat predicated streams ----
+  const uint16_t ONE = (uint16_t) M;    // row of 1.0
+  auto pack_flat = [&](const std::vector<std::vector<NodeList>> &levels, bool reverse, int vw, FlatPass &out) {
+    out = FlatPass();
+    out.vw = vw;
+    out.nlevels = (int) levels.size();
+    out.stream_begin.push_back(0);
+    for (const auto &lv : levels) {
+      // node -> uniform terms (base first, then the list in its original order)
+      std::vector<std::vector<FlatTerm>> per_node;
+      for (const NodeList &l : lv) {
+        std::vector<FlatTerm> t;
+        if (!reverse) {
+          if (l.node < p.alpha_index_basic_count) t.push_back(FlatTerm{(uint16_t) l.node, ONE, 0, 0, 1.0});
+          for (const ProgramTerm &q : l.terms) t.push_back(FlatTerm{q.a, q.b, 0, 0, (double) q.mult});
+        } else {
+          t.push_back(FlatTerm{ONE, ONE, 0, 0, prog.ginit[l.node]});
+          for (const ProgramTerm &q : l.terms) {
+            if (!is_source[q.a]) {
+              const double c = (double) q.mult * prog.ginit[q.a];    // g[a3] stays ginit[a3]
+              if (c == 0.0) continue;
+              t.push_back(FlatTerm{ONE, q.b, 0, 0, c});
+            } else
+              t.push_back(FlatTerm{q.a, q.b, 0, 0, (double) q.mult});
+          }
+        }
+        if (t.empty()) t.push_back(FlatTerm{ONE, ONE, 0, 0, 0.0});
+        for (auto &x : t) x.node = (uint16_t) l.node;
+        t.back().store = 1;
+        per_node.push_back(std::move(t));
+      }
+      std::vector<int> order(per_node.size());
+      for (size_t i = 0; i < order.size(); i++) order[i] = (int) i;
+      std::stable_sort(order.begin(), order.end(),
+                       [&](int x, int y) { return per_node[x].size() > per_node[y].size(); });
+      std::vector<std::vector<FlatTerm>> bins(vw);
+      for (int idx : order) {
+        int best = 0;
+        for (int b = 1; b < vw; b++)
+          if (bins[b].size() < bins[best].size()) best = b;
+        bins[best].insert(bins[best].end(), per_node[idx].begin(), per_node[idx].end());
+      }
+      for (int b = 0; b < vw; b++) {
+        while (bins[b].size() % FLAT_UNROLL) bins[b].push_back(FlatTerm{ONE, ONE, 0, 0, 0.0});
+        out.terms.insert(out.terms.end(), bins[b].begin(), bins[b].end());
+        out.stream_begin.push_back((int) out.terms.size());
+      }
+    }
+  };
+  for (int v = 0; v < 2; v++) {
+    pack_flat(fwd, false, v == 0 ? vw_large : vw_small, prog.ffwd[v]);
+    pack_flat(rev, true, v == 0 ? vw_large : vw_small, prog.frev[v]);
+  }
 }
 
 }    // namespace mtpb200

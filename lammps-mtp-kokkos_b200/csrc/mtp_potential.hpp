@@ -77,15 +77,38 @@ struct ChunkPass {
   std::vector<double> init;         // [nslots] reverse: ginit[node]; forward: unused (0)
 };
 
+// Flat predicated term streams for the CTA-per-atom-chunk program kernel (lane = atom).  The nodes of one
+// dependency level are dealt to VW "virtual warps" (longest list first onto the least loaded one); each virtual
+// warp then owns ONE flat stream of uniform terms per level
+//        acc += coef * A[a] * B[b];   if (store) { dst[node] = acc; acc = 0; }
+// (forward: A = B = dst = moments; reverse: A = dst = adjoints, B = moments).  Row M of both tables holds 1.0, so
+// "acc = m[node]", "acc = ginit[node]" and terms whose adjoint is a constant are ordinary terms with a = M and/or
+// b = M.  Streams are padded with no-ops (a = b = M, coef = 0) to a multiple of FLAT_UNROLL, so the kernel's inner
+// loop is branch-free and all descriptor / operand loads of an unrolled group are independent.
+constexpr int FLAT_UNROLL = 4;
+struct FlatTerm {
+  uint16_t a, b;        // operand rows
+  uint16_t node;        // destination row (valid when store)
+  uint16_t store;       // 1: last term of its node
+  double coef;
+};
+static_assert(sizeof(FlatTerm) == 16, "FlatTerm packing");
+struct FlatPass {
+  int vw = 0, nlevels = 0;
+  std::vector<int> stream_begin;    // [nlevels * vw + 1]
+  std::vector<FlatTerm> terms;
+};
+
 struct Program {
   int depth = 0;                  // number of waves
   ChunkPass cfwd, crev;
+  FlatPass ffwd[2], frev[2];      // for the two atoms-per-CTA shapes of the program kernel (vw = 16 * 32 / NA)
   std::vector<int> level;         // [M]
   ProgramPass fwd, rev;
   std::vector<double> ginit;      // [M]: dE/dm seed, g[map[s]] = xi_s (pair_mtp.cpp:217-218)
 };
 
 // Throws std::runtime_error if the table is not a topologically ordered program.
-void compile_program(const Potential &p, Program &out);
+void compile_program(const Potential &p, Program &out, int vw_large = 16, int vw_small = 64);
 
 }    // namespace mtpb200

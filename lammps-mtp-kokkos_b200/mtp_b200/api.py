@@ -49,7 +49,7 @@ class MTPComputeArgs(C.Structure):
                 ("eflag", C.c_int), ("vflag", C.c_int), ("want_grade", C.c_int), ("natoms_total", C.c_longlong),
                 ("f", C.c_void_p), ("eatom", C.c_void_p), ("vatom", C.c_void_p), ("ev_out", C.c_void_p),
                 ("grades", C.c_void_p), ("cfg_candidate", C.c_void_p), ("within_cutoff", C.c_void_p),
-                ("stream", C.c_void_p)]
+                ("stream", C.c_void_p), ("max_numneigh", C.c_int)]
 
 
 EXPORTS = ["mtp_create_from_file", "mtp_create", "mtp_destroy", "mtp_last_error", "mtp_get_info",
@@ -200,6 +200,7 @@ class MTPB200:
         a.f, a.eatom, a.vatom, a.ev_out = r.f.ctypes.data, r.eatom.ctypes.data, r.vatom.ctypes.data, r.ev.ctypes.data
         a.grades, a.cfg_candidate = r.grades.ctypes.data, r.candidate.ctypes.data
         a.within_cutoff = r.mask.ctypes.data if want_mask else None
+        a.max_numneigh = 0          # mtp_compute_host derives it from the host numneigh array
         self._keep = (x, type_, numneigh, neigh, il, off)
         _check(self.lib, self.lib.mtp_compute_host(self.h, C.byref(a), int(list_changed)))
         return r
@@ -210,7 +211,7 @@ class MTPB200:
     # ---- device buffers (torch tensors as plain device memory) ----------------------------------------
     def compute_device(self, x, type_, ilist, numneigh, neigh, offsets, f, ev_out, *, eatom=None, vatom=None,
                        grades=None, cfg_candidate=None, within=None, stride_i=0, stride_jj=1, eflag=1, vflag=1,
-                       grade=False, natoms_total=0, variant=VARIANT_LARGE, stream=None):
+                       grade=False, natoms_total=0, variant=VARIANT_LARGE, stream=None, max_numneigh=0):
         def ptr(t):
             return None if t is None else t.data_ptr()
 
@@ -224,6 +225,7 @@ class MTPB200:
         a.f, a.eatom, a.vatom, a.ev_out = ptr(f), ptr(eatom), ptr(vatom), ptr(ev_out)
         a.grades, a.cfg_candidate, a.within_cutoff = ptr(grades), ptr(cfg_candidate), ptr(within)
         a.stream = stream
+        a.max_numneigh = int(max_numneigh)
         _check(self.lib, self.lib.mtp_compute(self.h, C.byref(a)))
 
     PROF_CLASSES = ("pack", "gather", "moments", "program", "forces", "grade", "finalize", "site")
