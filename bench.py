@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--ref-cells", type=int, nargs=3, default=None, help="CPU-baseline sample box")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", default="large", choices=["large", "small"])
+    ap.add_argument("--chunksize", type=int, default=32768, help="pair_style ... chunksize N (README.md:44 of the reference)")
     args = ap.parse_args()
 
     from mtp_b200 import almtp, harness
@@ -246,6 +247,7 @@ def main():
 
     variant = api.VARIANT_SMALL if args.variant == "small" else api.VARIANT_LARGE
     mtp = MTPB200(pot_path, selection_state=bool(cfg.get("active_set")), device=local_rank)
+    mtp.set_chunksize(args.chunksize)
 
     # one brick per rank on the grid {1, 2x1x1, 2x2x1, 2x2x2}; at N = 1 all six swaps are periodic self-images
     from mtp_b200 import decomp
@@ -272,6 +274,7 @@ def main():
     t_ev = torch.zeros(8, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     stream = torch.cuda.current_stream().cuda_stream
+    max_nn = int(sysm.numneigh[:nlocal].max())      # what a LAMMPS-KOKKOS list knows as d_neighbors.extent(1)
 
     def step_device():
         # what LAMMPS does around Pair::compute every step: forward comm of x, zero f, compute, reverse comm of f,
@@ -279,7 +282,7 @@ def main():
         halo.forward(t_x)
         t_f.zero_()
         mtp.compute_device(t_x, t_type, t_ilist, t_nn, t_neigh, t_off, t_f, t_ev, eflag=1, vflag=1,
-                           variant=variant, stream=stream)
+                           variant=variant, stream=stream, max_numneigh=max_nn)
         halo.reverse(t_f)
         halo.allreduce_ev(t_ev)
 
@@ -446,7 +449,7 @@ def main():
                        "parallelism": "brick grid %dx%dx%d, one rank per GPU, NCCL send/recv halo (%d B/rank/step)" % (
                            *brick_grid(world), halo.bytes_per_step),
                        "l2": "256 MiB write between timed iterations (L2 flush), per-step CUDA events summed",
-                       "variant": args.variant, "flags": "eflag=1 vflag=1"},
+                       "variant": args.variant, "chunksize": args.chunksize, "flags": "eflag=1 vflag=1"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "energy": energy}
     print(json.dumps(line))

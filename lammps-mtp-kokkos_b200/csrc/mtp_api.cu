@@ -112,16 +112,20 @@ struct ChunkBufs {
 struct FlatBufs {
   DevBuf<int> begin;
   DevBuf<uint4> terms;
+  DevBuf<unsigned> st;
   DevFlatPass upload(const FlatPass &f)
   {
     begin.upload(f.stream_begin, 0);
     static_assert(sizeof(FlatTerm) == sizeof(uint4), "FlatTerm packing");
     terms.upload(reinterpret_cast<const uint4 *>(f.terms.data()), f.terms.size(), 0);
+    st.upload(f.st, 0);
     DevFlatPass d;
     d.stream_begin = begin.p;
     d.terms = terms.p;
+    d.st = st.p;
     d.nlevels = f.nlevels;
     d.vw = f.vw;
+    d.nterms = (int) f.terms.size();
     return d;
   }
 };
@@ -140,6 +144,7 @@ struct mtp_handle {
   PassBufs d_fwd, d_rev;
   ChunkBufs d_cfwd, d_crev;
   FlatBufs d_ffwd[2], d_frev[2];
+  size_t prog_max = 0;
   int pl_na[2] = {0, 0};          // atoms per CTA of the program kernel: throughput shape, latency shape
   DevPotential dpot{};
   // work buffers (grow-only)
@@ -173,7 +178,7 @@ struct mtp_handle {
   DevBuf<double> d_pfld;
   DevBuf<int> d_pj, d_pjt, d_pcnt, d_maxnn;
   int v2_grid_g = 0, v2_grid_m = 0, v2_grid_f = 0, v2_ab = 0;
-  size_t v2_smem_g = 0, v2_smem_f = 0;
+  size_t v2_smem_g = 0, v2_smem_f = 0, v2_smem_m = 0;
   int v2_chunk = 0;
   // optional per-kernel-class device timing (mtp_profile_enable): CUDA events recorded on the launch stream
   bool profile = false;
@@ -191,7 +196,6 @@ namespace {
 void set_device(const mtp_handle *h) { CUDA_CHECK(cudaSetDevice(h->device)); }
 
 // dynamic shared memory a kernel may request: opt-in limit minus its static allocation
-size_t program_smem_bytes(int M, int na) { return ((((size_t) M + 1) * (na + 1) * 8 + 15) & ~(size_t) 15) * 2; }
 
 size_t max_dynamic_smem(const void *fn, size_t optin)
 {
@@ -247,16 +251,18 @@ bool build_v1_tables(mtp_handle *h, int e)
 
 // ---- instantiations of the v2 pair stages, one per D0 (MLIP levels 2..24) ----
 typedef void (*V2GatherKernel)(DevPotential, SiteArgs, PairBuf);
-typedef void (*V2MomentsKernel)(SiteArgs, PairBuf, const short *, double *, int);
-typedef void (*V2ForcesKernel)(SiteArgs, PairBuf, const short *, const double *, int, int, double *);
+typedef void (*V2MomentsKernel)(SiteArgs, PairBuf, double *, int);
+typedef void (*V2ForcesKernel)(SiteArgs, PairBuf, const double *, int, double *);
+constexpr int kV2AB[4] = {64, 32, 16, 8};    // atoms per CTA of the force kernel
 struct V2Entry {
   int d0, R, KF, NP;
   V2GatherKernel gather;
   V2MomentsKernel moments;
-  V2ForcesKernel forces;
+  V2ForcesKernel forces[4];
 };
-#define V2_ENTRY(D) \
-  {D, V2Shape<D>::R, V2Shape<D>::KF, V2Shape<D>::NP, mtp_gather_kernel<V2Shape<D>::R>, mtp_moments_v2<D>, mtp_forces_v2<D>}
+#define V2_ENTRY(D)                                                                                          \
+  {D, V2Shape<D>::R, V2Shape<D>::KF, V2Shape<D>::NP, mtp_gather_kernel<V2Shape<D>::R>, mtp_moments_v2<D>,    \
+   {mtp_forces_v2<D, 64>, mtp_forces_v2<D, 32>, mtp_forces_v2<D, 16>, mtp_forces_v2<D, 8>}}
 const V2Entry kV2[] = {V2_ENTRY(0), V2_ENTRY(1), V2_ENTRY(2), V2_ENTRY(3), V2_ENTRY(4), V2_ENTRY(5),
                        V2_ENTRY(6), V2_ENTRY(7), V2_ENTRY(8), V2_ENTRY(9), V2_ENTRY(10)};
 constexpr int kV2Count = sizeof(kV2) / sizeof(kV2[0]);
@@ -304,15 +310,16 @@ void upload_potential(mtp_handle *h)
     CUDA_CHECK(cudaGetDeviceProperties(&prop0, h->device));
     const size_t prog_max = std::min(max_dynamic_smem((const void *) mtp_program_kernel<false>, prop0.sharedMemPerBlockOptin),
                                      max_dynamic_smem((const void *) mtp_program_kernel<true>, prop0.sharedMemPerBlockOptin));
+    h->prog_max = prog_max;
     h->pl_na_fit = 0;
-    for (int na = 32; na >= 1; na >>= 1)
-      if (program_smem_bytes(p.alpha_moment_count, na) <= prog_max) {
+    for (int na = 32; na >= 2; na >>= 1)
+      if (program_layout(p.alpha_moment_count, na, 2 * p.alpha_index_basic_count, 0, 0, false).total <= prog_max) {
         h->pl_na_fit = na;
         break;
       }
-    h->pl_na[0] = std::max(1, h->pl_na_fit);
+    h->pl_na[0] = std::max(2, h->pl_na_fit);
     h->pl_na[1] = std::min(h->pl_na[0], 8);
-    compile_program(p, h->prog, 16 * 32 / h->pl_na[0], 16 * 32 / h->pl_na[1]);
+    compile_program(p, h->prog, h->pl_na[0], h->pl_na[1]);
     CUDA_CHECK(cudaFuncSetAttribute((const void *) mtp_program_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) prog_max));
     CUDA_CHECK(cudaFuncSetAttribute((const void *) mtp_program_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) prog_max));
   }
@@ -409,21 +416,28 @@ void upload_potential(mtp_handle *h)
       int per_sm = 0;
       CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.gather, 256, h->v2_smem_g));
       h->v2_grid_g = std::max(1, per_sm) * h->sm_count;
-      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.moments, 32 * E.NP, 0));
-      h->v2_grid_m = std::max(1, per_sm) * h->sm_count;
-      // forces: atoms per CTA so that the canonical adjoints stay below ~72 KB of shared memory
-      const size_t ks = (size_t) (E.KF | 1);
-      h->v2_ab = 0;
-      for (int ab = 64; ab >= 8; ab >>= 1)
-        if (ab * ks * 8 + (ab + 1) * 4 <= std::min<size_t>(72 * 1024, max_dynamic_smem((const void *) E.forces, smem_max))) {
-          h->v2_ab = ab;
+      h->v2_smem_m = (size_t) 2 * V2_NT * (3 + E.R) * 33 * 8;
+      ok = h->v2_smem_m <= max_dynamic_smem((const void *) E.moments, smem_max);
+      if (ok) {
+        CUDA_CHECK(cudaFuncSetAttribute((const void *) E.moments, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->v2_smem_m));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.moments, 32 * E.NP, h->v2_smem_m));
+        h->v2_grid_m = std::max(1, per_sm) * h->sm_count;
+      }
+      // forces: atoms per CTA so that two buffers of canonical adjoints stay below ~110 KB (two CTAs per SM)
+      h->v2_ab = -1;
+      for (int q = 0; q < 4 && ok; q++) {
+        const size_t need = (size_t) 2 * E.KF * kV2AB[q] * 8 + (size_t) 2 * (kV2AB[q] + 1) * 4;
+        if (need <= std::min<size_t>(110 * 1024, max_dynamic_smem((const void *) E.forces[q], smem_max))) {
+          h->v2_ab = q;
+          h->v2_smem_f = need;
           break;
         }
-      ok = h->v2_ab > 0;
+      }
+      ok = ok && h->v2_ab >= 0;
       if (ok) {
-        h->v2_smem_f = h->v2_ab * ks * 8 + (h->v2_ab + 1) * 4;
-        CUDA_CHECK(cudaFuncSetAttribute((const void *) E.forces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->v2_smem_f));
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.forces, 256, h->v2_smem_f));
+        const void *fk = (const void *) E.forces[h->v2_ab];
+        CUDA_CHECK(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->v2_smem_f));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk, 256, h->v2_smem_f));
         h->v2_grid_f = std::max(1, per_sm) * h->sm_count;
       }
     }
@@ -560,7 +574,7 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
   int chunk = std::max(1, std::min(h->chunksize, a.inum > 0 ? a.inum : 1));
   if (pipeline) {
     long long fit = std::max(8192LL, (48LL << 20) / (16LL * d.K) / 1024 * 1024);
-    if (use_v2 && h->v2_chunk > 0) fit = h->v2_chunk;
+    if (use_v2) fit = h->v2_chunk > 0 ? h->v2_chunk : (1LL << 30);    // v2: the user's chunksize alone bounds the scratch
     chunk = (int) std::min<long long>(chunk, fit);
   }
   PairBuf pb{};
@@ -590,11 +604,12 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
   } else if (!grade) {
     chunk = a.inum > 0 ? a.inum : 1;
   }
-  const int ld = (chunk + 31) / 32 * 32;
+  const int ld = (chunk + 63) / 64 * 64;
   if (grade) h->d_cand.ensure((size_t) chunk * h->qpad);
   if (pipeline) {
-    h->d_mb.ensure((size_t) d.K * ld);
-    h->d_gb.ensure((size_t) d.K * ld);
+    const size_t rows = use_v2 ? (size_t) kV2[h->v2_entry].KF : (size_t) d.K;
+    h->d_mb.ensure(rows * ld);
+    h->d_gb.ensure(rows * ld);
   }
   if (cfg) CUDA_CHECK(cudaMemsetAsync(h->d_cfg.p, 0, sizeof(double) * h->qpad, st));
   CUDA_CHECK(cudaMemsetAsync(a.ev_out, 0, sizeof(double) * 8, st));
@@ -602,7 +617,7 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
   const int nsuper = a.inum > 0 ? (a.inum + chunk - 1) / chunk : 1;
   const int W = 8;
   // program kernel shape: atoms per CTA (power of two), smaller for small systems so that every SM gets work
-  int na = 1, grid_p_cap = 1;
+  int na = 1, lna = 0, grid_p_cap = 1;
   size_t smem_p = 0;
   if (pipeline) {
     // throughput shape unless the system is too small to give every SM a chunk (or the latency variant is asked for)
@@ -610,10 +625,17 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
     const bool small = a.variant == MTP_VARIANT_SMALL || (nfirst + h->pl_na[0] - 1) / h->pl_na[0] < h->sm_count;
     na = h->pl_na[small ? 1 : 0];
     s.prog_shape = small ? 1 : 0;
-    smem_p = program_smem_bytes(d.M, na);
+    const int nslots = use_v2 ? kV2[h->v2_entry].KF : d.K;
+    const int ntf = d.ffwd[s.prog_shape].nterms, ntr = d.frev[s.prog_shape].nterms;
+    s.prog_dsmem = program_layout(d.M, na, nslots, ntf, ntr, true).total <= h->prog_max ? 1 : 0;
+    if (getenv("MTP_B200_PROG_DSMEM")) s.prog_dsmem = s.prog_dsmem && atoi(getenv("MTP_B200_PROG_DSMEM"));
+    smem_p = program_layout(d.M, na, nslots, ntf, ntr, s.prog_dsmem != 0).total;
+    for (lna = 0; (1 << lna) < na; lna++) {}
+    s.slot_to_k = use_v2 ? h->d_slot_to_k.p : nullptr;
+    s.nslots = nslots;
     int per_sm = 0;
     const void *pk = grade ? (const void *) mtp_program_kernel<true> : (const void *) mtp_program_kernel<false>;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, 512, smem_p));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, PROG_THREADS, smem_p));
     grid_p_cap = std::max(1, per_sm) * h->sm_count;
   }
   const int rows_per_super = pipeline ? grid_p_cap + std::max(h->pl_grid_f[gi], h->v2_grid_f) : h->grid_cap[gi];
@@ -637,20 +659,21 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
       {
         ProfSpan sp(h, MTP_PROF_MOMENTS, st);
         const int gm = std::max(1, std::min(h->v2_grid_m, (n + 31) / 32));
-        E.moments<<<gm, 32 * E.NP, 0, st>>>(s, pb, h->d_slot_to_k.p, h->d_mb.p, ld);
+        E.moments<<<gm, 32 * E.NP, h->v2_smem_m, st>>>(s, pb, h->d_mb.p, ld);
       }
       const int gp = std::max(1, std::min(grid_p_cap, (n + na - 1) / na));
       double *part_p = h->d_partials.p + (size_t) rows_used * 8;
       {
         ProfSpan sp(h, MTP_PROF_PROGRAM, st);
-        mtp_program_kernel<false><<<gp, 512, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, part_p);
+        mtp_program_kernel<false><<<gp, PROG_THREADS, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, lna, part_p);
       }
       rows_used += gp;
-      const int gf = std::max(1, std::min(h->v2_grid_f, (n + h->v2_ab - 1) / h->v2_ab));
+      const int ab = kV2AB[h->v2_ab];
+      const int gf = std::max(1, std::min(h->v2_grid_f, (n + ab - 1) / ab));
       double *part_f = h->d_partials.p + (size_t) rows_used * 8;
       {
         ProfSpan sp(h, MTP_PROF_FORCES, st);
-        E.forces<<<gf, 256, h->v2_smem_f, st>>>(s, pb, h->d_slot_to_k.p, h->d_gb.p, ld, h->v2_ab, part_f);
+        E.forces[h->v2_ab]<<<gf, 256, h->v2_smem_f, st>>>(s, pb, h->d_gb.p, ld, part_f);
       }
       rows_used += gf;
       g_launches += 4;
@@ -665,9 +688,9 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
       double *part_p = h->d_partials.p + (size_t) rows_used * 8;
       {
         ProfSpan sp(h, MTP_PROF_PROGRAM, st);
-        if (grade) mtp_program_kernel<true><<<gp, 512, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, part_p);
+        if (grade) mtp_program_kernel<true><<<gp, PROG_THREADS, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, lna, part_p);
         else
-          mtp_program_kernel<false><<<gp, 512, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, part_p);
+          mtp_program_kernel<false><<<gp, PROG_THREADS, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, lna, part_p);
       }
       rows_used += gp;
       const int gf = std::max(1, std::min(h->pl_grid_f[gi], (n + W - 1) / W));

@@ -28,8 +28,9 @@ struct DevChunkPass {
 // flat predicated term streams (mtp_potential.hpp: FlatPass)
 struct DevFlatPass {
   const int *stream_begin;     // [nlevels * vw + 1]
-  const uint4 *terms;          // {a | b << 16, node | store << 16, coef lo, coef hi}
-  int nlevels, vw;
+  const uint4 *terms;          // {a_off, b_off, coef lo, coef hi}
+  const unsigned *st;          // destination row byte offset | store flag
+  int nlevels, vw, nterms;
 };
 
 struct DevPotential {
@@ -72,6 +73,9 @@ struct SiteArgs {
   int cand_ld;            // Qpad
   int first_ii;           // chunk offset into ilist (grade steps)
   int prog_shape;         // which flat-stream table set the program kernel uses (0 throughput, 1 latency)
+  int prog_dsmem;         // program kernel: term streams staged in shared memory
+  const short *slot_to_k; // rows of mb / gb are canonical slots (v2 pipeline) instead of basic-moment indices; or NULL
+  int nslots;             // rows of mb / gb
   int *status;
 };
 

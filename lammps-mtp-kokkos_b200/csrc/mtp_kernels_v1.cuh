@@ -496,31 +496,66 @@ mtp_moments_kernel(DevPotential pot, V1Tables tb, SiteArgs a, double *__restrict
 //     acc += coef * A[a] * B[b];  if (store) { dst[node] = acc; acc = 0; }
 // so the inner loop has no data-dependent branch and the descriptor + operand loads of FLAT_UNROLL terms are all
 // independent (the only serial chain is the accumulator).
-template <bool REVERSE>
-__device__ __forceinline__ void run_flat_pass(const DevFlatPass &ps, double *cm, double *cg, int NAp, int al, int vwarp)
+// shared-memory plan of the program kernel (host and device agree through this one function)
+constexpr int PROG_THREADS = 256;    // 8 warps; every thread owns TWO adjacent atoms of the chunk (double2 operands)
+struct ProgLayout {
+  size_t node_bytes, off_cg, off_epart, off_s2k, off_terms[2], off_st[2], total;
+};
+__host__ __device__ inline ProgLayout program_layout(int M, int na, int nslots, int nterms_f, int nterms_r, bool dsmem)
 {
-  const double *A = REVERSE ? cg : cm;
-  double *dst = REVERSE ? cg : cm;
+  ProgLayout L;
+  const int vw = 16 * 32 / na;
+  L.node_bytes = ((size_t) (M + 1) * na * 8 + 15) & ~(size_t) 15;
+  L.off_cg = L.node_bytes;
+  L.off_epart = 2 * L.node_bytes;
+  L.off_s2k = L.off_epart + (size_t) vw * na * 8;
+  size_t o = (L.off_s2k + (size_t) nslots * 2 + 15) & ~(size_t) 15;
+  L.off_terms[0] = o;
+  if (dsmem) o += (size_t) nterms_f * 16;
+  L.off_terms[1] = o;
+  if (dsmem) o += (size_t) nterms_r * 16;
+  L.off_st[0] = o;
+  if (dsmem) o += (size_t) nterms_f * 4;
+  L.off_st[1] = o;
+  if (dsmem) o += (size_t) nterms_r * 4;
+  L.total = (o + 15) & ~(size_t) 15;
+  return L;
+}
+
+template <bool REVERSE>
+__device__ __forceinline__ void run_flat_pass(const DevFlatPass &ps, const uint4 *__restrict__ terms,
+                                              const unsigned *__restrict__ st, unsigned char *cm_lane,
+                                              unsigned char *cg_lane, int vwarp)
+{
+  const unsigned char *A = REVERSE ? cg_lane : cm_lane;
+  unsigned char *dst = REVERSE ? cg_lane : cm_lane;
   for (int lv = 0; lv < ps.nlevels; lv++) {
     const int t0 = ps.stream_begin[lv * ps.vw + vwarp], t1 = ps.stream_begin[lv * ps.vw + vwarp + 1];
-    double acc = 0.0;
-    for (int t = t0; t < t1; t += 4) {
-      uint4 d[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) d[u] = __ldg(ps.terms + t + u);
-      double va[4], vb[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        va[u] = A[(d[u].x & 0xffffu) * NAp + al];
-        vb[u] = cm[(d[u].x >> 16) * NAp + al];
+    double2 acc = make_double2(0.0, 0.0);
+    for (int t = t0; t < t1; t += 8) {
+      uint4 d[8];
+      unsigned sw[8];
+      {
+        const uint4 s0 = *reinterpret_cast<const uint4 *>(st + t), s1 = *reinterpret_cast<const uint4 *>(st + t + 4);
+        sw[0] = s0.x, sw[1] = s0.y, sw[2] = s0.z, sw[3] = s0.w;
+        sw[4] = s1.x, sw[5] = s1.y, sw[6] = s1.z, sw[7] = s1.w;
       }
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < 8; u++) d[u] = terms[t + u];
+      double2 va[8], vb[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        va[u] = *reinterpret_cast<const double2 *>(A + d[u].x);
+        vb[u] = *reinterpret_cast<const double2 *>(cm_lane + d[u].y);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
         const double coef = __hiloint2double((int) d[u].w, (int) d[u].z);
-        acc += coef * va[u] * vb[u];
-        if (d[u].y >> 16) {
-          dst[(d[u].y & 0xffffu) * NAp + al] = acc;
-          acc = 0.0;
+        acc.x = fma(coef * va[u].x, vb[u].x, acc.x);
+        acc.y = fma(coef * va[u].y, vb[u].y, acc.y);
+        if (sw[u] & 1u) {
+          *reinterpret_cast<double2 *>(dst + (sw[u] & ~7u)) = acc;
+          acc = make_double2(0.0, 0.0);
         }
       }
     }
@@ -528,69 +563,107 @@ __device__ __forceinline__ void run_flat_pass(const DevFlatPass &ps, double *cm,
   }
 }
 
+// NA = atoms per CTA (power of two, >= 2), lna = log2(NA)
 template <bool GRADE>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(PROG_THREADS)
 mtp_program_kernel(DevPotential pot, SiteArgs a, const double *__restrict__ mb, double *__restrict__ gb, int ld,
-                   int NA, double *__restrict__ partials)
+                   int NA, int lna, double *__restrict__ partials)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-  const int NAp = NA + 1;
-  const size_t node_bytes = ((size_t) (pot.M + 1) * NAp * 8 + 15) & ~(size_t) 15;
-  double *cm = reinterpret_cast<double *>(smem);
-  double *cg = reinterpret_cast<double *>(smem + node_bytes);
-  const int al_t = lane & (NA - 1);         // atom of this lane
-  const int vwarp = warp * (32 / NA) + lane / NA;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int fi = a.prog_shape;
+  const DevFlatPass &pf = pot.ffwd[fi], &pr = pot.frev[fi];
+  const int nslots = a.slot_to_k ? a.nslots : pot.K;
+  const ProgLayout L = program_layout(pot.M, NA, nslots, pf.nterms, pr.nterms, a.prog_dsmem != 0);
+  double *cm = reinterpret_cast<double *>(smem);
+  double *cg = reinterpret_cast<double *>(smem + L.off_cg);
+  double *epart = reinterpret_cast<double *>(smem + L.off_epart);
+  short *s2k = reinterpret_cast<short *>(smem + L.off_s2k);
+  const int lpv = NA >> 1;                      // lanes per virtual warp (each lane = 2 atoms)
+  const int al2 = (lane & (lpv - 1)) * 2;       // first atom of this lane
+  const int VW = (PROG_THREADS * 2) >> lna;
+  const int vwarp = threadIdx.x >> (lna - 1);
   const int radial_count = pot.S * pot.S * pot.R * pot.B;
   double e_thread = 0.0;
 
-  for (int t = threadIdx.x; t < NAp; t += blockDim.x) cm[pot.M * NAp + t] = cg[pot.M * NAp + t] = 1.0;
+  // one-time setup: constant row, slot map, term streams
+  for (int t = threadIdx.x; t < NA; t += blockDim.x) cm[pot.M * NA + t] = cg[pot.M * NA + t] = 1.0;
+  for (int t = threadIdx.x; t < nslots; t += blockDim.x) s2k[t] = a.slot_to_k ? a.slot_to_k[t] : (short) t;
+  const uint4 *terms_f = pf.terms, *terms_r = pr.terms;
+  const unsigned *st_f = pf.st, *st_r = pr.st;
+  if (a.prog_dsmem) {
+    uint4 *tf = reinterpret_cast<uint4 *>(smem + L.off_terms[0]), *tr = reinterpret_cast<uint4 *>(smem + L.off_terms[1]);
+    unsigned *sf = reinterpret_cast<unsigned *>(smem + L.off_st[0]), *sr = reinterpret_cast<unsigned *>(smem + L.off_st[1]);
+    for (int t = threadIdx.x; t < pf.nterms; t += blockDim.x) {
+      tf[t] = pf.terms[t];
+      sf[t] = pf.st[t];
+    }
+    for (int t = threadIdx.x; t < pr.nterms; t += blockDim.x) {
+      tr[t] = pr.terms[t];
+      sr[t] = pr.st[t];
+    }
+    terms_f = tf;
+    terms_r = tr;
+    st_f = sf;
+    st_r = sr;
+  }
+  unsigned char *cm_lane = smem + (size_t) al2 * 8, *cg_lane = smem + L.off_cg + (size_t) al2 * 8;
+  __syncthreads();
 
   for (int chunk0 = blockIdx.x * NA; chunk0 < a.inum; chunk0 += gridDim.x * NA) {
     const int na = min(NA, a.inum - chunk0);
     // basic moments of the chunk -> cm (rows of NA atoms, coalesced)
-    for (int t = threadIdx.x; t < pot.K * NA; t += blockDim.x) {
-      const int k = t / NA, al = t - k * NA;
-      cm[k * NAp + al] = al < na ? mb[(size_t) k * ld + chunk0 + al] : 0.0;
+#pragma unroll 4
+    for (int t = threadIdx.x; t < (nslots << lna); t += blockDim.x) {
+      const int s = t >> lna, al = t & (NA - 1);
+      const int k = s2k[s];
+      const double v = al < na ? mb[(size_t) s * ld + chunk0 + al] : 0.0;
+      if (k >= 0) cm[(k << lna) + al] = v;
     }
     __syncthreads();
-    run_flat_pass<false>(pot.ffwd[fi], cm, cg, NAp, al_t, vwarp);
-    // site energies: one warp per atom, lanes stride the basis functions
+    run_flat_pass<false>(pf, terms_f, st_f, cm_lane, cg_lane, vwarp);
+    // site energies: the virtual warps split the basis functions; fixed-order reduction
     if (a.eflag_global || a.eflag_atom || GRADE) {
-      for (int al = warp; al < na; al += W) {
-        const int i = a.ilist ? a.ilist[a.first_ii + chunk0 + al] : a.first_ii + chunk0 + al;
-        double e = 0.0;
-        for (int s = lane; s < pot.A; s += 32) {
-          const double bm = cm[pot.map[s] * NAp + al];
-          e += pot.lin[s] * bm;
-          if (GRADE) a.cand_rows[(size_t) (chunk0 + al) * a.cand_ld + radial_count + pot.S + s] = bm;
+      double e0 = 0.0, e1 = 0.0;
+      for (int s = vwarp; s < pot.A; s += VW) {
+        const double2 bm = *reinterpret_cast<const double2 *>(cm + ((size_t) pot.map[s] << lna) + al2);
+        const double c = pot.lin[s];
+        e0 = fma(c, bm.x, e0);
+        e1 = fma(c, bm.y, e1);
+        if (GRADE) {
+          if (al2 < na) a.cand_rows[(size_t) (chunk0 + al2) * a.cand_ld + radial_count + pot.S + s] = bm.x;
+          if (al2 + 1 < na) a.cand_rows[(size_t) (chunk0 + al2 + 1) * a.cand_ld + radial_count + pot.S + s] = bm.y;
         }
+      }
+      *reinterpret_cast<double2 *>(epart + (size_t) vwarp * NA + al2) = make_double2(e0, e1);
+      __syncthreads();
+      if (threadIdx.x < na) {
+        const int al = threadIdx.x;
+        const int i = a.ilist ? a.ilist[a.first_ii + chunk0 + al] : a.first_ii + chunk0 + al;
         int itype = (int) a.xt[i].t;
         if (itype < 0 || itype >= pot.S) itype = 0;
-        e = warp_sum(e) + pot.species[itype];
-        if (a.eflag_atom && lane == 0) a.eatom[i] = e;
-        if (a.eflag_global && lane == 0) e_thread += e;
+        double es = 0.0;
+        for (int v = 0; v < VW; v++) es += epart[v * NA + al];
+        es += pot.species[itype];
+        if (a.eflag_atom) a.eatom[i] = es;
+        if (a.eflag_global) e_thread += es;
       }
     }
-    run_flat_pass<true>(pot.frev[fi], cm, cg, NAp, al_t, vwarp);
+    run_flat_pass<true>(pr, terms_r, st_r, cm_lane, cg_lane, vwarp);
     // adjoints of the basic moments -> gb
-    for (int t = threadIdx.x; t < pot.K * NA; t += blockDim.x) {
-      const int k = t / NA, al = t - k * NA;
-      if (al < na) gb[(size_t) k * ld + chunk0 + al] = cg[k * NAp + al];
+#pragma unroll 4
+    for (int t = threadIdx.x; t < (nslots << lna); t += blockDim.x) {
+      const int s = t >> lna, al = t & (NA - 1);
+      const int k = s2k[s];
+      if (al < na) gb[(size_t) s * ld + chunk0 + al] = k >= 0 ? cg[(k << lna) + al] : 0.0;
     }
     __syncthreads();
   }
 
-  // per-CTA energy partial (fixed order)
-  __shared__ double s_e[16];
-  if (lane == 0) s_e[warp] = e_thread;
-  __syncthreads();
-  if (threadIdx.x < 8) {
-    double s = 0.0;
-    if (threadIdx.x == 0)
-      for (int w = 0; w < W; w++) s += s_e[w];
-    partials[(size_t) blockIdx.x * 8 + threadIdx.x] = s;
+  // per-CTA energy partial (fixed order): only warp 0 holds per-atom energies
+  if (warp == 0) {
+    const double s = warp_sum(e_thread);
+    if (lane < 8) partials[(size_t) blockIdx.x * 8 + lane] = lane == 0 ? s : 0.0;
   }
 }
 

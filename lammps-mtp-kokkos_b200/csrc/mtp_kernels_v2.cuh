@@ -108,6 +108,20 @@ template <int D0> struct V2Shape {
 constexpr int V2_PEND = 64;
 constexpr int V2_NT = 16;      // pairs per staged tile of the moment kernel
 
+// Ampere-style asynchronous copies global -> shared (LDGSTS): no registers, many in flight per thread
+__device__ __forceinline__ void cp_async8_zfill(void *smem_dst, const void *gsrc, int src_bytes /*8 or 0*/)
+{
+  const unsigned d = (unsigned) __cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+  const unsigned d = (unsigned) __cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
 // ===================================================================================================== gather
 template <int R>
 __global__ void __launch_bounds__(256)
@@ -260,37 +274,69 @@ __device__ __forceinline__ void v2_fwd_accumulate(double ux, double uy, double u
   V2FwdA<D0, P, 0>::run(1.0, ux, uy, uz, f, acc);
 }
 
+// Work items of a CTA are (atom block, tile of V2_NT pairs) in order; the tile of item i + 1 is in flight
+// (cp.async into the other buffer) while item i is consumed, across block boundaries too.
 template <int D0, int P>
-__device__ __forceinline__ void v2_moments_body(const SiteArgs &a, const PairBuf &pb, const short *__restrict__ slot_to_k,
-                                                double *__restrict__ mb, int ld, double *tile)
+__device__ __forceinline__ void v2_moments_body(const SiteArgs &a, const PairBuf &pb, double *__restrict__ mb, int ld,
+                                                double *tiles)
 {
   using Sh = V2Shape<D0>;
-  constexpr int R = Sh::R, NF = Sh::NF, NW = Sh::NP;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int R = Sh::R, NF = Sh::NF, NTH = 32 * Sh::NP, TILE = V2_NT * NF * 33;
+  const int lane = threadIdx.x & 31;
   const int nblk = (a.inum + 31) >> 5;
-  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    const int ii = blk * 32 + lane;
-    const int cnt_l = ii < a.inum ? pb.pcnt[ii] : 0;
-    int nmax = cnt_l;
+
+  auto load_cnt = [&](int blk) { return (blk < nblk && blk * 32 + lane < a.inum) ? pb.pcnt[blk * 32 + lane] : 0; };
+  auto warp_max_i = [&](int v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
-    double acc[Sh::AMAX];
-#pragma unroll
-    for (int t = 0; t < Sh::AMAX; t++) acc[t] = 0.0;
-    for (int n0 = 0; n0 < nmax; n0 += V2_NT) {
-      __syncthreads();    // previous tile fully consumed
-      // stage: the warps split the 32 atoms; 16 lanes cover the tile's pairs of one field (coalesced 128 B)
-      for (int al = warp; al < 32; al += NW) {
-        const int cnt_al = __shfl_sync(FULL, cnt_l, al);
-        const long long base = (long long) (blk * 32 + al) * pb.ncap + n0;
-        for (int e = lane; e < V2_NT * NF; e += 32) {
-          const int fi = e / V2_NT, n = e - fi * V2_NT;
-          const int gf = fi < 3 ? fi : fi + 1;    // skip the distance field
-          const double v = (n0 + n < cnt_al) ? pb.fld[(size_t) gf * pb.cap + base + n] : 0.0;
-          tile[(n * NF + fi) * 33 + al] = v;
-        }
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+  };
+  // stage tile (blk, n0) into buffer buf; cnt_l = this lane's pair count for atom `lane` of blk
+  auto stage = [&](int buf, int blk, int n0, int cnt_l) {
+    double *tile = tiles + (size_t) buf * TILE;
+    for (int e0 = 0; e0 < 32 * V2_NT * NF; e0 += NTH) {    // (al, field, n), n fastest: 128-byte runs
+      const int e = e0 + threadIdx.x;
+      const bool valid = e < 32 * V2_NT * NF;
+      const int al = valid ? e / (V2_NT * NF) : 0, r = e - al * (V2_NT * NF);
+      const int fi = r / V2_NT, n = r - fi * V2_NT;
+      const int gf = fi < 3 ? fi : fi + 1;    // skip the distance field
+      const int cnt_al = __shfl_sync(FULL, cnt_l, al);
+      if (valid) {
+        const bool live = n0 + n < cnt_al;
+        const double *src = pb.fld + (size_t) gf * pb.cap + (size_t) (blk * 32 + al) * pb.ncap + (live ? n0 + n : 0);
+        cp_async8_zfill(tile + (n * NF + fi) * 33 + al, src, live ? 8 : 0);
       }
-      __syncthreads();
+    }
+    cp_async_commit();
+  };
+
+  int blk = blockIdx.x;
+  if (blk >= nblk) return;
+  int cnt_l = load_cnt(blk), nmax = warp_max_i(cnt_l), n0 = 0, buf = 0;
+  int cnt_nb = load_cnt(blk + gridDim.x);    // next block's counts, one block ahead
+  stage(0, blk, 0, cnt_l);
+  double acc[Sh::AMAX];
+#pragma unroll
+  for (int t = 0; t < Sh::AMAX; t++) acc[t] = 0.0;
+
+  while (true) {
+    // next item
+    int nblk_i = blk, nn0 = n0 + V2_NT, ncnt = cnt_l;
+    const bool last_tile = nn0 >= nmax;
+    if (last_tile) {
+      nblk_i = blk + gridDim.x;
+      nn0 = 0;
+      ncnt = cnt_nb;
+    }
+    const bool have_next = nblk_i < nblk;
+    if (have_next) {
+      stage(buf ^ 1, nblk_i, nn0, ncnt);
+      cp_async_wait<1>();
+    } else
+      cp_async_wait<0>();
+    __syncthreads();
+    {
+      const double *tile = tiles + (size_t) buf * TILE;
       const int nt = min(V2_NT, nmax - n0);
       for (int n = 0; n < nt; n++) {
         const double *rec = tile + (size_t) n * NF * 33 + lane;
@@ -301,42 +347,54 @@ __device__ __forceinline__ void v2_moments_body(const SiteArgs &a, const PairBuf
         v2_fwd_accumulate<D0, P>(ux, uy, uz, f, acc);    // padded records have f = 0
       }
     }
-    if (ii < a.inum) {
-      constexpr int beg = Sh::pass_begin(P), cnt = Sh::pass_begin(P + 1) - Sh::pass_begin(P);
+    if (last_tile) {
+      const int ii = blk * 32 + lane;
+      if (ii < a.inum) {
+        constexpr int beg = Sh::pass_begin(P), cnt = Sh::pass_begin(P + 1) - Sh::pass_begin(P);
 #pragma unroll
-      for (int t = 0; t < cnt; t++) {
-        const int k = slot_to_k[beg + t];
-        if (k >= 0) mb[(size_t) k * ld + ii] = acc[t];
+        for (int t = 0; t < cnt; t++) mb[(size_t) (beg + t) * ld + ii] = acc[t];    // rows = canonical slots
       }
+#pragma unroll
+      for (int t = 0; t < Sh::AMAX; t++) acc[t] = 0.0;
     }
+    __syncthreads();    // everyone is done with `buf` before it is refilled
+    if (!have_next) break;
+    if (last_tile) {
+      blk = nblk_i;
+      cnt_l = cnt_nb;
+      nmax = warp_max_i(cnt_l);
+      cnt_nb = load_cnt(blk + gridDim.x);
+    }
+    n0 = nn0;
+    buf ^= 1;
   }
 }
 
 template <int D0, int P> struct V2PassDispatch {
-  __device__ __forceinline__ static void run(int pass, const SiteArgs &a, const PairBuf &pb, const short *slot_to_k,
-                                             double *mb, int ld, double *tile)
+  __device__ __forceinline__ static void run(int pass, const SiteArgs &a, const PairBuf &pb, double *mb, int ld,
+                                             double *tiles)
   {
-    if (pass == P) v2_moments_body<D0, P>(a, pb, slot_to_k, mb, ld, tile);
+    if (pass == P) v2_moments_body<D0, P>(a, pb, mb, ld, tiles);
     else
-      V2PassDispatch<D0, P + 1>::run(pass, a, pb, slot_to_k, mb, ld, tile);
+      V2PassDispatch<D0, P + 1>::run(pass, a, pb, mb, ld, tiles);
   }
 };
 template <int D0> struct V2PassDispatch<D0, V2Shape<D0>::NP> {
-  __device__ __forceinline__ static void run(int, const SiteArgs &, const PairBuf &, const short *, double *, int, double *) {}
+  __device__ __forceinline__ static void run(int, const SiteArgs &, const PairBuf &, double *, int, double *) {}
 };
 
 template <int D0>
-__global__ void __launch_bounds__(32 * V2Shape<D0>::NP)
-mtp_moments_v2(SiteArgs a, PairBuf pb, const short *__restrict__ slot_to_k, double *__restrict__ mb, int ld)
+__global__ void __launch_bounds__(32 * V2Shape<D0>::NP, (288 / (32 * V2Shape<D0>::NP)) > 0 ? (288 / (32 * V2Shape<D0>::NP)) : 1)
+mtp_moments_v2(SiteArgs a, PairBuf pb, double *__restrict__ mb, int ld)
 {
-  __shared__ double tile[V2_NT * V2Shape<D0>::NF * 33];
-  V2PassDispatch<D0, 0>::run(threadIdx.x >> 5, a, pb, slot_to_k, mb, ld, tile);
+  extern __shared__ __align__(16) unsigned char smem[];    // two tiles of V2_NT x NF x 33 doubles
+  V2PassDispatch<D0, 0>::run(threadIdx.x >> 5, a, pb, mb, ld, reinterpret_cast<double *>(smem));
 }
 
 // ===================================================================================================== forces
 // gradient of sum_mu f_mu(d) P_mu(u), P_mu(u) = sum_q g[q][mu] u^q, by three nested Horner sweeps; g = canonical row
-template <int D0>
-__device__ __forceinline__ void v2_pair_force(const double *__restrict__ gr, double ux, double uy, double uz,
+template <int D0, int AB>
+__device__ __forceinline__ void v2_pair_force(const double *__restrict__ gr /* g + al, row stride AB */, double ux, double uy, double uz,
                                               const double (&fvi)[V2Shape<D0>::R], const double (&fder)[V2Shape<D0>::R],
                                               double &Fx, double &Fy, double &Fz)
 {
@@ -358,7 +416,7 @@ __device__ __forceinline__ void v2_pair_force(const double *__restrict__ gr, dou
         double W = 0, Wd = 0;
 #pragma unroll
         for (int mu = 0; mu < rc; mu++) {
-          const double g = gr[sl + mu];
+          const double g = gr[(sl + mu) * AB];
           if (mu == 0) {
             W = fvi[0] * g;
             Wd = fder[0] * g;
@@ -406,30 +464,33 @@ __device__ __forceinline__ void v2_pair_force(const double *__restrict__ gr, dou
   Fz = fma(uz, S, Pz);
 }
 
-template <int D0>
+template <int D0, int AB>
 __global__ void __launch_bounds__(256)
-mtp_forces_v2(SiteArgs a, PairBuf pb, const short *__restrict__ slot_to_k, const double *__restrict__ gb, int ld,
-              int AB, double *__restrict__ partials)
+mtp_forces_v2(SiteArgs a, PairBuf pb, const double *__restrict__ gb, int ld, double *__restrict__ partials)
 {
   using Sh = V2Shape<D0>;
-  constexpr int R = Sh::R, KS = Sh::KF | 1;
+  constexpr int R = Sh::R, KF = Sh::KF, GSZ = KF * AB;
   extern __shared__ __align__(16) unsigned char smem[];
-  double *g = reinterpret_cast<double *>(smem);               // [AB][KS] canonical adjoints
-  int *pre = reinterpret_cast<int *>(g + (size_t) AB * KS);   // [AB + 1] exclusive prefix of pcnt
+  double *gbuf = reinterpret_cast<double *>(smem);                      // [2][KF][AB] adjoints, rows = canonical slots
+  int *prebuf = reinterpret_cast<int *>(gbuf + 2 * (size_t) GSZ);       // [2][AB + 1] exclusive prefix of pcnt
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double vloc[6] = {0, 0, 0, 0, 0, 0};
-
   const int nblk = (a.inum + AB - 1) / AB;
-  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    const int ii0 = blk * AB, na = min(AB, a.inum - ii0);
-    __syncthreads();    // previous block's g / pre no longer in use
-    for (int t = threadIdx.x; t < AB * Sh::KF; t += blockDim.x) {
-      const int s = t / AB, al = t - s * AB;    // atom fastest: coalesced rows of gb
-      const int k = slot_to_k[s];
-      g[(size_t) al * KS + s] = (k >= 0 && al < na) ? gb[(size_t) k * ld + ii0 + al] : 0.0;
+
+  // asynchronous fill of one block's adjoints (straight 16-byte copies of the rows of gb) + pair-count prefix
+  auto prefetch = [&](int buf, int blk) {
+    double *g = gbuf + (size_t) buf * GSZ;
+    const int ii0 = blk * AB;
+    for (int c = threadIdx.x; c < KF * (AB / 2); c += 256) {
+      const int s = c / (AB / 2), c2 = c - s * (AB / 2);
+      cp_async16(g + s * AB + 2 * c2, gb + (size_t) s * ld + ii0 + 2 * c2);
     }
-    if (warp == 0) {    // exclusive scan of the block's pair counts (AB <= 128: 4 values per lane)
+    cp_async_commit();
+    if (warp == 0) {
+      int *pre = prebuf + buf * (AB + 1);
+      const int na = min(AB, a.inum - ii0);
       int run = 0;
+#pragma unroll
       for (int b0 = 0; b0 < AB; b0 += 32) {
         const int al = b0 + lane;
         const int c = (al < na) ? pb.pcnt[ii0 + al] : 0;
@@ -444,15 +505,26 @@ mtp_forces_v2(SiteArgs a, PairBuf pb, const short *__restrict__ slot_to_k, const
       }
       if (lane == 0) pre[AB] = run;
     }
-    __syncthreads();
+  };
+
+  int blk = blockIdx.x, buf = 0;
+  if (blk < nblk) prefetch(0, blk);
+  for (; blk < nblk; blk += gridDim.x, buf ^= 1) {
+    cp_async_wait<0>();
+    __syncthreads();    // this block's adjoints + prefix are in place; the other buffer is free
+    if (blk + gridDim.x < nblk) prefetch(buf ^ 1, blk + gridDim.x);
+    const double *g = gbuf + (size_t) buf * GSZ;
+    const int *pre = prebuf + buf * (AB + 1);
+    const int ii0 = blk * AB;
     const int total = pre[AB];
-    for (int p0 = 0; p0 < total; p0 += blockDim.x) {
+    for (int p0 = 0; p0 < total; p0 += 256) {
       const int p = p0 + threadIdx.x;
       const bool live = p < total;
       int al = 0;
       if (live) {    // largest al with pre[al] <= p
         int lo = 0, hi = AB;
-        while (hi - lo > 1) {
+#pragma unroll
+        for (int it = 0; (1 << it) < AB; it++) {
           const int mid = (lo + hi) >> 1;
           if (pre[mid] <= p) lo = mid;
           else
@@ -472,7 +544,7 @@ mtp_forces_v2(SiteArgs a, PairBuf pb, const short *__restrict__ slot_to_k, const
           fvi[mu] = pb.fld[(4 + mu) * pb.cap + s] * invd;
           fder[mu] = pb.fld[(4 + R + mu) * pb.cap + s];
         }
-        v2_pair_force<D0>(g + (size_t) al * KS, ux, uy, uz, fvi, fder, Fx, Fy, Fz);
+        v2_pair_force<D0, AB>(g + al, ux, uy, uz, fvi, fder, Fx, Fy, Fz);
         const int j = pb.pj[s];
         atomicAdd(&a.f[3 * (size_t) j], -Fx);
         atomicAdd(&a.f[3 * (size_t) j + 1], -Fy);

@@ -385,7 +385,7 @@ void pack_pass(const std::vector<std::vector<NodeList>> &per_level, ProgramPass 
 
 }    // namespace
 
-void compile_program(const Potential &p, Program &prog, int vw_large, int vw_small)
+void compile_program(const Potential &p, Program &prog, int na_large, int na_small)
 {
   const int M = p.alpha_moment_count, T = p.alpha_index_times_count, A = p.alpha_scalar_count;
   const int *times = p.alpha_index_times.data();
@@ -493,41 +493,49 @@ void compile_program(const Potential &p, Program &prog, int vw_large, int vw_sma
   pack_chunk(rev, true, prog.crev);
 
   // ---- flat predicated streams ----
-  const uint16_t ONE = (uint16_t) M;    // row of 1.0
-  auto pack_flat = [&](const std::vector<std::vector<NodeList>> &levels, bool reverse, int vw, FlatPass &out) {
+  struct Raw {
+    int a, b, node;
+    bool store;
+    double coef;
+  };
+  const int ONE = M;    // row of 1.0
+  auto pack_flat = [&](const std::vector<std::vector<NodeList>> &levels, bool reverse, int na, FlatPass &out) {
     out = FlatPass();
+    const int vw = 16 * 32 / na;
+    const uint32_t row_bytes = (uint32_t) na * 8;    // rows are [node][atom], no padding
     out.vw = vw;
+    out.na = na;
     out.nlevels = (int) levels.size();
     out.stream_begin.push_back(0);
     for (const auto &lv : levels) {
       // node -> uniform terms (base first, then the list in its original order)
-      std::vector<std::vector<FlatTerm>> per_node;
+      std::vector<std::vector<Raw>> per_node;
       for (const NodeList &l : lv) {
-        std::vector<FlatTerm> t;
+        std::vector<Raw> t;
         if (!reverse) {
-          if (l.node < p.alpha_index_basic_count) t.push_back(FlatTerm{(uint16_t) l.node, ONE, 0, 0, 1.0});
-          for (const ProgramTerm &q : l.terms) t.push_back(FlatTerm{q.a, q.b, 0, 0, (double) q.mult});
+          if (l.node < p.alpha_index_basic_count) t.push_back(Raw{l.node, ONE, 0, false, 1.0});
+          for (const ProgramTerm &q : l.terms) t.push_back(Raw{q.a, q.b, 0, false, (double) q.mult});
         } else {
-          t.push_back(FlatTerm{ONE, ONE, 0, 0, prog.ginit[l.node]});
+          t.push_back(Raw{ONE, ONE, 0, false, prog.ginit[l.node]});
           for (const ProgramTerm &q : l.terms) {
             if (!is_source[q.a]) {
               const double c = (double) q.mult * prog.ginit[q.a];    // g[a3] stays ginit[a3]
               if (c == 0.0) continue;
-              t.push_back(FlatTerm{ONE, q.b, 0, 0, c});
+              t.push_back(Raw{ONE, q.b, 0, false, c});
             } else
-              t.push_back(FlatTerm{q.a, q.b, 0, 0, (double) q.mult});
+              t.push_back(Raw{q.a, q.b, 0, false, (double) q.mult});
           }
         }
-        if (t.empty()) t.push_back(FlatTerm{ONE, ONE, 0, 0, 0.0});
-        for (auto &x : t) x.node = (uint16_t) l.node;
-        t.back().store = 1;
+        if (t.empty()) t.push_back(Raw{ONE, ONE, 0, false, 0.0});
+        for (auto &x : t) x.node = l.node;
+        t.back().store = true;
         per_node.push_back(std::move(t));
       }
       std::vector<int> order(per_node.size());
       for (size_t i = 0; i < order.size(); i++) order[i] = (int) i;
       std::stable_sort(order.begin(), order.end(),
                        [&](int x, int y) { return per_node[x].size() > per_node[y].size(); });
-      std::vector<std::vector<FlatTerm>> bins(vw);
+      std::vector<std::vector<Raw>> bins(vw);
       for (int idx : order) {
         int best = 0;
         for (int b = 1; b < vw; b++)
@@ -535,15 +543,18 @@ void compile_program(const Potential &p, Program &prog, int vw_large, int vw_sma
         bins[best].insert(bins[best].end(), per_node[idx].begin(), per_node[idx].end());
       }
       for (int b = 0; b < vw; b++) {
-        while (bins[b].size() % FLAT_UNROLL) bins[b].push_back(FlatTerm{ONE, ONE, 0, 0, 0.0});
-        out.terms.insert(out.terms.end(), bins[b].begin(), bins[b].end());
+        while (bins[b].size() % FLAT_UNROLL) bins[b].push_back(Raw{ONE, ONE, ONE, false, 0.0});
+        for (const Raw &r : bins[b]) {
+          out.terms.push_back(FlatTerm{(uint32_t) r.a * row_bytes, (uint32_t) r.b * row_bytes, r.coef});
+          out.st.push_back((uint32_t) r.node * row_bytes | (r.store ? 1u : 0u));
+        }
         out.stream_begin.push_back((int) out.terms.size());
       }
     }
   };
   for (int v = 0; v < 2; v++) {
-    pack_flat(fwd, false, v == 0 ? vw_large : vw_small, prog.ffwd[v]);
-    pack_flat(rev, true, v == 0 ? vw_large : vw_small, prog.frev[v]);
+    pack_flat(fwd, false, v == 0 ? na_large : na_small, prog.ffwd[v]);
+    pack_flat(rev, true, v == 0 ? na_large : na_small, prog.frev[v]);
   }
 }
 

@@ -85,18 +85,17 @@ struct ChunkPass {
 // "acc = m[node]", "acc = ginit[node]" and terms whose adjoint is a constant are ordinary terms with a = M and/or
 // b = M.  Streams are padded with no-ops (a = b = M, coef = 0) to a multiple of FLAT_UNROLL, so the kernel's inner
 // loop is branch-free and all descriptor / operand loads of an unrolled group are independent.
-constexpr int FLAT_UNROLL = 4;
+constexpr int FLAT_UNROLL = 8;
 struct FlatTerm {
-  uint16_t a, b;        // operand rows
-  uint16_t node;        // destination row (valid when store)
-  uint16_t store;       // 1: last term of its node
+  uint32_t a_off, b_off;    // byte offsets of the operand rows: row * NA * 8
   double coef;
 };
 static_assert(sizeof(FlatTerm) == 16, "FlatTerm packing");
 struct FlatPass {
-  int vw = 0, nlevels = 0;
+  int vw = 0, nlevels = 0, na = 0;
   std::vector<int> stream_begin;    // [nlevels * vw + 1]
   std::vector<FlatTerm> terms;
+  std::vector<uint32_t> st;         // per term: byte offset of the destination row | 1 if the term ends its node
 };
 
 struct Program {
@@ -109,6 +108,6 @@ struct Program {
 };
 
 // Throws std::runtime_error if the table is not a topologically ordered program.
-void compile_program(const Potential &p, Program &out, int vw_large = 16, int vw_small = 64);
+void compile_program(const Potential &p, Program &out, int na_large = 32, int na_small = 8);
 
 }    // namespace mtpb200
