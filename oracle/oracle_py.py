@@ -167,7 +167,8 @@ class ReferenceMTP:
         return self.lib.mtpref_log(C.c_void_p(self.h)).decode()
 
     def set_domain(self, prd, natoms):
-        a = np.ascontiguousarray(prd, dtype=np.float64)
+        a = np.zeros(6)
+        a[: len(prd)] = prd            # xprd, yprd, zprd [, xy, xz, yz]
         self.lib.mtpref_set_domain(C.c_void_p(self.h), _ptr(a, _dp), C.c_long(natoms))
 
     def compute(self, x, type_, nlocal, ilist, numneigh, neigh_flat, offsets, eflag=3, vflag=5, grade=False,

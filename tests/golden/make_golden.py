@@ -82,11 +82,21 @@ def make_case(name, level, species, kind, a, cells, mode, ncentres, outdir):
                               want_mask=True)
             mask[off[i]: off[i] + nn[i]] = one.mask
         ref.close()
+        # MLIP-3 style run (output file + thresholds): the text block the reference's write_config() emits
+        cfg_text = np.zeros(0, dtype=np.uint8)
+        if mode is not None:
+            out = os.path.join(td, "preselected.cfg")
+            ref2 = oracle_py.ReferenceMTP("mtp/extrapolation", path, out, "0.0", "1e300")
+            ref2.set_domain(sysm.box, len(ilist))
+            ref2.compute(sysm.x, sysm.type, sysm.nlocal, ilist, nn, neigh, off, eflag=1, vflag=0, grade=False)
+            ref2.close()
+            cfg_text = np.frombuffer(open(out, "rb").read(), dtype=np.uint8)
         np.savez_compressed(
             os.path.join(outdir, name + ".npz"), potential=pot_bytes, mode=np.array(mode or ""),
             x=sysm.x, type=sysm.type, nlocal=np.array(sysm.nlocal), box=sysm.box, ilist=ilist, numneigh=nn,
             offsets=off, neigh=neigh, energy=np.array(r.energy), virial=r.virial.copy(), f=r.f, eatom=r.eatom,
-            vatom=r.vatom, mask=mask, grades=r.grades, max_grade=np.array(r.max_grade), candidate=r.candidate)
+            vatom=r.vatom, mask=mask, grades=r.grades, max_grade=np.array(r.max_grade), candidate=r.candidate,
+            cfg_text=cfg_text)
         print(f"{name}: nall={sysm.nall} centres={len(ilist)} pairs={neigh.size} in-cutoff={int(mask.sum())} "
               f"E={r.energy:.12g} max|F|={np.abs(r.f).max():.6g} max_grade={r.max_grade:.6g}")
 

@@ -20,7 +20,7 @@ class Golden:
             fh.write(z["potential"].tobytes())
         self.pot = almtp.read_almtp(self.path)
         for k in ("x", "type", "box", "ilist", "numneigh", "offsets", "neigh", "virial", "f", "eatom", "vatom", "mask",
-                  "grades", "candidate"):
+                  "grades", "candidate", "cfg_text"):
             setattr(self, k, z[k])
         self.nlocal = int(z["nlocal"])
         self.energy = float(z["energy"])
