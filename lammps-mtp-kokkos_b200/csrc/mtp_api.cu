@@ -175,8 +175,19 @@ struct mtp_handle {
   // register-resident pair stages for standard basic-moment sets (mtp_kernels_v2.cuh), -1 = not applicable
   int v2_entry = -1;
   DevBuf<short> d_slot_to_k;
-  DevBuf<double> d_pfld;
-  DevBuf<int> d_pj, d_pjt, d_pcnt, d_maxnn;
+  DevBuf<int> d_maxnn;
+  // super-chunks are dealt round-robin to `nlanes` internal streams, each with its own scratch, so that the
+  // shared-memory-bound program kernel of one chunk overlaps the FP64-bound pair kernels of its neighbours
+  struct Lane {
+    DevBuf<double> pfld, mb, gb;
+    DevBuf<int> pj, pjt, pcnt;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+  };
+  static constexpr int kMaxLanes = 4;
+  Lane lanes[kMaxLanes];
+  cudaEvent_t ev_fork = nullptr;
+  int nlanes = 2;
   int v2_grid_g = 0, v2_grid_m = 0, v2_grid_f = 0, v2_ab = 0;
   size_t v2_smem_g = 0, v2_smem_f = 0, v2_smem_m = 0;
   int v2_chunk = 0;
@@ -313,11 +324,12 @@ void upload_potential(mtp_handle *h)
     h->prog_max = prog_max;
     h->pl_na_fit = 0;
     for (int na = 32; na >= 2; na >>= 1)
-      if (program_layout(p.alpha_moment_count, na, 2 * p.alpha_index_basic_count, 0, 0, false).total <= prog_max) {
+      if (program_layout(p.alpha_moment_count, p.alpha_scalar_count, na, 2 * p.alpha_index_basic_count, 0, 0, false).total <= prog_max) {
         h->pl_na_fit = na;
         break;
       }
     h->pl_na[0] = std::max(2, h->pl_na_fit);
+    if (const char *e = getenv("MTP_B200_PROG_NA")) h->pl_na[0] = std::max(2, std::min(h->pl_na[0], atoi(e)));
     h->pl_na[1] = std::min(h->pl_na[0], 8);
     compile_program(p, h->prog, h->pl_na[0], h->pl_na[1]);
     CUDA_CHECK(cudaFuncSetAttribute((const void *) mtp_program_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) prog_max));
@@ -442,6 +454,7 @@ void upload_potential(mtp_handle *h)
       }
     }
     if (!ok) h->v2_entry = -1;
+    if (const char *le = getenv("MTP_B200_LANES")) h->nlanes = std::max(1, std::min((int) mtp_handle::kMaxLanes, atoi(le)));
     const char *ce = getenv("MTP_B200_CHUNK");
     h->v2_chunk = ce ? std::max(1024, atoi(ce)) : 0;
     h->d_maxnn.ensure(1);
@@ -593,28 +606,37 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
     const V2Entry &E = kV2[h->v2_entry];
     pb.ncap = std::max(4, (maxnn + 3) / 4 * 4);
     pb.cap = (long long) chunk * pb.ncap;
-    h->d_pfld.ensure((size_t) (4 + 2 * E.R) * pb.cap);
-    h->d_pj.ensure((size_t) pb.cap);
-    h->d_pjt.ensure((size_t) pb.cap);
-    h->d_pcnt.ensure((size_t) chunk);
-    pb.fld = h->d_pfld.p;
-    pb.pj = h->d_pj.p;
-    pb.pjt = h->d_pjt.p;
-    pb.pcnt = h->d_pcnt.p;
+    (void) E;
   } else if (!grade) {
     chunk = a.inum > 0 ? a.inum : 1;
   }
   const int ld = (chunk + 63) / 64 * 64;
   if (grade) h->d_cand.ensure((size_t) chunk * h->qpad);
-  if (pipeline) {
-    const size_t rows = use_v2 ? (size_t) kV2[h->v2_entry].KF : (size_t) d.K;
-    h->d_mb.ensure(rows * ld);
-    h->d_gb.ensure(rows * ld);
+  const int nsuper = a.inum > 0 ? (a.inum + chunk - 1) / chunk : 1;
+  const int nlanes = use_v2 ? std::max(1, std::min(h->nlanes, nsuper)) : 1;
+  if (use_v2) {
+    const V2Entry &E = kV2[h->v2_entry];
+    for (int l = 0; l < nlanes; l++) {
+      mtp_handle::Lane &L = h->lanes[l];
+      L.pfld.ensure((size_t) (4 + 2 * E.R) * pb.cap);
+      L.pj.ensure((size_t) pb.cap);
+      L.pjt.ensure((size_t) pb.cap);
+      L.pcnt.ensure((size_t) chunk);
+      L.mb.ensure((size_t) E.KF * ld);
+      L.gb.ensure((size_t) E.KF * ld);
+      if (nlanes > 1 && !L.stream) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+      }
+    }
+    if (nlanes > 1 && !h->ev_fork) CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  } else if (pipeline) {
+    h->d_mb.ensure((size_t) d.K * ld);
+    h->d_gb.ensure((size_t) d.K * ld);
   }
   if (cfg) CUDA_CHECK(cudaMemsetAsync(h->d_cfg.p, 0, sizeof(double) * h->qpad, st));
   CUDA_CHECK(cudaMemsetAsync(a.ev_out, 0, sizeof(double) * 8, st));
 
-  const int nsuper = a.inum > 0 ? (a.inum + chunk - 1) / chunk : 1;
   const int W = 8;
   // program kernel shape: atoms per CTA (power of two), smaller for small systems so that every SM gets work
   int na = 1, lna = 0, grid_p_cap = 1;
@@ -627,9 +649,15 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
     s.prog_shape = small ? 1 : 0;
     const int nslots = use_v2 ? kV2[h->v2_entry].KF : d.K;
     const int ntf = d.ffwd[s.prog_shape].nterms, ntr = d.frev[s.prog_shape].nterms;
-    s.prog_dsmem = program_layout(d.M, na, nslots, ntf, ntr, true).total <= h->prog_max ? 1 : 0;
-    if (getenv("MTP_B200_PROG_DSMEM")) s.prog_dsmem = s.prog_dsmem && atoi(getenv("MTP_B200_PROG_DSMEM"));
-    smem_p = program_layout(d.M, na, nslots, ntf, ntr, s.prog_dsmem != 0).total;
+    // shared-memory options in order of preference: prefetch staging + term streams, prefetch only, streams only
+    auto fits = [&](bool ds, bool pf) { return program_layout(d.M, d.A, na, nslots, ntf, ntr, ds, pf).total <= h->prog_max; };
+    s.prog_prefetch = 0;
+    s.prog_dsmem = fits(true, s.prog_prefetch != 0) ? 1 : 0;
+    if (const char *e = getenv("MTP_B200_PROG_PREFETCH")) s.prog_prefetch = atoi(e) && fits(false, true);
+    if (const char *e = getenv("MTP_B200_PROG_DSMEM")) s.prog_dsmem = atoi(e) && fits(true, s.prog_prefetch != 0);
+    else if (!fits(true, s.prog_prefetch != 0)) s.prog_dsmem = 0;
+    smem_p = program_layout(d.M, d.A, na, nslots, ntf, ntr, s.prog_dsmem != 0, s.prog_prefetch != 0).total;
+    s.prog_debug = getenv("MTP_B200_PROG_DEBUG") ? atoi(getenv("MTP_B200_PROG_DEBUG")) : 0;
     for (lna = 0; (1 << lna) < na; lna++) {}
     s.slot_to_k = use_v2 ? h->d_slot_to_k.p : nullptr;
     s.nslots = nslots;
@@ -641,6 +669,10 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
   const int rows_per_super = pipeline ? grid_p_cap + std::max(h->pl_grid_f[gi], h->v2_grid_f) : h->grid_cap[gi];
   h->d_partials.ensure((size_t) nsuper * rows_per_super * 8);
   int rows_used = 0;
+  if (nlanes > 1) {    // fork: the lanes start after everything queued on the caller's stream so far
+    CUDA_CHECK(cudaEventRecord(h->ev_fork, st));
+    for (int l = 0; l < nlanes; l++) CUDA_CHECK(cudaStreamWaitEvent(h->lanes[l].stream, h->ev_fork, 0));
+  }
 
   for (int sc = 0; sc < nsuper; sc++) {
     const int first = sc * chunk;
@@ -651,29 +683,35 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
     s.cand_ld = h->qpad;
     if (use_v2) {
       const V2Entry &E = kV2[h->v2_entry];
+      mtp_handle::Lane &L = h->lanes[sc % nlanes];
+      cudaStream_t ls = nlanes > 1 ? L.stream : st;
+      pb.fld = L.pfld.p;
+      pb.pj = L.pj.p;
+      pb.pjt = L.pjt.p;
+      pb.pcnt = L.pcnt.p;
       {
-        ProfSpan sp(h, MTP_PROF_GATHER, st);
+        ProfSpan sp(h, MTP_PROF_GATHER, ls);
         const int gg = std::max(1, std::min(h->v2_grid_g, (n + 7) / 8));
-        E.gather<<<gg, 256, h->v2_smem_g, st>>>(d, s, pb);
+        E.gather<<<gg, 256, h->v2_smem_g, ls>>>(d, s, pb);
       }
       {
-        ProfSpan sp(h, MTP_PROF_MOMENTS, st);
+        ProfSpan sp(h, MTP_PROF_MOMENTS, ls);
         const int gm = std::max(1, std::min(h->v2_grid_m, (n + 31) / 32));
-        E.moments<<<gm, 32 * E.NP, h->v2_smem_m, st>>>(s, pb, h->d_mb.p, ld);
+        E.moments<<<gm, 32 * E.NP, h->v2_smem_m, ls>>>(s, pb, L.mb.p, ld);
       }
       const int gp = std::max(1, std::min(grid_p_cap, (n + na - 1) / na));
       double *part_p = h->d_partials.p + (size_t) rows_used * 8;
       {
-        ProfSpan sp(h, MTP_PROF_PROGRAM, st);
-        mtp_program_kernel<false><<<gp, PROG_THREADS, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, lna, part_p);
+        ProfSpan sp(h, MTP_PROF_PROGRAM, ls);
+        mtp_program_kernel<false><<<gp, PROG_THREADS, smem_p, ls>>>(d, s, L.mb.p, L.gb.p, ld, na, lna, part_p);
       }
       rows_used += gp;
       const int ab = kV2AB[h->v2_ab];
       const int gf = std::max(1, std::min(h->v2_grid_f, (n + ab - 1) / ab));
       double *part_f = h->d_partials.p + (size_t) rows_used * 8;
       {
-        ProfSpan sp(h, MTP_PROF_FORCES, st);
-        E.forces[h->v2_ab]<<<gf, 256, h->v2_smem_f, st>>>(s, pb, h->d_gb.p, ld, part_f);
+        ProfSpan sp(h, MTP_PROF_FORCES, ls);
+        E.forces[h->v2_ab]<<<gf, 256, h->v2_smem_f, ls>>>(s, pb, L.gb.p, ld, part_f);
       }
       rows_used += gf;
       g_launches += 4;
@@ -728,6 +766,11 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
       }
     }
   }
+  if (nlanes > 1)    // join
+    for (int l = 0; l < nlanes; l++) {
+      CUDA_CHECK(cudaEventRecord(h->lanes[l].done, h->lanes[l].stream));
+      CUDA_CHECK(cudaStreamWaitEvent(st, h->lanes[l].done, 0));
+    }
   {
     ProfSpan sp(h, MTP_PROF_FINALIZE, st);
     finalize_ev_kernel<<<1, 7 * 32, 0, st>>>(h->d_partials.p, rows_used, a.ev_out, 1);
@@ -904,6 +947,11 @@ void mtp_destroy(mtp_handle *h)
   cudaSetDevice(h->device);
   if (h->hstream) cudaStreamDestroy(h->hstream);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  for (auto &L : h->lanes) {
+    if (L.stream) cudaStreamDestroy(L.stream);
+    if (L.done) cudaEventDestroy(L.done);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   delete h;
 }
 

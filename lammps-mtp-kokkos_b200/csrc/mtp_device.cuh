@@ -74,9 +74,25 @@ struct SiteArgs {
   int first_ii;           // chunk offset into ilist (grade steps)
   int prog_shape;         // which flat-stream table set the program kernel uses (0 throughput, 1 latency)
   int prog_dsmem;         // program kernel: term streams staged in shared memory
+  int prog_debug;         // timing experiments only: bit0 skip forward pass, bit1 skip reverse pass, bit2 skip energy
+  int prog_prefetch;      // program kernel: next chunk's basic moments prefetched (cp.async) into a staging buffer
   const short *slot_to_k; // rows of mb / gb are canonical slots (v2 pipeline) instead of basic-moment indices; or NULL
   int nslots;             // rows of mb / gb
   int *status;
 };
+
+// Ampere-style asynchronous copies global -> shared (LDGSTS): no registers, many in flight per thread
+__device__ __forceinline__ void cp_async8_zfill(void *smem_dst, const void *gsrc, int src_bytes /*8 or 0*/)
+{
+  const unsigned d = (unsigned) __cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+  const unsigned d = (unsigned) __cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 }    // namespace mtpb200

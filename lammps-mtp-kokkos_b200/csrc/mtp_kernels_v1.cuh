@@ -499,9 +499,10 @@ mtp_moments_kernel(DevPotential pot, V1Tables tb, SiteArgs a, double *__restrict
 // shared-memory plan of the program kernel (host and device agree through this one function)
 constexpr int PROG_THREADS = 256;    // 8 warps; every thread owns TWO adjacent atoms of the chunk (double2 operands)
 struct ProgLayout {
-  size_t node_bytes, off_cg, off_epart, off_s2k, off_terms[2], off_st[2], total;
+  size_t node_bytes, off_cg, off_epart, off_s2k, off_lin, off_map, off_stage, off_terms[2], off_st[2], total;
 };
-__host__ __device__ inline ProgLayout program_layout(int M, int na, int nslots, int nterms_f, int nterms_r, bool dsmem)
+__host__ __device__ inline ProgLayout program_layout(int M, int A, int na, int nslots, int nterms_f, int nterms_r,
+                                                     bool dsmem, bool prefetch = false)
 {
   ProgLayout L;
   const int vw = 16 * 32 / na;
@@ -510,6 +511,12 @@ __host__ __device__ inline ProgLayout program_layout(int M, int na, int nslots, 
   L.off_epart = 2 * L.node_bytes;
   L.off_s2k = L.off_epart + (size_t) vw * na * 8;
   size_t o = (L.off_s2k + (size_t) nslots * 2 + 15) & ~(size_t) 15;
+  L.off_lin = o;
+  o += (size_t) A * 8;
+  L.off_map = o;
+  o = (o + (size_t) A * 4 + 15) & ~(size_t) 15;
+  L.off_stage = o;
+  if (prefetch) o += (size_t) nslots * na * 8;
   L.off_terms[0] = o;
   if (dsmem) o += (size_t) nterms_f * 16;
   L.off_terms[1] = o;
@@ -522,6 +529,37 @@ __host__ __device__ inline ProgLayout program_layout(int M, int na, int nslots, 
   return L;
 }
 
+template <int U>
+__device__ __forceinline__ void flat_terms(const uint4 *__restrict__ terms, const unsigned *__restrict__ st, int t,
+                                           const unsigned char *A, const unsigned char *B, unsigned char *dst, double2 &acc)
+{
+  uint4 d[U];
+  unsigned sw[U];
+#pragma unroll
+  for (int q = 0; q < U / 4; q++) {
+    const uint4 s4 = *reinterpret_cast<const uint4 *>(st + t + 4 * q);
+    sw[4 * q] = s4.x, sw[4 * q + 1] = s4.y, sw[4 * q + 2] = s4.z, sw[4 * q + 3] = s4.w;
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++) d[u] = terms[t + u];
+  double2 va[U], vb[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    va[u] = *reinterpret_cast<const double2 *>(A + d[u].x);
+    vb[u] = *reinterpret_cast<const double2 *>(B + d[u].y);
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const double coef = __hiloint2double((int) d[u].w, (int) d[u].z);
+    acc.x = fma(coef * va[u].x, vb[u].x, acc.x);
+    acc.y = fma(coef * va[u].y, vb[u].y, acc.y);
+    if (sw[u] & 1u) {
+      *reinterpret_cast<double2 *>(dst + (sw[u] & ~7u)) = acc;
+      acc = make_double2(0.0, 0.0);
+    }
+  }
+}
+
 template <bool REVERSE>
 __device__ __forceinline__ void run_flat_pass(const DevFlatPass &ps, const uint4 *__restrict__ terms,
                                               const unsigned *__restrict__ st, unsigned char *cm_lane,
@@ -532,33 +570,9 @@ __device__ __forceinline__ void run_flat_pass(const DevFlatPass &ps, const uint4
   for (int lv = 0; lv < ps.nlevels; lv++) {
     const int t0 = ps.stream_begin[lv * ps.vw + vwarp], t1 = ps.stream_begin[lv * ps.vw + vwarp + 1];
     double2 acc = make_double2(0.0, 0.0);
-    for (int t = t0; t < t1; t += 8) {
-      uint4 d[8];
-      unsigned sw[8];
-      {
-        const uint4 s0 = *reinterpret_cast<const uint4 *>(st + t), s1 = *reinterpret_cast<const uint4 *>(st + t + 4);
-        sw[0] = s0.x, sw[1] = s0.y, sw[2] = s0.z, sw[3] = s0.w;
-        sw[4] = s1.x, sw[5] = s1.y, sw[6] = s1.z, sw[7] = s1.w;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; u++) d[u] = terms[t + u];
-      double2 va[8], vb[8];
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        va[u] = *reinterpret_cast<const double2 *>(A + d[u].x);
-        vb[u] = *reinterpret_cast<const double2 *>(cm_lane + d[u].y);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const double coef = __hiloint2double((int) d[u].w, (int) d[u].z);
-        acc.x = fma(coef * va[u].x, vb[u].x, acc.x);
-        acc.y = fma(coef * va[u].y, vb[u].y, acc.y);
-        if (sw[u] & 1u) {
-          *reinterpret_cast<double2 *>(dst + (sw[u] & ~7u)) = acc;
-          acc = make_double2(0.0, 0.0);
-        }
-      }
-    }
+    int t = t0;
+    for (; t + 8 <= t1; t += 8) flat_terms<8>(terms, st, t, A, cm_lane, dst, acc);
+    if (t < t1) flat_terms<4>(terms, st, t, A, cm_lane, dst, acc);    // streams are padded to a multiple of 4
     __syncthreads();
   }
 }
@@ -574,7 +588,10 @@ mtp_program_kernel(DevPotential pot, SiteArgs a, const double *__restrict__ mb, 
   const int fi = a.prog_shape;
   const DevFlatPass &pf = pot.ffwd[fi], &pr = pot.frev[fi];
   const int nslots = a.slot_to_k ? a.nslots : pot.K;
-  const ProgLayout L = program_layout(pot.M, NA, nslots, pf.nterms, pr.nterms, a.prog_dsmem != 0);
+  const ProgLayout L = program_layout(pot.M, pot.A, NA, nslots, pf.nterms, pr.nterms, a.prog_dsmem != 0, a.prog_prefetch != 0);
+  double *s_lin = reinterpret_cast<double *>(smem + L.off_lin);
+  int *s_map = reinterpret_cast<int *>(smem + L.off_map);
+  double *stage = reinterpret_cast<double *>(smem + L.off_stage);
   double *cm = reinterpret_cast<double *>(smem);
   double *cg = reinterpret_cast<double *>(smem + L.off_cg);
   double *epart = reinterpret_cast<double *>(smem + L.off_epart);
@@ -589,6 +606,10 @@ mtp_program_kernel(DevPotential pot, SiteArgs a, const double *__restrict__ mb, 
   // one-time setup: constant row, slot map, term streams
   for (int t = threadIdx.x; t < NA; t += blockDim.x) cm[pot.M * NA + t] = cg[pot.M * NA + t] = 1.0;
   for (int t = threadIdx.x; t < nslots; t += blockDim.x) s2k[t] = a.slot_to_k ? a.slot_to_k[t] : (short) t;
+  for (int t = threadIdx.x; t < pot.A; t += blockDim.x) {
+    s_lin[t] = pot.lin[t];
+    s_map[t] = pot.map[t] << lna;    // row offset in doubles
+  }
   const uint4 *terms_f = pf.terms, *terms_r = pr.terms;
   const unsigned *st_f = pf.st, *st_r = pr.st;
   if (a.prog_dsmem) {
@@ -610,24 +631,50 @@ mtp_program_kernel(DevPotential pot, SiteArgs a, const double *__restrict__ mb, 
   unsigned char *cm_lane = smem + (size_t) al2 * 8, *cg_lane = smem + L.off_cg + (size_t) al2 * 8;
   __syncthreads();
 
-  for (int chunk0 = blockIdx.x * NA; chunk0 < a.inum; chunk0 += gridDim.x * NA) {
-    const int na = min(NA, a.inum - chunk0);
-    // basic moments of the chunk -> cm (rows of NA atoms, coalesced)
-#pragma unroll 4
+  // basic moments of chunk c0 -> dst rows (dst = cm directly, or the staging buffer [slot][atom] when prefetching)
+  auto fetch_basic = [&](int c0, bool to_stage) {
+    const int nac = min(NA, a.inum - c0);
     for (int t = threadIdx.x; t < (nslots << lna); t += blockDim.x) {
       const int s = t >> lna, al = t & (NA - 1);
       const int k = s2k[s];
-      const double v = al < na ? mb[(size_t) s * ld + chunk0 + al] : 0.0;
-      if (k >= 0) cm[(k << lna) + al] = v;
+      double *dstp = to_stage ? stage + t : cm + (k << lna) + al;
+      if (to_stage || k >= 0)
+        cp_async8_zfill(dstp, mb + (size_t) s * ld + c0 + (al < nac ? al : 0), al < nac ? 8 : 0);
     }
-    __syncthreads();
-    run_flat_pass<false>(pf, terms_f, st_f, cm_lane, cg_lane, vwarp);
+    cp_async_commit();
+  };
+  if (a.prog_prefetch && (int) (blockIdx.x * NA) < a.inum) fetch_basic(blockIdx.x * NA, true);
+
+  for (int chunk0 = blockIdx.x * NA; chunk0 < a.inum; chunk0 += gridDim.x * NA) {
+    const int na = min(NA, a.inum - chunk0);
+    // this thread's atom for the energy epilogue: id and species requested now, consumed after the forward pass
+    int my_i = 0, my_type = 0;
+    if ((int) threadIdx.x < na && (a.eflag_global || a.eflag_atom)) {
+      my_i = a.ilist ? a.ilist[a.first_ii + chunk0 + threadIdx.x] : a.first_ii + chunk0 + threadIdx.x;
+      my_type = (int) a.xt[my_i].t;
+    }
+    if (a.prog_prefetch) {
+      cp_async_wait<0>();
+      __syncthreads();
+      for (int t = threadIdx.x; t < (nslots << lna); t += blockDim.x) {
+        const int k = s2k[t >> lna];
+        if (k >= 0) cm[(k << lna) + (t & (NA - 1))] = stage[t];
+      }
+      __syncthreads();
+      const int next0 = chunk0 + gridDim.x * NA;
+      if (next0 < a.inum) fetch_basic(next0, true);    // in flight during this chunk's passes
+    } else {
+      fetch_basic(chunk0, false);
+      cp_async_wait<0>();
+      __syncthreads();
+    }
+    if (!(a.prog_debug & 1)) run_flat_pass<false>(pf, terms_f, st_f, cm_lane, cg_lane, vwarp);
     // site energies: the virtual warps split the basis functions; fixed-order reduction
-    if (a.eflag_global || a.eflag_atom || GRADE) {
+    if ((a.eflag_global || a.eflag_atom || GRADE) && !(a.prog_debug & 4)) {
       double e0 = 0.0, e1 = 0.0;
       for (int s = vwarp; s < pot.A; s += VW) {
-        const double2 bm = *reinterpret_cast<const double2 *>(cm + ((size_t) pot.map[s] << lna) + al2);
-        const double c = pot.lin[s];
+        const double2 bm = *reinterpret_cast<const double2 *>(cm + s_map[s] + al2);
+        const double c = s_lin[s];
         e0 = fma(c, bm.x, e0);
         e1 = fma(c, bm.y, e1);
         if (GRADE) {
@@ -639,8 +686,8 @@ mtp_program_kernel(DevPotential pot, SiteArgs a, const double *__restrict__ mb, 
       __syncthreads();
       if (threadIdx.x < na) {
         const int al = threadIdx.x;
-        const int i = a.ilist ? a.ilist[a.first_ii + chunk0 + al] : a.first_ii + chunk0 + al;
-        int itype = (int) a.xt[i].t;
+        const int i = my_i;
+        int itype = my_type;
         if (itype < 0 || itype >= pot.S) itype = 0;
         double es = 0.0;
         for (int v = 0; v < VW; v++) es += epart[v * NA + al];
@@ -649,7 +696,7 @@ mtp_program_kernel(DevPotential pot, SiteArgs a, const double *__restrict__ mb, 
         if (a.eflag_global) e_thread += es;
       }
     }
-    run_flat_pass<true>(pr, terms_r, st_r, cm_lane, cg_lane, vwarp);
+    if (!(a.prog_debug & 2)) run_flat_pass<true>(pr, terms_r, st_r, cm_lane, cg_lane, vwarp);
     // adjoints of the basic moments -> gb
 #pragma unroll 4
     for (int t = threadIdx.x; t < (nslots << lna); t += blockDim.x) {

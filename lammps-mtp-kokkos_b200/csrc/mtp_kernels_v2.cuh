@@ -108,19 +108,6 @@ template <int D0> struct V2Shape {
 constexpr int V2_PEND = 64;
 constexpr int V2_NT = 16;      // pairs per staged tile of the moment kernel
 
-// Ampere-style asynchronous copies global -> shared (LDGSTS): no registers, many in flight per thread
-__device__ __forceinline__ void cp_async8_zfill(void *smem_dst, const void *gsrc, int src_bytes /*8 or 0*/)
-{
-  const unsigned d = (unsigned) __cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes));
-}
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
-{
-  const unsigned d = (unsigned) __cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // ===================================================================================================== gather
 template <int R>

@@ -85,7 +85,7 @@ struct ChunkPass {
 // "acc = m[node]", "acc = ginit[node]" and terms whose adjoint is a constant are ordinary terms with a = M and/or
 // b = M.  Streams are padded with no-ops (a = b = M, coef = 0) to a multiple of FLAT_UNROLL, so the kernel's inner
 // loop is branch-free and all descriptor / operand loads of an unrolled group are independent.
-constexpr int FLAT_UNROLL = 8;
+constexpr int FLAT_UNROLL = 4;
 struct FlatTerm {
   uint32_t a_off, b_off;    // byte offsets of the operand rows: row * NA * 8
   double coef;
