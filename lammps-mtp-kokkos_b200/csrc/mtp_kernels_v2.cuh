@@ -281,17 +281,21 @@ __device__ __forceinline__ void v2_moments_body(const SiteArgs &a, const PairBuf
   // stage tile (blk, n0) into buffer buf; cnt_l = this lane's pair count for atom `lane` of blk
   auto stage = [&](int buf, int blk, int n0, int cnt_l) {
     double *tile = tiles + (size_t) buf * TILE;
-    for (int e0 = 0; e0 < 32 * V2_NT * NF; e0 += NTH) {    // (al, field, n), n fastest: 128-byte runs
-      const int e = e0 + threadIdx.x;
-      const bool valid = e < 32 * V2_NT * NF;
-      const int al = valid ? e / (V2_NT * NF) : 0, r = e - al * (V2_NT * NF);
-      const int fi = r / V2_NT, n = r - fi * V2_NT;
-      const int gf = fi < 3 ? fi : fi + 1;    // skip the distance field
+    // warps split the atoms; lanes cover (field, pair) with the pair index fastest: 128-byte runs per field
+    const int warp = threadIdx.x >> 5;
+    for (int al = warp; al < 32; al += Sh::NP) {
       const int cnt_al = __shfl_sync(FULL, cnt_l, al);
-      if (valid) {
-        const bool live = n0 + n < cnt_al;
-        const double *src = pb.fld + (size_t) gf * pb.cap + (size_t) (blk * 32 + al) * pb.ncap + (live ? n0 + n : 0);
-        cp_async8_zfill(tile + (n * NF + fi) * 33 + al, src, live ? 8 : 0);
+      const double *abase = pb.fld + (size_t) (blk * 32 + al) * pb.ncap + n0;
+      double *trow = tile + al;
+#pragma unroll
+      for (int r0 = 0; r0 < V2_NT * NF; r0 += 32) {
+        const int r = r0 + lane;
+        const int fi = r / V2_NT, n = r % V2_NT;    // V2_NT is a power of two
+        if (r < V2_NT * NF) {
+          const int gf = fi < 3 ? fi : fi + 1;      // skip the distance field
+          const bool live = n0 + n < cnt_al;
+          cp_async8_zfill(trow + (n * NF + fi) * 33, abase + (size_t) gf * pb.cap + (live ? n : 0), live ? 8 : 0);
+        }
       }
     }
     cp_async_commit();
@@ -452,7 +456,7 @@ __device__ __forceinline__ void v2_pair_force(const double *__restrict__ gr /* g
 }
 
 template <int D0, int AB>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 mtp_forces_v2(SiteArgs a, PairBuf pb, const double *__restrict__ gb, int ld, double *__restrict__ partials)
 {
   using Sh = V2Shape<D0>;
@@ -504,11 +508,17 @@ mtp_forces_v2(SiteArgs a, PairBuf pb, const double *__restrict__ gb, int ld, dou
     const int *pre = prebuf + buf * (AB + 1);
     const int ii0 = blk * AB;
     const int total = pre[AB];
-    for (int p0 = 0; p0 < total; p0 += 256) {
-      const int p = p0 + threadIdx.x;
-      const bool live = p < total;
-      int al = 0;
-      if (live) {    // largest al with pre[al] <= p
+    // pair records are requested one iteration ahead of their use
+    struct Rec {
+      double ux, uy, uz, d, f[R], fd[R];
+      int j, al;
+      bool live;
+    };
+    auto load_rec = [&](int p, Rec &r) {
+      r.live = p < total;
+      r.al = 0;
+      r.j = 0;
+      if (r.live) {    // largest al with pre[al] <= p
         int lo = 0, hi = AB;
 #pragma unroll
         for (int it = 0; (1 << it) < AB; it++) {
@@ -517,22 +527,40 @@ mtp_forces_v2(SiteArgs a, PairBuf pb, const double *__restrict__ gb, int ld, dou
           else
             hi = mid;
         }
-        al = lo;
+        r.al = lo;
+        const size_t s = (size_t) (ii0 + lo) * pb.ncap + (p - pre[lo]);
+        r.ux = pb.fld[s];
+        r.uy = pb.fld[pb.cap + s];
+        r.uz = pb.fld[2 * pb.cap + s];
+        r.d = pb.fld[3 * pb.cap + s];
+#pragma unroll
+        for (int mu = 0; mu < R; mu++) {
+          r.f[mu] = pb.fld[(4 + mu) * pb.cap + s];
+          r.fd[mu] = pb.fld[(4 + R + mu) * pb.cap + s];
+        }
+        r.j = pb.pj[s];
       }
+    };
+    Rec cur;
+    load_rec(threadIdx.x, cur);
+    for (int p0 = 0; p0 < total; p0 += 256) {
+      Rec nxt;
+      load_rec(p0 + 256 + threadIdx.x, nxt);
+      const bool live = cur.live;
+      const int al = cur.al;
       double Fx = 0, Fy = 0, Fz = 0;
       const int i = a.ilist ? a.ilist[a.first_ii + ii0 + al] : a.first_ii + ii0 + al;
       if (live) {
-        const size_t s = (size_t) (ii0 + al) * pb.ncap + (p - pre[al]);
-        const double ux = pb.fld[s], uy = pb.fld[pb.cap + s], uz = pb.fld[2 * pb.cap + s], d = pb.fld[3 * pb.cap + s];
+        const double ux = cur.ux, uy = cur.uy, uz = cur.uz, d = cur.d;
         const double invd = 1.0 / d;
         double fvi[R], fder[R];
 #pragma unroll
         for (int mu = 0; mu < R; mu++) {
-          fvi[mu] = pb.fld[(4 + mu) * pb.cap + s] * invd;
-          fder[mu] = pb.fld[(4 + R + mu) * pb.cap + s];
+          fvi[mu] = cur.f[mu] * invd;
+          fder[mu] = cur.fd[mu];
         }
         v2_pair_force<D0, AB>(g + al, ux, uy, uz, fvi, fder, Fx, Fy, Fz);
-        const int j = pb.pj[s];
+        const int j = cur.j;
         atomicAdd(&a.f[3 * (size_t) j], -Fx);
         atomicAdd(&a.f[3 * (size_t) j + 1], -Fy);
         atomicAdd(&a.f[3 * (size_t) j + 2], -Fz);
@@ -574,6 +602,7 @@ mtp_forces_v2(SiteArgs a, PairBuf pb, const double *__restrict__ gb, int ld, dou
         atomicAdd(&a.f[3 * (size_t) i + 1], Fy);
         atomicAdd(&a.f[3 * (size_t) i + 2], Fz);
       }
+      cur = nxt;
     }
   }
 
