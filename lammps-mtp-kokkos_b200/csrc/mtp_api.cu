@@ -157,6 +157,8 @@ struct mtp_handle {
   DevBuf<long long> h_offsets;
   DevBuf<unsigned char> h_within;
   long long h_list_len = 0;
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> copy_events;
   int h_maxnn = 0;
   cudaStream_t hstream = nullptr;
   // register-resident kernel family (mtp_kernels_v1.cuh), -1 = generic kernel only
@@ -334,6 +336,12 @@ void upload_potential(mtp_handle *h)
     compile_program(p, h->prog, h->pl_na[0], h->pl_na[1]);
     CUDA_CHECK(cudaFuncSetAttribute((const void *) mtp_program_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) prog_max));
     CUDA_CHECK(cudaFuncSetAttribute((const void *) mtp_program_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) prog_max));
+    // one shared-memory carve-out for every kernel of the pipeline: an SM cannot change its L1 / shared split while
+    // CTAs are resident, so kernels of different lanes can only co-reside if they all ask for the same (maximum) split
+    if (!getenv("MTP_B200_NO_CARVEOUT")) {
+      CUDA_CHECK(cudaFuncSetAttribute((const void *) mtp_program_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      CUDA_CHECK(cudaFuncSetAttribute((const void *) mtp_program_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
   }
   std::vector<uint32_t> basic(p.alpha_index_basic_count);
   for (int k = 0; k < p.alpha_index_basic_count; k++) {
@@ -425,6 +433,12 @@ void upload_potential(mtp_handle *h)
     bool ok = h->v2_smem_g <= max_dynamic_smem((const void *) E.gather, smem_max);
     if (ok) {
       CUDA_CHECK(cudaFuncSetAttribute((const void *) E.gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->v2_smem_g));
+      if (!getenv("MTP_B200_NO_CARVEOUT")) {
+        CUDA_CHECK(cudaFuncSetAttribute((const void *) E.gather, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_CHECK(cudaFuncSetAttribute((const void *) E.moments, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        for (int q = 0; q < 4; q++)
+          CUDA_CHECK(cudaFuncSetAttribute((const void *) E.forces[q], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      }
       int per_sm = 0;
       CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.gather, 256, h->v2_smem_g));
       h->v2_grid_g = std::max(1, per_sm) * h->sm_count;
@@ -540,7 +554,26 @@ struct ProfSpan {
   }
 };
 
-void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
+// atoms per super-chunk for a call with inum centres (shared by launch_site and the host path's upload pipeline)
+int plan_chunk(const mtp_handle *h, int inum, bool grade)
+{
+  const bool use_v2 = h->v2_entry >= 0 && !grade;
+  const bool pipeline = use_v2 || h->v1_entry >= 0;
+  int chunk = std::max(1, std::min(h->chunksize, inum > 0 ? inum : 1));
+  if (pipeline) {
+    long long fit = std::max(8192LL, (48LL << 20) / (16LL * h->dpot.K) / 1024 * 1024);
+    if (use_v2) fit = h->v2_chunk > 0 ? h->v2_chunk : (1LL << 30);    // v2: the user's chunksize alone bounds the scratch
+    chunk = (int) std::min<long long>(chunk, fit);
+  } else if (!grade) {
+    chunk = inum > 0 ? inum : 1;
+  }
+  return chunk;
+}
+
+// chunk_ready (optional): one event per super-chunk that must have completed before the chunk's kernels may read
+// the neighbor list (the host path uploads the list slice by slice while earlier chunks compute)
+void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
+                 const std::vector<cudaEvent_t> *chunk_ready = nullptr)
 {
   const DevPotential &d = h->dpot;
   const bool grade = a.want_grade != 0;
@@ -584,12 +617,7 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
   const bool pipeline = use_v2 || h->v1_entry >= 0;
   // super-chunk: bounded by the user's "chunksize"; the pipeline additionally keeps its two [K][chunk]
   // intermediates within ~48 MB so that they stay L2-resident
-  int chunk = std::max(1, std::min(h->chunksize, a.inum > 0 ? a.inum : 1));
-  if (pipeline) {
-    long long fit = std::max(8192LL, (48LL << 20) / (16LL * d.K) / 1024 * 1024);
-    if (use_v2) fit = h->v2_chunk > 0 ? h->v2_chunk : (1LL << 30);    // v2: the user's chunksize alone bounds the scratch
-    chunk = (int) std::min<long long>(chunk, fit);
-  }
+  const int chunk = plan_chunk(h, a.inum, grade);
   PairBuf pb{};
   if (use_v2) {
     int maxnn = a.max_numneigh;
@@ -607,8 +635,6 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
     pb.ncap = std::max(4, (maxnn + 3) / 4 * 4);
     pb.cap = (long long) chunk * pb.ncap;
     (void) E;
-  } else if (!grade) {
-    chunk = a.inum > 0 ? a.inum : 1;
   }
   const int ld = (chunk + 63) / 64 * 64;
   if (grade) h->d_cand.ensure((size_t) chunk * h->qpad);
@@ -652,7 +678,7 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
     // shared-memory options in order of preference: prefetch staging + term streams, prefetch only, streams only
     auto fits = [&](bool ds, bool pf) { return program_layout(d.M, d.A, na, nslots, ntf, ntr, ds, pf).total <= h->prog_max; };
     s.prog_prefetch = 0;
-    s.prog_dsmem = fits(true, s.prog_prefetch != 0) ? 1 : 0;
+    s.prog_dsmem = (nlanes == 1 && fits(true, s.prog_prefetch != 0)) ? 1 : 0;    // lanes: leave room for a co-resident CTA
     if (const char *e = getenv("MTP_B200_PROG_PREFETCH")) s.prog_prefetch = atoi(e) && fits(false, true);
     if (const char *e = getenv("MTP_B200_PROG_DSMEM")) s.prog_dsmem = atoi(e) && fits(true, s.prog_prefetch != 0);
     else if (!fits(true, s.prog_prefetch != 0)) s.prog_dsmem = 0;
@@ -681,6 +707,10 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st)
     s.first_ii = first;
     s.cand_rows = grade ? h->d_cand.p : nullptr;
     s.cand_ld = h->qpad;
+    if (chunk_ready && sc < (int) chunk_ready->size()) {
+      cudaStream_t ws = (use_v2 && nlanes > 1) ? h->lanes[sc % nlanes].stream : st;
+      CUDA_CHECK(cudaStreamWaitEvent(ws, (*chunk_ready)[sc], 0));
+    }
     if (use_v2) {
       const V2Entry &E = kV2[h->v2_entry];
       mtp_handle::Lane &L = h->lanes[sc % nlanes];
@@ -952,6 +982,8 @@ void mtp_destroy(mtp_handle *h)
     if (L.done) cudaEventDestroy(L.done);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (cudaEvent_t e : h->copy_events) cudaEventDestroy(e);
   delete h;
 }
 
@@ -1079,29 +1111,52 @@ int mtp_compute_host(mtp_handle *h, const mtp_compute_args *a, int list_changed)
     h->h_x.upload(a->x, 3 * nall, st);
     h->h_type.upload(a->type, nall, st);
     h->h_f.upload(a->f, 3 * nall, st);
+    std::vector<cudaEvent_t> ready;
     if (list_changed || h->h_list_len == 0) {
-      long long len = 0;
-      if (a->neigh_offsets) {
-        for (size_t k = 0; k < inum; k++) {
-          const size_t i = a->ilist ? (size_t) a->ilist[k] : k;
-          len = std::max(len, a->neigh_offsets[i] + (long long) a->numneigh[i] * std::max(1LL, a->stride_jj));
-        }
-        h->h_offsets.upload(a->neigh_offsets, nid, st);
-      } else {
-        long long mx = 0;
-        for (size_t k = 0; k < inum; k++) {
-          const size_t i = a->ilist ? (size_t) a->ilist[k] : k;
-          mx = std::max(mx, (long long) i * a->stride_i + (long long) a->numneigh[i] * a->stride_jj);
-        }
-        len = mx + 1;
+      // one pass over the listed centres: extent of the list, max row length, and whether the CSR rows are laid out
+      // in ilist order (then the list can be uploaded slice by slice, overlapped with the compute of earlier chunks)
+      long long len = 0, prev_end = 0;
+      int mx = 0;
+      bool ordered = a->neigh_offsets != nullptr && a->stride_jj <= 1;
+      for (size_t k = 0; k < inum; k++) {
+        const size_t i = a->ilist ? (size_t) a->ilist[k] : k;
+        const int nn = a->numneigh[i];
+        mx = std::max(mx, nn);
+        if (a->neigh_offsets) {
+          const long long o = a->neigh_offsets[i];
+          len = std::max(len, o + (long long) nn * std::max(1LL, a->stride_jj));
+          if (o < prev_end) ordered = false;
+          prev_end = o + nn;
+        } else
+          len = std::max(len, (long long) i * a->stride_i + (long long) nn * a->stride_jj + 1);
       }
-      h->h_neigh.upload(a->neighbors, (size_t) len, st);
+      h->h_maxnn = mx;
+      if (a->neigh_offsets) h->h_offsets.upload(a->neigh_offsets, nid, st);
       h->h_numneigh.upload(a->numneigh, nid, st);
       if (a->ilist) h->h_ilist.upload(a->ilist, inum, st);
+      h->h_neigh.ensure((size_t) len);
       h->h_list_len = len;
-      int mx = 0;
-      for (size_t k = 0; k < inum; k++) mx = std::max(mx, a->numneigh[a->ilist ? (size_t) a->ilist[k] : k]);
-      h->h_maxnn = mx;
+      const int chunk = plan_chunk(h, a->inum, a->want_grade != 0);
+      const int nsuper = a->inum > 0 ? (a->inum + chunk - 1) / chunk : 1;
+      if (ordered && nsuper > 1 && !a->within_cutoff) {
+        if (!h->copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        while ((int) h->copy_events.size() < nsuper) {
+          cudaEvent_t e;
+          CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+          h->copy_events.push_back(e);
+        }
+        for (int c = 0; c < nsuper; c++) {
+          const size_t k0 = (size_t) c * chunk, k1 = std::min(inum, k0 + (size_t) chunk) - 1;
+          const size_t i0 = a->ilist ? (size_t) a->ilist[k0] : k0, i1 = a->ilist ? (size_t) a->ilist[k1] : k1;
+          const long long lo = a->neigh_offsets[i0], hi = a->neigh_offsets[i1] + a->numneigh[i1];
+          if (hi > lo)
+            CUDA_CHECK(cudaMemcpyAsync(h->h_neigh.p + lo, a->neighbors + lo, sizeof(int) * (size_t) (hi - lo),
+                                       cudaMemcpyHostToDevice, h->copy_stream));
+          CUDA_CHECK(cudaEventRecord(h->copy_events[c], h->copy_stream));
+          ready.push_back(h->copy_events[c]);
+        }
+      } else if (len > 0)
+        CUDA_CHECK(cudaMemcpyAsync(h->h_neigh.p, a->neighbors, sizeof(int) * (size_t) len, cudaMemcpyHostToDevice, st));
     }
     d.max_numneigh = h->h_maxnn;
     d.x = h->h_x.p;
@@ -1140,7 +1195,7 @@ int mtp_compute_host(mtp_handle *h, const mtp_compute_args *a, int list_changed)
       d.within_cutoff = h->h_within.p;
     }
     d.stream = st;
-    launch_site(h, d, st);
+    launch_site(h, d, st, ready.empty() ? nullptr : &ready);
     CUDA_CHECK(cudaMemcpyAsync(a->f, d.f, sizeof(double) * 3 * nall, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(a->ev_out, d.ev_out, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
     if (d.eatom) CUDA_CHECK(cudaMemcpyAsync(a->eatom, d.eatom, sizeof(double) * nall, cudaMemcpyDeviceToHost, st));
