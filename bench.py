@@ -47,17 +47,18 @@ def algorithmic_flops_per_atom(pot, n_list, n_cut):
 
 
 def algorithmic_flops_split(pot, n_list, n_cut):
-    """The same count apportioned to the kernels of the pipeline: the moment kernel owns
-    gather/cutoff, radial basis, powers, radial contraction and the m[k] accumulation (6 flop per k: nf, val, pw x2,
-    fma); the force kernel owns the Jacobian part (9 + 5 nz_k) and the contraction with dE/dm (6K + 6); the program
-    kernel owns the contraction tree forward/reverse and the energy."""
+    """The same count apportioned to the kernels of the pipeline: the gather kernel owns
+    gather/cutoff, Chebyshev and the radial contraction; the moment kernel the powers and the m[k] accumulation (6 flop
+    per k: nf, val, pw x2, fma); the force kernel the Jacobian part (9 + 5 nz_k) and the contraction with dE/dm
+    (6K + 6); the program kernel the contraction tree forward/reverse and the energy."""
     B, R, P = pot.radial_basis_size, pot.radial_funcs_count, pot.max_alpha_index_basic
     K, T, A = pot.K, pot.T, pot.A
     nz = (np.asarray(pot.alpha_index_basic)[:, 1:] != 0).sum(axis=1)
-    moments = 9.0 * n_list + n_cut * ((8 * B + 19) + 4 * (P - 1) + 4 * R * B + 6.0 * K)
+    gather = 9.0 * n_list + n_cut * ((8 * B + 19) + 4 * R * B)
+    moments = n_cut * (4 * (P - 1) + 6.0 * K)
     forces = n_cut * (float((9 + 5 * nz).sum()) + 6 * K + 6)
     program = 9.0 * T + 2.0 * A
-    return {"moments": moments, "forces": forces, "program": program}
+    return {"gather": gather, "moments": moments, "forces": forces, "program": program}
 
 
 def algorithmic_bytes_per_atom(n_list):
@@ -189,6 +190,7 @@ def main():
     ap.add_argument("--ref-cells", type=int, nargs=3, default=None, help="CPU-baseline sample box")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", default="large", choices=["large", "small"])
+    ap.add_argument("--lanes", type=int, default=2, help="internal streams the super-chunks are dealt to (mtp_set_lanes)")
     ap.add_argument("--chunksize", type=int, default=32768, help="pair_style ... chunksize N (README.md:44 of the reference)")
     args = ap.parse_args()
 
@@ -248,6 +250,7 @@ def main():
     variant = api.VARIANT_SMALL if args.variant == "small" else api.VARIANT_LARGE
     mtp = MTPB200(pot_path, selection_state=bool(cfg.get("active_set")), device=local_rank)
     mtp.set_chunksize(args.chunksize)
+    mtp.set_lanes(args.lanes)
 
     # one brick per rank on the grid {1, 2x1x1, 2x2x1, 2x2x2}; at N = 1 all six swaps are periodic self-images
     from mtp_b200 import decomp
@@ -298,7 +301,6 @@ def main():
         step_device()
     barrier()
     launches0 = api.kernel_launch_count() + halo.launches
-    mtp.profile_enable(True)
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
@@ -309,8 +311,18 @@ def main():
         ev1[s].record()
     barrier()
     launches = api.kernel_launch_count() + halo.launches - launches0
+    # per-kernel durations for the roofline: the same steps once more with the kernels serialised on one stream
+    # (lanes = 1), CUDA events recorded by the library around every launch; not part of `value`
+    prof_steps = min(args.steps, 5)
+    mtp.set_lanes(1)
+    step_device()
+    mtp.profile_enable(True)
+    for s in range(prof_steps):
+        flush.fill_(s & 0xff)
+        step_device()
     prof = mtp.profile_read()
     mtp.profile_enable(False)
+    mtp.set_lanes(args.lanes)
     step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
     total_ms = float(sum(step_ms))
     if world > 1:
@@ -420,24 +432,40 @@ def main():
     for cls, (ms, spans) in prof.items():
         if spans == 0:
             continue
-        k = {"ms_per_step": ms / args.steps, "launches_per_step": spans / args.steps}
+        k = {"ms_per_step": ms / prof_steps, "launches_per_step": spans / prof_steps}
         if cls in split:
             k["algorithmic_flops_per_atom"] = split[cls]
-            k["achieved_tflops"] = split[cls] * nlocal / (ms / args.steps * 1e-3) / 1e12
+            k["achieved_tflops"] = split[cls] * nlocal / (ms / prof_steps * 1e-3) / 1e12
             k["frac_of_fp64_peak"] = k["achieved_tflops"] / dfma
         kernels[cls] = k
     dom = max((c for c in kernels if c in split), key=lambda c: kernels[c]["ms_per_step"], default=None)
     pipe_ms = sum(k["ms_per_step"] for k in kernels.values())
     achieved_tf = flops_atom * nlocal / (pipe_ms * 1e-3) / 1e12 if pipe_ms else 0.0
     achieved_gbs = bytes_atom * nlocal / (ms_per_step * 1e-3) / 1e9
-    roofline = {"bound": "fp64", "unit": "TFLOP/s", "peak": dfma,
-                "peak_source": "FP64 DFMA peak measured in this run by mtp_fp64_peak (DMMA m8n8k4: %.2f TFLOP/s); "
-                               "MEASURED_PEAKS.json has no FP64 entry" % dmma,
-                "kernel": dom, "achieved": kernels[dom]["achieved_tflops"] if dom else None,
-                "frac": kernels[dom]["frac_of_fp64_peak"] if dom else None, "traffic": None,
+    # the contraction-program kernel moves two FP64 operands per term through shared memory and is bound by that
+    # pipe (128 B/clk/SM), not by FP64: forward T terms + reverse 2T terms -> 6T operand reads of 8 B per atom
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    sm_mhz = clocks.get("sm_max_mhz") or 1965.0
+    smem_peak_tbs = 128.0 * sm_count * sm_mhz * 1e6 / 1e12
+    if "program" in kernels:
+        kp = kernels["program"]
+        kp["algorithmic_smem_bytes_per_atom"] = 48.0 * pot.T
+        kp["achieved_smem_tbs"] = 48.0 * pot.T * nlocal / (kp["ms_per_step"] * 1e-3) / 1e12
+        kp["frac_of_smem_peak"] = kp["achieved_smem_tbs"] / smem_peak_tbs
+    roofline = {"kernel": dom, "traffic": None,
                 "duration_ms": kernels[dom]["ms_per_step"] / kernels[dom]["launches_per_step"] if dom else None,
-                "duration_note": "average launch duration of the dominant kernel: CUDA events recorded by the library on "
-                                 "the launch stream around every launch of the timed region (mtp_profile_read)",
+                "duration_note": "average launch duration of the dominant kernel (largest share of the step): CUDA events "
+                                 "recorded by the library on its launch stream around every launch (mtp_profile_read) in a "
+                                 "pass with the kernels serialised (lanes = 1) right after the timed region",
+                "fp64_peak_tflops": dfma,
+                "fp64_peak_source": "FP64 DFMA peak measured in this run by mtp_fp64_peak (DMMA m8n8k4: %.2f TFLOP/s); "
+                                    "MEASURED_PEAKS.json has no FP64 entry" % dmma,
+                "smem_peak_tbs": smem_peak_tbs,
+                "smem_peak_source": "128 B/clk/SM x %d SMs x %.0f MHz" % (sm_count, sm_mhz),
+                **({"bound": "smem", "unit": "TB/s", "achieved": kernels[dom]["achieved_smem_tbs"], "peak": smem_peak_tbs,
+                    "frac": kernels[dom]["frac_of_smem_peak"]} if dom == "program" else
+                   {"bound": "fp64", "unit": "TFLOP/s", "achieved": kernels[dom]["achieved_tflops"] if dom else None,
+                    "peak": dfma, "frac": kernels[dom]["frac_of_fp64_peak"] if dom else None}),
                 "kernels": kernels,
                 "pipeline": {"ms_per_step_kernels": pipe_ms, "algorithmic_flops_per_atom": flops_atom,
                              "achieved": achieved_tf, "frac": achieved_tf / dfma,

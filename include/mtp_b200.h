@@ -139,6 +139,11 @@ int mtp_get_tables(const mtp_handle *h, double *radial_basis_coeffs, int *alpha_
  * all per-atom state on chip).  Must be >= 1. */
 int mtp_set_chunksize(mtp_handle *h, int chunksize);
 
+/* Number of internal streams ("lanes") the super-chunks of one mtp_compute() are dealt to (1..4, default 2): with
+ * more than one lane the shared-memory-bound contraction-program kernel of one chunk overlaps the FP64-bound pair
+ * kernels of its neighbours.  1 = all kernels serialised on the caller's stream (used for per-kernel timing). */
+int mtp_set_lanes(mtp_handle *h, int lanes);
+
 /* ---- the hot path ---------------------------------------------------------------------------- */
 /* Asynchronous on args->stream; results are valid after the stream is synchronised. */
 int mtp_compute(mtp_handle *h, const mtp_compute_args *device_args);

@@ -1066,6 +1066,13 @@ int mtp_profile_read(mtp_handle *h, double *ms, long long *count)
   });
 }
 
+int mtp_set_lanes(mtp_handle *h, int lanes)
+{
+  if (!h || lanes < 1 || lanes > mtp_handle::kMaxLanes) return fail(MTP_ERR_ARG, "lanes must be 1..4");
+  h->nlanes = lanes;
+  return MTP_OK;
+}
+
 int mtp_compute(mtp_handle *h, const mtp_compute_args *a)
 {
   if (!h || !a) return fail(MTP_ERR_ARG, "null argument");

@@ -531,7 +531,8 @@ __host__ __device__ inline ProgLayout program_layout(int M, int A, int na, int n
 
 template <int U>
 __device__ __forceinline__ void flat_terms(const uint4 *__restrict__ terms, const unsigned *__restrict__ st, int t,
-                                           const unsigned char *A, const unsigned char *B, unsigned char *dst, double2 &acc)
+                                           const unsigned char *A, const unsigned char *B, unsigned char *dst,
+                                           const unsigned char *one, double2 &acc)
 {
   uint4 d[U];
   unsigned sw[U];
@@ -542,11 +543,15 @@ __device__ __forceinline__ void flat_terms(const uint4 *__restrict__ terms, cons
   }
 #pragma unroll
   for (int u = 0; u < U; u++) d[u] = terms[t + u];
+  // operand flag bit 0: the operand is the constant 1.0 -> every lane reads the same 16-byte word (one broadcast
+  // wavefront instead of four); selected by address so that the loads stay unconditional and batched
   double2 va[U], vb[U];
 #pragma unroll
   for (int u = 0; u < U; u++) {
-    va[u] = *reinterpret_cast<const double2 *>(A + d[u].x);
-    vb[u] = *reinterpret_cast<const double2 *>(B + d[u].y);
+    const unsigned char *pa = (d[u].x & 1u) ? one : A + d[u].x;
+    const unsigned char *pb = (d[u].y & 1u) ? one : B + d[u].y;
+    va[u] = *reinterpret_cast<const double2 *>(pa);
+    vb[u] = *reinterpret_cast<const double2 *>(pb);
   }
 #pragma unroll
   for (int u = 0; u < U; u++) {
@@ -563,7 +568,7 @@ __device__ __forceinline__ void flat_terms(const uint4 *__restrict__ terms, cons
 template <bool REVERSE>
 __device__ __forceinline__ void run_flat_pass(const DevFlatPass &ps, const uint4 *__restrict__ terms,
                                               const unsigned *__restrict__ st, unsigned char *cm_lane,
-                                              unsigned char *cg_lane, int vwarp)
+                                              unsigned char *cg_lane, const unsigned char *one, int vwarp)
 {
   const unsigned char *A = REVERSE ? cg_lane : cm_lane;
   unsigned char *dst = REVERSE ? cg_lane : cm_lane;
@@ -571,8 +576,8 @@ __device__ __forceinline__ void run_flat_pass(const DevFlatPass &ps, const uint4
     const int t0 = ps.stream_begin[lv * ps.vw + vwarp], t1 = ps.stream_begin[lv * ps.vw + vwarp + 1];
     double2 acc = make_double2(0.0, 0.0);
     int t = t0;
-    for (; t + 8 <= t1; t += 8) flat_terms<8>(terms, st, t, A, cm_lane, dst, acc);
-    if (t < t1) flat_terms<4>(terms, st, t, A, cm_lane, dst, acc);    // streams are padded to a multiple of 4
+    for (; t + 8 <= t1; t += 8) flat_terms<8>(terms, st, t, A, cm_lane, dst, one, acc);
+    if (t < t1) flat_terms<4>(terms, st, t, A, cm_lane, dst, one, acc);    // streams are padded to a multiple of 4
     __syncthreads();
   }
 }
@@ -629,6 +634,7 @@ mtp_program_kernel(DevPotential pot, SiteArgs a, const double *__restrict__ mb, 
     st_r = sr;
   }
   unsigned char *cm_lane = smem + (size_t) al2 * 8, *cg_lane = smem + L.off_cg + (size_t) al2 * 8;
+  const unsigned char *one_ptr = smem + (size_t) pot.M * NA * 8;    // row M of cm holds 1.0
   __syncthreads();
 
   // basic moments of chunk c0 -> dst rows (dst = cm directly, or the staging buffer [slot][atom] when prefetching)
@@ -668,7 +674,7 @@ mtp_program_kernel(DevPotential pot, SiteArgs a, const double *__restrict__ mb, 
       cp_async_wait<0>();
       __syncthreads();
     }
-    if (!(a.prog_debug & 1)) run_flat_pass<false>(pf, terms_f, st_f, cm_lane, cg_lane, vwarp);
+    if (!(a.prog_debug & 1)) run_flat_pass<false>(pf, terms_f, st_f, cm_lane, cg_lane, one_ptr, vwarp);
     // site energies: the virtual warps split the basis functions; fixed-order reduction
     if ((a.eflag_global || a.eflag_atom || GRADE) && !(a.prog_debug & 4)) {
       double e0 = 0.0, e1 = 0.0;
@@ -696,7 +702,7 @@ mtp_program_kernel(DevPotential pot, SiteArgs a, const double *__restrict__ mb, 
         if (a.eflag_global) e_thread += es;
       }
     }
-    if (!(a.prog_debug & 2)) run_flat_pass<true>(pr, terms_r, st_r, cm_lane, cg_lane, vwarp);
+    if (!(a.prog_debug & 2)) run_flat_pass<true>(pr, terms_r, st_r, cm_lane, cg_lane, one_ptr, vwarp);
     // adjoints of the basic moments -> gb
 #pragma unroll 4
     for (int t = threadIdx.x; t < (nslots << lna); t += blockDim.x) {

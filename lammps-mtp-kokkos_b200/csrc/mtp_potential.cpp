@@ -517,13 +517,21 @@ void compile_program(const Potential &p, Program &prog, int na_large, int na_sma
           for (const ProgramTerm &q : l.terms) t.push_back(Raw{q.a, q.b, 0, false, (double) q.mult});
         } else {
           t.push_back(Raw{ONE, ONE, 0, false, prog.ginit[l.node]});
-          for (const ProgramTerm &q : l.terms) {
+          for (size_t qi = 0; qi < l.terms.size(); qi++) {
+            const ProgramTerm &q = l.terms[qi];
+            double mult = (double) q.mult;
+            // a self product m[a3] += mult*m[s]*m[s] lists the same reverse term twice in a row: merge (x + x == 2x)
+            if (qi + 1 < l.terms.size() && l.terms[qi + 1].a == q.a && l.terms[qi + 1].b == q.b &&
+                l.terms[qi + 1].mult == q.mult && q.b == (uint16_t) l.node) {
+              mult *= 2.0;
+              qi++;
+            }
             if (!is_source[q.a]) {
-              const double c = (double) q.mult * prog.ginit[q.a];    // g[a3] stays ginit[a3]
+              const double c = mult * prog.ginit[q.a];    // g[a3] stays ginit[a3]
               if (c == 0.0) continue;
               t.push_back(Raw{ONE, q.b, 0, false, c});
             } else
-              t.push_back(Raw{q.a, q.b, 0, false, (double) q.mult});
+              t.push_back(Raw{q.a, q.b, 0, false, mult});
           }
         }
         if (t.empty()) t.push_back(Raw{ONE, ONE, 0, false, 0.0});
@@ -545,7 +553,10 @@ void compile_program(const Potential &p, Program &prog, int na_large, int na_sma
       for (int b = 0; b < vw; b++) {
         while (bins[b].size() % FLAT_UNROLL) bins[b].push_back(Raw{ONE, ONE, ONE, false, 0.0});
         for (const Raw &r : bins[b]) {
-          out.terms.push_back(FlatTerm{(uint32_t) r.a * row_bytes, (uint32_t) r.b * row_bytes, r.coef});
+          // operand flag (offsets are multiples of 8): bit 0 = the operand is the constant 1.0 (broadcast read)
+          const uint32_t ao = r.a == ONE ? 1u : (uint32_t) r.a * row_bytes;
+          const uint32_t bo = r.b == ONE ? 1u : (uint32_t) r.b * row_bytes;
+          out.terms.push_back(FlatTerm{ao, bo, r.coef});
           out.st.push_back((uint32_t) r.node * row_bytes | (r.store ? 1u : 0u));
         }
         out.stream_begin.push_back((int) out.terms.size());

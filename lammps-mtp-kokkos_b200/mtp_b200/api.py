@@ -78,6 +78,7 @@ def load_library():
     lib.mtp_get_info.argtypes = [C.c_void_p, C.POINTER(MTPInfo)]
     lib.mtp_get_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 7
     lib.mtp_set_chunksize.argtypes = [C.c_void_p, C.c_int]
+    lib.mtp_set_lanes.argtypes = [C.c_void_p, C.c_int]
     lib.mtp_compute.argtypes = [C.c_void_p, C.POINTER(MTPComputeArgs)]
     lib.mtp_synchronize.argtypes = [C.c_void_p]
     lib.mtp_compute_host.argtypes = [C.c_void_p, C.POINTER(MTPComputeArgs), C.c_int]
@@ -171,6 +172,9 @@ class MTPB200:
     def set_chunksize(self, n: int):
         _check(self.lib, self.lib.mtp_set_chunksize(self.h, int(n)))
         self.info.chunksize = int(n)
+
+    def set_lanes(self, n: int):
+        _check(self.lib, self.lib.mtp_set_lanes(self.h, int(n)))
 
     # ---- host buffers ---------------------------------------------------------------------------
     def compute_host(self, x, type_, ilist, numneigh, neigh, offsets=None, *, stride_i=0, stride_jj=1, eflag=3,
