@@ -190,7 +190,7 @@ struct mtp_handle {
   Lane lanes[kMaxLanes];
   cudaEvent_t ev_fork = nullptr;
   int nlanes = 2;
-  int v2_grid_g = 0, v2_grid_m = 0, v2_grid_f = 0, v2_ab = 0;
+  int v2_grid_g = 0, v2_grid_r = 0, v2_grid_m = 0, v2_grid_f = 0, v2_ab = 0;
   size_t v2_smem_g = 0, v2_smem_f = 0, v2_smem_m = 0;
   int v2_chunk = 0;
   // optional per-kernel-class device timing (mtp_profile_enable): CUDA events recorded on the launch stream
@@ -269,12 +269,12 @@ typedef void (*V2ForcesKernel)(SiteArgs, PairBuf, const double *, int, double *)
 constexpr int kV2AB[4] = {64, 32, 16, 8};    // atoms per CTA of the force kernel
 struct V2Entry {
   int d0, R, KF, NP;
-  V2GatherKernel gather;
+  V2GatherKernel radial;
   V2MomentsKernel moments;
   V2ForcesKernel forces[4];
 };
 #define V2_ENTRY(D)                                                                                          \
-  {D, V2Shape<D>::R, V2Shape<D>::KF, V2Shape<D>::NP, mtp_gather_kernel<V2Shape<D>::R>, mtp_moments_v2<D>,    \
+  {D, V2Shape<D>::R, V2Shape<D>::KF, V2Shape<D>::NP, mtp_radial_kernel<V2Shape<D>::R>, mtp_moments_v2<D>,    \
    {mtp_forces_v2<D, 64>, mtp_forces_v2<D, 32>, mtp_forces_v2<D, 16>, mtp_forces_v2<D, 8>}}
 const V2Entry kV2[] = {V2_ENTRY(0), V2_ENTRY(1), V2_ENTRY(2), V2_ENTRY(3), V2_ENTRY(4), V2_ENTRY(5),
                        V2_ENTRY(6), V2_ENTRY(7), V2_ENTRY(8), V2_ENTRY(9), V2_ENTRY(10)};
@@ -429,19 +429,22 @@ void upload_potential(mtp_handle *h)
   if (h->v2_entry >= 0) {
     const V2Entry &E = kV2[h->v2_entry];
     const int nrad = d.S * d.S * d.R * d.B;
-    h->v2_smem_g = (size_t) ((nrad + 1) & ~1) * 8 + 8 * (size_t) (3 * V2_PEND * 8 + 2 * V2_PEND * 4);
-    bool ok = h->v2_smem_g <= max_dynamic_smem((const void *) E.gather, smem_max);
+    h->v2_smem_g = (size_t) ((nrad + 1) & ~1) * 8;
+    bool ok = h->v2_smem_g <= max_dynamic_smem((const void *) E.radial, smem_max);
     if (ok) {
-      CUDA_CHECK(cudaFuncSetAttribute((const void *) E.gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->v2_smem_g));
+      CUDA_CHECK(cudaFuncSetAttribute((const void *) E.radial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->v2_smem_g));
       if (!getenv("MTP_B200_NO_CARVEOUT")) {
-        CUDA_CHECK(cudaFuncSetAttribute((const void *) E.gather, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_CHECK(cudaFuncSetAttribute((const void *) mtp_gather_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_CHECK(cudaFuncSetAttribute((const void *) E.radial, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CUDA_CHECK(cudaFuncSetAttribute((const void *) E.moments, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         for (int q = 0; q < 4; q++)
           CUDA_CHECK(cudaFuncSetAttribute((const void *) E.forces[q], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       }
       int per_sm = 0;
-      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.gather, 256, h->v2_smem_g));
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) mtp_gather_kernel, 256, 0));
       h->v2_grid_g = std::max(1, per_sm) * h->sm_count;
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.radial, 256, h->v2_smem_g));
+      h->v2_grid_r = std::max(1, per_sm) * h->sm_count;
       h->v2_smem_m = (size_t) 2 * V2_NT * (3 + E.R) * 33 * 8;
       ok = h->v2_smem_m <= max_dynamic_smem((const void *) E.moments, smem_max);
       if (ok) {
@@ -722,7 +725,9 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
       {
         ProfSpan sp(h, MTP_PROF_GATHER, ls);
         const int gg = std::max(1, std::min(h->v2_grid_g, (n + 7) / 8));
-        E.gather<<<gg, 256, h->v2_smem_g, ls>>>(d, s, pb);
+        mtp_gather_kernel<<<gg, 256, 0, ls>>>(d, s, pb);
+        const int gr = std::max(1, std::min(h->v2_grid_r, (n + 7) / 8));
+        E.radial<<<gr, 256, h->v2_smem_g, ls>>>(d, s, pb);
       }
       {
         ProfSpan sp(h, MTP_PROF_MOMENTS, ls);
@@ -744,7 +749,7 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
         E.forces[h->v2_ab]<<<gf, 256, h->v2_smem_f, ls>>>(s, pb, L.gb.p, ld, part_f);
       }
       rows_used += gf;
-      g_launches += 4;
+      g_launches += 5;
     } else if (pipeline) {
       const V1Entry &E = kV1[h->v1_entry];
       const int gm = std::max(1, std::min(h->pl_grid_m, (n + W - 1) / W));

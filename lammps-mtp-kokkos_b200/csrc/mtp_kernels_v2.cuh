@@ -6,10 +6,10 @@
 // straight-line FP64 code on registers.  Canonical slot order: q lexicographic in (a, b, c), then mu.
 //
 //   mtp_gather_kernel    warp per centre atom: neighbor gather (32-byte position records), cutoff mask exactly as
-//                        pair_mtp.cpp:112-129, compaction, then lane = in-cutoff pair: Chebyshev x cutoff and the
-//                        radial contraction (mtp_rb_chevbyshev_basis.cpp:29-54, pair_mtp.cpp:139-151).  Writes one
-//                        record per pair {u, d, f_mu, f'_mu, j} into the pair buffer, field-major, atom ii owning
-//                        the slots [ii * ncap, ii * ncap + pcnt[ii]).
+//                        pair_mtp.cpp:112-129, ballot compaction straight into the pair buffer (field-major, atom ii
+//                        owning the slots [ii * ncap, ii * ncap + pcnt[ii])).
+//   mtp_radial_kernel    lane = in-cutoff pair: Chebyshev x cutoff and the radial contraction
+//                        (mtp_rb_chevbyshev_basis.cpp:29-54, pair_mtp.cpp:139-151) -> record {u, d, f_mu, f'_mu, j}.
 //   mtp_moments_v2       CTA = 32 atoms x NP warps, lane = atom, warp = "pass" (a contiguous range of canonical
 //                        slots, <= ~48 accumulators held in registers).  Pair records are staged through shared
 //                        memory (coalesced read, transposed so that lane = atom reads are conflict free);
@@ -110,73 +110,155 @@ constexpr int V2_NT = 16;      // pairs per staged tile of the moment kernel
 
 
 // ===================================================================================================== gather
-template <int R>
+// stage 1: warp per centre atom, lane = listed neighbor.  Gather the 32-byte position records, apply the cutoff mask
+// exactly as pair_mtp.cpp:112-129 and write the in-cutoff displacements, compacted in list order, straight to the
+// pair buffer (fields 0..2 hold r until stage 2 turns them into the unit vector).  No shared memory, few registers:
+// the whole SM's worth of warps hides the gather latency.
 __global__ void __launch_bounds__(256)
 mtp_gather_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
 {
-  extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-  double *s_radial = reinterpret_cast<double *>(smem);
-  const int nrad = pot.S * pot.S * pot.R * pot.B;
-  for (int t = threadIdx.x; t < nrad; t += blockDim.x) s_radial[t] = pot.radial[t];
-  double *pr = s_radial + ((nrad + 1) & ~1) + (size_t) warp * (3 * V2_PEND + V2_PEND);
-  int *pj = reinterpret_cast<int *>(pr + 3 * V2_PEND);
-  int *pt = pj + V2_PEND;
-  __syncthreads();
-
   for (int ii = blockIdx.x * W + warp; ii < a.inum; ii += gridDim.x * W) {
     V1Atom at;
     v1_load_atom(pot, a, ii, lane, at);
     const long long slot0 = (long long) ii * pb.ncap;
-    int pend = 0, done = 0;
-    for (int base = 0; base < at.jnum || pend > 0; base += 32) {
-      if (base < at.jnum) {
-        const int jj = base + lane;
-        bool within = false;
-        int j = 0, jt = 0;
-        double r0 = 0, r1 = 0, r2 = 0;
-        if (jj < at.jnum) {
-          const long long pos = at.row0 + (long long) jj * a.stride_jj;
-          j = a.neighbors[pos] & a.neighmask;
-          const double2 *nrec = reinterpret_cast<const double2 *>(a.xt + j);
-          const double2 nxy = __ldg(nrec);
-          const double2 nzt = __ldg(nrec + 1);
-          jt = (int) __double_as_longlong(nzt.y);
-          r0 = nxy.x - at.xi0;
-          r1 = nxy.y - at.xi1;
-          r2 = nzt.x - at.xi2;
-          // separately rounded, left to right, exactly pair_mtp.cpp:121-123 (no FMA contraction)
-          const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2));
-          within = !(rsq > pot.cutsq);
-          if (jt < 0 || jt >= pot.S) {    // pair_mtp.cpp:116-118
-            atomicOr(a.status, 1);
-            within = false;
-          }
-          if (a.within) a.within[pos] = within ? 1 : 0;
+    int done = 0;
+    for (int base = 0; base < at.jnum; base += 32) {
+      const int jj = base + lane;
+      bool within = false;
+      int j = 0, jt = 0;
+      double r0 = 0, r1 = 0, r2 = 0;
+      if (jj < at.jnum) {
+        const long long pos = at.row0 + (long long) jj * a.stride_jj;
+        j = a.neighbors[pos] & a.neighmask;
+        const double2 *nrec = reinterpret_cast<const double2 *>(a.xt + j);
+        const double2 nxy = __ldg(nrec);
+        const double2 nzt = __ldg(nrec + 1);
+        jt = (int) __double_as_longlong(nzt.y);
+        r0 = nxy.x - at.xi0;
+        r1 = nxy.y - at.xi1;
+        r2 = nzt.x - at.xi2;
+        // separately rounded, left to right, exactly pair_mtp.cpp:121-123 (no FMA contraction)
+        const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2));
+        within = !(rsq > pot.cutsq);
+        if (jt < 0 || jt >= pot.S) {    // pair_mtp.cpp:116-118
+          atomicOr(a.status, 1);
+          within = false;
         }
-        const unsigned bal = __ballot_sync(FULL, within);
-        if (within) {
-          const int slot = pend + __popc(bal & ((1u << lane) - 1u));
-          pr[slot] = r0;
-          pr[V2_PEND + slot] = r1;
-          pr[2 * V2_PEND + slot] = r2;
-          pj[slot] = j;
-          pt[slot] = jt;
-        }
-        pend += __popc(bal);
-        __syncwarp();
-        if (pend < 32 && base + 32 < at.jnum) continue;    // keep filling the batch
+        if (a.within) a.within[pos] = within ? 1 : 0;
       }
-      const int nb = pend < 32 ? pend : 32;
-      if (nb == 0) break;
-      if (lane < nb) {
-        const double r0 = pr[lane], r1 = pr[V2_PEND + lane], r2 = pr[2 * V2_PEND + lane];
-        const int jt = pt[lane];
+      const unsigned bal = __ballot_sync(FULL, within);
+      if (within) {
+        const long long s = slot0 + done + __popc(bal & ((1u << lane) - 1u));
+        pb.fld[s] = r0;
+        pb.fld[pb.cap + s] = r1;
+        pb.fld[2 * pb.cap + s] = r2;
+        pb.pj[s] = j;
+        pb.pjt[s] = jt | (at.itype << 16);    // neighbor species | centre species
+      }
+      done += __popc(bal);
+    }
+    if (lane == 0) pb.pcnt[ii] = done;
+  }
+}
+
+// Chebyshev x cutoff (mtp_rb_chevbyshev_basis.cpp:29-54) contracted with the radial coefficients of one species
+// pair (pair_mtp.cpp:139-151), fully unrolled; ct = coefficients transposed to [ri][mu]
+template <int R, int B>
+__device__ __forceinline__ void radial_unrolled(const DevPotential &pot, const double *__restrict__ ct, double d,
+                                                double (&F)[R], double (&Fd)[R])
+{
+  const double t = d - pot.rmax;
+  const double ksi = (2 * d - (pot.rmin + pot.rmax)) / (pot.rmax - pot.rmin);
+  const double mult = 2.0 / (pot.rmax - pot.rmin);
+  double v_prev = pot.scaling * (1 * t * t), d_prev = pot.scaling * 2 * t;
+#pragma unroll
+  for (int mu = 0; mu < R; mu++) {
+    F[mu] = ct[mu] * v_prev;
+    Fd[mu] = ct[mu] * d_prev;
+  }
+  if (B == 1) return;
+  double v_cur = pot.scaling * (ksi * t * t), d_cur = pot.scaling * (mult * t * t + 2 * ksi * t);
+#pragma unroll
+  for (int ri = 1; ri < B; ri++) {
+    if (ri > 1) {
+      const double vn = 2 * ksi * v_cur - v_prev;
+      const double dn = 2 * (mult * v_cur + ksi * d_cur) - d_prev;
+      v_prev = v_cur;
+      d_prev = d_cur;
+      v_cur = vn;
+      d_cur = dn;
+    }
+#pragma unroll
+    for (int mu = 0; mu < R; mu++) {
+      const double cc = ct[ri * R + mu];
+      F[mu] = fma(cc, v_cur, F[mu]);
+      Fd[mu] = fma(cc, d_cur, Fd[mu]);
+    }
+  }
+}
+
+// stage 2: lane = in-cutoff pair (perfectly parallel): distance, unit vector, radial functions -> the remaining
+// fields of the record
+template <int R>
+__global__ void __launch_bounds__(256)
+mtp_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  double *s_ct = reinterpret_cast<double *>(smem);    // [S*S][B][R]: transposed radial coefficients
+  const int nrad = pot.S * pot.S * pot.R * pot.B, RB = pot.R * pot.B;
+  for (int t = threadIdx.x; t < nrad; t += blockDim.x) {
+    const int pt = t / RB, r = t - pt * RB, mu = r / pot.B, ri = r - mu * pot.B;
+    s_ct[pt * RB + ri * pot.R + mu] = pot.radial[t];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  for (int ii = blockIdx.x * W + warp; ii < a.inum; ii += gridDim.x * W) {
+    // the record loads do not wait for the pair count: slots beyond it hold stale but readable data
+    const long long s0 = (long long) ii * pb.ncap;
+    const int cnt = pb.pcnt[ii];
+    for (int n0 = 0; n0 < pb.ncap; n0 += 32) {
+      const int n = n0 + lane;
+      const long long s = s0 + (n < pb.ncap ? n : 0);
+      const double r0 = pb.fld[s], r1 = pb.fld[pb.cap + s], r2 = pb.fld[2 * pb.cap + s];
+      const int tt = pb.pjt[s];
+      if (n0 >= cnt) break;    // warp-uniform
+      if (n < cnt) {
+        const int jt = tt & 0xffff, itype = tt >> 16;
         const double dist = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2)));
         const double invd = 1.0 / dist;
         double F[R], Fd[R];
-        radial_functions<R>(pot, s_radial + (size_t) (at.itype * pot.S + jt) * pot.R * pot.B, dist, F, Fd);
-        const long long s = slot0 + done + lane;
+        const double *ct = s_ct + (size_t) (itype * pot.S + jt) * RB;
+        if (pot.B == 8) radial_unrolled<R, 8>(pot, ct, dist, F, Fd);
+        else {    // any other basis size: same recurrence with a run-time trip count
+          const double t = dist - pot.rmax;
+          const double ksi = (2 * dist - (pot.rmin + pot.rmax)) / (pot.rmax - pot.rmin);
+          const double mult = 2.0 / (pot.rmax - pot.rmin);
+          double v_prev = 0, v_cur = pot.scaling * (1 * t * t), d_prev = 0, d_cur = pot.scaling * 2 * t;
+#pragma unroll
+          for (int mu = 0; mu < R; mu++) F[mu] = Fd[mu] = 0.0;
+          for (int ri = 0; ri < pot.B; ri++) {
+            if (ri == 1) {
+              v_prev = v_cur;
+              d_prev = d_cur;
+              v_cur = pot.scaling * (ksi * t * t);
+              d_cur = pot.scaling * (mult * t * t + 2 * ksi * t);
+            } else if (ri > 1) {
+              const double vn = 2 * ksi * v_cur - v_prev;
+              const double dn = 2 * (mult * v_cur + ksi * d_cur) - d_prev;
+              v_prev = v_cur;
+              d_prev = d_cur;
+              v_cur = vn;
+              d_cur = dn;
+            }
+#pragma unroll
+            for (int mu = 0; mu < R; mu++) {
+              const double cc = ct[ri * R + mu];
+              F[mu] += cc * v_cur;
+              Fd[mu] += cc * d_cur;
+            }
+          }
+        }
         pb.fld[s] = r0 * invd;
         pb.fld[pb.cap + s] = r1 * invd;
         pb.fld[2 * pb.cap + s] = r2 * invd;
@@ -186,34 +268,8 @@ mtp_gather_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
           pb.fld[(4 + mu) * pb.cap + s] = F[mu];
           pb.fld[(4 + R + mu) * pb.cap + s] = Fd[mu];
         }
-        pb.pj[s] = pj[lane];
-        pb.pjt[s] = jt;
       }
-      done += nb;
-      // drop the consumed batch, keep the remainder (< 32 entries)
-      const int rem = pend - nb;
-      double t0 = 0, t1 = 0, t2 = 0;
-      int tj = 0, tt = 0;
-      __syncwarp();
-      if (lane < rem) {
-        t0 = pr[32 + lane];
-        t1 = pr[V2_PEND + 32 + lane];
-        t2 = pr[2 * V2_PEND + 32 + lane];
-        tj = pj[32 + lane];
-        tt = pt[32 + lane];
-      }
-      __syncwarp();
-      if (lane < rem) {
-        pr[lane] = t0;
-        pr[V2_PEND + lane] = t1;
-        pr[2 * V2_PEND + lane] = t2;
-        pj[lane] = tj;
-        pt[lane] = tt;
-      }
-      pend = rem;
-      __syncwarp();
     }
-    if (lane == 0) pb.pcnt[ii] = done;
   }
 }
 
