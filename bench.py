@@ -245,6 +245,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version / debug lines must not land on stdout
         dist.init_process_group("nccl", device_id=dev)
 
     variant = api.VARIANT_SMALL if args.variant == "small" else api.VARIANT_LARGE
