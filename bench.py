@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--ref-cells", type=int, nargs=3, default=None, help="CPU-baseline sample box")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", default="large", choices=["large", "small"])
+    ap.add_argument("--halo", default="direct", choices=["direct", "staged"],
+                    help="ghost exchange: one 26-direction stage (default) or LAMMPS's three dimension-by-dimension stages")
     ap.add_argument("--lanes", type=int, default=2, help="internal streams the super-chunks are dealt to (mtp_set_lanes)")
     ap.add_argument("--chunksize", type=int, default=32768, help="pair_style ... chunksize N (README.md:44 of the reference)")
     args = ap.parse_args()
@@ -255,7 +257,8 @@ def main():
 
     # one brick per rank on the grid {1, 2x1x1, 2x2x1, 2x2x2}; at N = 1 all six swaps are periodic self-images
     from mtp_b200 import decomp
-    sysm, halo = decomp.make_rank_system(args.config, cells, brick_grid(world), rank, dev, mtp.lib)
+    sysm, halo = decomp.make_rank_system(args.config, cells, brick_grid(world), rank, dev, mtp.lib,
+                                         direct=args.halo == "direct")
     nlocal, nall = sysm.nlocal, sysm.nall
 
     # workload statistics for the roofline (listed / in-cutoff neighbors per atom)
@@ -485,8 +488,8 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload, "atoms_per_gpu": nlocal, "ghosts_per_gpu": nall - nlocal,
-                       "parallelism": "brick grid %dx%dx%d, one rank per GPU, NCCL send/recv halo (%d B/rank/step)" % (
-                           *brick_grid(world), halo.bytes_per_step),
+                       "parallelism": "brick grid %dx%dx%d, one rank per GPU, %s NCCL send/recv halo (%d B/rank/step)" % (
+                           *brick_grid(world), args.halo, halo.bytes_per_step),
                        "l2": "256 MiB write between timed iterations (L2 flush), per-step CUDA events summed",
                        "variant": args.variant, "chunksize": args.chunksize, "flags": "eflag=1 vflag=1"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

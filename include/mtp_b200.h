@@ -158,6 +158,9 @@ int mtp_compute_host(mtp_handle *h, const mtp_compute_args *host_args, int list_
 /* forward: out[k][:] = x[sendlist[k]][:] + shift[:]   (LAMMPS Comm::forward_comm pack, on device) */
 int mtp_halo_pack_x(const double *x, const int *sendlist, int n, const double *shift3_host, double *out,
                     void *stream);
+/* forward, several swaps at once: out[k][:] = x[sendlist[k]][:] + shifts[seg[k]][:]   (shifts: DEVICE array [nseg][3]) */
+int mtp_halo_pack_x_multi(const double *x, const int *sendlist, const unsigned char *seg, const double *shifts_dev, int n,
+                          double *out, void *stream);
 /* reverse: f[sendlist[k]][:] += buf[k][:]             (Comm::reverse_comm unpack, newton on) */
 int mtp_halo_unpack_add_f(double *f, const int *sendlist, int n, const double *buf, void *stream);
 

@@ -1243,6 +1243,18 @@ int mtp_halo_pack_x(const double *x, const int *sendlist, int n, const double *s
   });
 }
 
+int mtp_halo_pack_x_multi(const double *x, const int *sendlist, const unsigned char *seg, const double *shifts_dev, int n,
+                          double *out, void *stream)
+{
+  if (n < 0 || (n > 0 && (!x || !sendlist || !seg || !shifts_dev || !out))) return fail(MTP_ERR_ARG, "bad halo arguments");
+  if (n == 0) return MTP_OK;
+  return guarded([&] {
+    halo_pack_x_multi_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t) stream>>>(x, sendlist, seg, shifts_dev, n, out);
+    g_launches++;
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
 int mtp_halo_unpack_add_f(double *f, const int *sendlist, int n, const double *buf, void *stream)
 {
   if (n < 0 || (n > 0 && (!f || !sendlist || !buf))) return fail(MTP_ERR_ARG, "bad halo arguments");

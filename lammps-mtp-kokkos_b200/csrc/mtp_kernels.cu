@@ -653,6 +653,20 @@ __global__ void halo_pack_x_kernel(const double *__restrict__ x, const int *__re
   out[3 * (size_t) k + 2] = x[3 * (size_t) i + 2] + sz;
 }
 
+// several swaps in one launch: entry k belongs to segment seg[k] whose periodic shift is shifts[3 * seg[k] ..]
+__global__ void halo_pack_x_multi_kernel(const double *__restrict__ x, const int *__restrict__ sendlist,
+                                         const unsigned char *__restrict__ seg, const double *__restrict__ shifts, int n,
+                                         double *__restrict__ out)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int i = sendlist[k];
+  const double *sh = shifts + 3 * (int) seg[k];
+  out[3 * (size_t) k] = x[3 * (size_t) i] + sh[0];
+  out[3 * (size_t) k + 1] = x[3 * (size_t) i + 1] + sh[1];
+  out[3 * (size_t) k + 2] = x[3 * (size_t) i + 2] + sh[2];
+}
+
 __global__ void halo_unpack_add_f_kernel(double *__restrict__ f, const int *__restrict__ sendlist, int n,
                                          const double *__restrict__ buf)
 {

@@ -83,6 +83,7 @@ def load_library():
     lib.mtp_synchronize.argtypes = [C.c_void_p]
     lib.mtp_compute_host.argtypes = [C.c_void_p, C.POINTER(MTPComputeArgs), C.c_int]
     lib.mtp_halo_pack_x.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _dp, C.c_void_p, C.c_void_p]
+    lib.mtp_halo_pack_x_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.mtp_halo_unpack_add_f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.mtp_profile_enable.argtypes = [C.c_void_p, C.c_int]
     lib.mtp_profile_read.argtypes = [C.c_void_p, _dp, _llp]

@@ -216,12 +216,196 @@ def build_rank_system(x_own, types_own, sublo, subhi, grid, rank, gbox, cutoff, 
     return sysm, Halo(swaps, rank, world, device, lib)
 
 
-def make_rank_system(config, cells, grid, rank, device, lib=None, cutoff=5.0, skin=2.0, jitter=0.05):
+DIRS = [(dx, dy, dz) for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1) if (dx, dy, dz) != (0, 0, 0)]
+
+
+class DirectHalo:
+    """Single-stage ghost exchange: every rank sends its owned boundary atoms straight to each of the 26
+    neighbor directions (faces, edges, corners), so a step needs ONE device pack, ONE grouped NCCL send/recv
+    each way and ONE scatter-add, instead of three dependent stages.  Ghost rows are laid out as
+    [self-image segments | remote segments], both in ``DIRS`` order; two ranks that exchange several segments
+    enumerate them in the same order, which is what NCCL's in-order matching between a pair needs."""
+
+    def __init__(self, rank, world, device, lib, nlocal, segs):
+        # segs: dicts with dir index, dest, src, sendlist (np int32), shift (3,), recv_n
+        self.rank, self.world, self.device, self.lib = rank, world, device, lib
+        self.cuda = device.type == "cuda"
+        self.launches = 0
+        self.nlocal = nlocal
+        selfs = [s for s in segs if s["dest"] == rank]
+        rem = [s for s in segs if s["dest"] != rank]
+        self.remote = rem
+
+        def cat(lst, key, dtype):
+            return np.concatenate([s[key] for s in lst] + [np.zeros(0, dtype)]).astype(dtype)
+
+        def seg_ids(lst):
+            return np.concatenate([np.full(len(s["sendlist"]), k, np.uint8) for k, s in enumerate(lst)]
+                                  + [np.zeros(0, np.uint8)])
+
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)  # noqa: E731
+        self.self_list, self.self_seg = t(cat(selfs, "sendlist", np.int32)), t(seg_ids(selfs))
+        self.self_shift = t(np.array([s["shift"] for s in selfs] + [[0, 0, 0]], dtype=np.float64))
+        self.rem_list, self.rem_seg = t(cat(rem, "sendlist", np.int32)), t(seg_ids(rem))
+        self.rem_shift = t(np.array([s["shift"] for s in rem] + [[0, 0, 0]], dtype=np.float64))
+        self.nself = len(self.self_list)
+        # ghost rows: self segments first (recv_n == send n), then remote segments
+        g = nlocal + self.nself
+        so = 0
+        for s in rem:
+            s["send_off"], s["ghost_first"] = so, g
+            so += len(s["sendlist"])
+            g += s["recv_n"]
+        self.nall = g
+        self.sendbuf = torch.empty((so, 3), dtype=torch.float64, device=device)
+        self.recvbuf = torch.empty((so, 3), dtype=torch.float64, device=device)
+        self.bytes_per_step = 2 * 24 * so
+
+    def _pack(self, x, lst, seg, shifts, out):
+        n = len(lst)
+        if n == 0:
+            return
+        if self.cuda:
+            rc = self.lib.mtp_halo_pack_x_multi(x.data_ptr(), lst.data_ptr(), seg.data_ptr(), shifts.data_ptr(), n,
+                                                out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            assert rc == 0
+            self.launches += 1
+        else:
+            out.copy_(x.index_select(0, lst.long()) + shifts.index_select(0, seg.long()))
+
+    def _unpack_add(self, f, lst, buf):
+        n = len(lst)
+        if n == 0:
+            return
+        if self.cuda:
+            rc = self.lib.mtp_halo_unpack_add_f(f.data_ptr(), lst.data_ptr(), n, buf.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream)
+            assert rc == 0
+            self.launches += 1
+        else:
+            f.index_add_(0, lst.long(), buf.clone())
+
+    def forward(self, x: torch.Tensor):
+        n0 = self.nlocal
+        self._pack(x, self.self_list, self.self_seg, self.self_shift, x[n0: n0 + self.nself])
+        self._pack(x, self.rem_list, self.rem_seg, self.rem_shift, self.sendbuf)
+        ops = []
+        for s in self.remote:
+            if len(s["sendlist"]):
+                ops.append(dist.P2POp(dist.isend, self.sendbuf[s["send_off"]: s["send_off"] + len(s["sendlist"])], s["dest"]))
+        for s in self.remote:
+            if s["recv_n"]:
+                ops.append(dist.P2POp(dist.irecv, x[s["ghost_first"]: s["ghost_first"] + s["recv_n"]], s["src"]))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+
+    def reverse(self, f: torch.Tensor):
+        ops = []
+        for s in self.remote:
+            if s["recv_n"]:
+                ops.append(dist.P2POp(dist.isend, f[s["ghost_first"]: s["ghost_first"] + s["recv_n"]], s["src"]))
+        for s in self.remote:
+            if len(s["sendlist"]):
+                ops.append(dist.P2POp(dist.irecv, self.recvbuf[s["send_off"]: s["send_off"] + len(s["sendlist"])], s["dest"]))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        n0 = self.nlocal
+        self._unpack_add(f, self.self_list, f[n0: n0 + self.nself])
+        self._unpack_add(f, self.rem_list, self.recvbuf)
+
+    allreduce_ev = Halo.allreduce_ev
+
+
+def build_rank_system_direct(x_own, types_own, sublo, subhi, grid, rank, gbox, cutoff, skin, device, lib=None):
+    """Same ghost shell as ``build_rank_system`` (possibly in a different row order), built for ``DirectHalo``."""
+    world = grid[0] * grid[1] * grid[2]
+    me = rank_coords(rank, grid)
+    rghost = cutoff + skin
+    x = np.ascontiguousarray(x_own, dtype=np.float64)
+    t = np.ascontiguousarray(types_own, dtype=np.int32)
+    nlocal = len(x)
+    lo, hi = [], []
+    for d in range(3):
+        if 2 * rghost >= (subhi[d] - sublo[d]) and grid[d] <= 2:
+            pass    # an atom may then be a ghost of the same neighbor through both faces; still correct
+        if rghost >= (subhi[d] - sublo[d]):
+            raise ValueError("ghost cutoff exceeds the brick length; use a larger per-GPU box")
+        lo.append(x[:, d] < sublo[d] + rghost)
+        hi.append(x[:, d] >= subhi[d] - rghost)
+    segs = []
+    for k, dv in enumerate(DIRS):
+        sel = np.ones(nlocal, dtype=bool)
+        shift = np.zeros(3)
+        for d in range(3):
+            if dv[d] == -1:
+                sel &= lo[d]
+                if me[d] == 0:
+                    shift[d] = gbox[d]
+            elif dv[d] == 1:
+                sel &= hi[d]
+                if me[d] == grid[d] - 1:
+                    shift[d] = -gbox[d]
+        dest = coords_rank([me[d] + dv[d] for d in range(3)], grid)
+        src = coords_rank([me[d] - dv[d] for d in range(3)], grid)
+        segs.append(dict(dir=k, dest=dest, src=src, sendlist=np.nonzero(sel)[0].astype(np.int32), shift=shift))
+    # segment sizes of every rank -> what each of my directions receives
+    counts = [len(s["sendlist"]) for s in segs]
+    if world > 1:
+        allc = [None] * world
+        dist.all_gather_object(allc, counts)
+    else:
+        allc = [counts]
+    for s in segs:
+        s["recv_n"] = allc[s["src"]][s["dir"]]
+    # setup exchange of ghost positions and types: one group, same matching order as the per-step exchange
+    ghosts_x, ghosts_t = {}, {}
+    sends, recvs, ops = [], [], []
+    for s in segs:
+        px, pt = x[s["sendlist"]] + s["shift"], t[s["sendlist"]]
+        if s["dest"] == rank:
+            ghosts_x[s["dir"]], ghosts_t[s["dir"]] = px, pt
+        else:
+            tx = torch.from_numpy(np.ascontiguousarray(px)).to(device)
+            tt = torch.from_numpy(np.ascontiguousarray(pt)).to(device)
+            sends.append((tx, tt))
+            if tx.numel():
+                ops += [dist.P2POp(dist.isend, tx, s["dest"]), dist.P2POp(dist.isend, tt, s["dest"])]
+    for s in segs:
+        if s["dest"] != rank:
+            rx = torch.empty((s["recv_n"], 3), dtype=torch.float64, device=device)
+            rt = torch.empty(s["recv_n"], dtype=torch.int32, device=device)
+            recvs.append((s["dir"], rx, rt))
+            if rx.numel():
+                ops += [dist.P2POp(dist.irecv, rx, s["src"]), dist.P2POp(dist.irecv, rt, s["src"])]
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        if device.type == "cuda":
+            torch.cuda.synchronize()
+    for k, rx, rt in recvs:
+        ghosts_x[k], ghosts_t[k] = rx.cpu().numpy(), rt.cpu().numpy()
+    halo = DirectHalo(rank, world, device, lib, nlocal, segs)
+    order = [s["dir"] for s in segs if s["dest"] == rank] + [s["dir"] for s in segs if s["dest"] != rank]
+    x = np.ascontiguousarray(np.concatenate([x] + [ghosts_x[k].reshape(-1, 3) for k in order]))
+    t = np.ascontiguousarray(np.concatenate([t] + [ghosts_t[k] for k in order]).astype(np.int32))
+    assert len(x) == halo.nall
+    numneigh, offsets, flat = harness.neighbor_list(x, nlocal, rghost)
+    owner = np.full(len(x), -1, dtype=np.int32)
+    owner[:nlocal] = np.arange(nlocal, dtype=np.int32)
+    sysm = harness.System(box=np.asarray(gbox, dtype=np.float64), nlocal=nlocal, x=x, type=t, owner=owner,
+                          ilist=np.arange(nlocal, dtype=np.int32), numneigh=numneigh, offsets=offsets, neigh=flat,
+                          rlist=rghost)
+    return sysm, halo
+
+
+def make_rank_system(config, cells, grid, rank, device, lib=None, cutoff=5.0, skin=2.0, jitter=0.05, direct=False):
     """BASELINE.json weak-scaling layout: the per-GPU box of ``config`` replicated on the brick grid."""
     cfg = harness.CONFIGS[config]
     x, box = harness.lattice(cfg["kind"], cfg["a"], cells or cfg["cells"], jitter=jitter, seed=2024)
     types = harness.random_types(x.shape[0], cfg["fractions"], cfg["type_seed"])
     me = np.array(rank_coords(rank, grid), dtype=np.float64)
     sublo = me * box
-    return build_rank_system(x + sublo, types, sublo, sublo + box, grid, rank, box * np.array(grid), cutoff, skin,
-                             device, lib)
+    build = build_rank_system_direct if direct else build_rank_system
+    return build(x + sublo, types, sublo, sublo + box, grid, rank, box * np.array(grid), cutoff, skin, device, lib)

@@ -21,13 +21,14 @@ from oracle_py import OracleMTP  # noqa: E402
 
 def main():
     out = sys.argv[1]
+    direct = len(sys.argv) > 2 and sys.argv[2] == "direct"
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     grid = decomp.brick_grid(world)
     dev = torch.device("cpu")
     cells = (5, 5, 5)
     pot = almtp.random_potential(10, 2)
-    sysm, halo = decomp.make_rank_system(2, cells, grid, rank, dev)
+    sysm, halo = decomp.make_rank_system(2, cells, grid, rank, dev, direct=direct)
     nlocal = sysm.nlocal
     # move the owned atoms after setup (same displacement field in every brick keeps the global reference simple)
     disp = np.random.default_rng(99).uniform(-0.05, 0.05, size=(nlocal, 3))

@@ -18,6 +18,7 @@ from mtp_b200.api import MTPB200  # noqa: E402
 
 def main():
     out, tmp = sys.argv[1], sys.argv[2]
+    direct = len(sys.argv) > 3 and sys.argv[3] == "direct"
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -29,7 +30,7 @@ def main():
     path = os.path.join(tmp, f"p{rank}.almtp")
     almtp.write_almtp(path, pot)
     mtp = MTPB200(path, device=local)
-    sysm, halo = decomp.make_rank_system(2, cells, grid, rank, dev, mtp.lib)
+    sysm, halo = decomp.make_rank_system(2, cells, grid, rank, dev, mtp.lib, direct=direct)
     nlocal, nall = sysm.nlocal, sysm.nall
     disp = np.random.default_rng(99).uniform(-0.05, 0.05, size=(nlocal, 3))
     x = torch.from_numpy(sysm.x.copy()).to(dev)

@@ -19,12 +19,13 @@ def _free_port():
     return p
 
 
+@pytest.mark.parametrize("kind", ["staged", "direct"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_decomposed_equals_global(tmp_path, built, world):
+def test_decomposed_equals_global(tmp_path, built, world, kind):
     out = str(tmp_path / "res.npz")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(HERE, "_mp_decomp_worker.py"), out]
+           os.path.join(HERE, "_mp_decomp_worker.py"), out, kind]
     env = dict(os.environ, OMP_NUM_THREADS="1")
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
@@ -35,6 +36,27 @@ def test_decomposed_equals_global(tmp_path, built, world):
     assert np.abs(z["ev"][1:7] - z["evref"][1:7]).max() <= 1e-11 * np.abs(z["evref"][1:7]).max()
     assert np.abs(z["eatom"] - z["eatomref"]).max() <= 1e-12 * np.abs(z["eatomref"]).max()
     assert z["ghosts"][0] > 0 and z["halo_bytes"][0] > 0
+
+
+def test_single_rank_direct_halo(built):
+    """world = 1, single-stage halo: same ghost set as the staged scheme, forward/reverse are self-images."""
+    import torch
+
+    from mtp_b200 import decomp, harness
+    sysm, halo = decomp.make_rank_system(1, (3, 3, 3), (1, 1, 1), 0, torch.device("cpu"), direct=True)
+    ref = harness.make_config(1, cells=(3, 3, 3))
+    assert sysm.nall == ref.nall
+    key = lambda a: a[np.lexsort(np.round(a, 9).T)]  # noqa: E731
+    assert np.allclose(key(sysm.x), key(ref.x))
+    assert np.array_equal(np.sort(sysm.numneigh[: sysm.nlocal]), np.sort(ref.numneigh[: ref.nlocal]))
+    x = torch.from_numpy(sysm.x.copy())
+    x[sysm.nlocal:] = 0.0
+    halo.forward(x)
+    assert np.array_equal(x.numpy(), sysm.x)
+    f = torch.from_numpy(np.random.default_rng(0).normal(size=(sysm.nall, 3)))
+    tot = f.sum(dim=0).clone()
+    halo.reverse(f)
+    assert np.allclose(f[: sysm.nlocal].sum(dim=0).numpy(), tot.numpy(), atol=1e-10)
 
 
 def test_single_rank_halo_is_periodic_self_image(built):

@@ -21,11 +21,11 @@ def _free_port():
     return p
 
 
-def _run(world, tmp_path):
+def _run(world, tmp_path, kind="direct"):
     out = str(tmp_path / "res.npz")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(HERE, "_mp_gpu_worker.py"), out, str(tmp_path)]
+           os.path.join(HERE, "_mp_gpu_worker.py"), out, str(tmp_path), kind]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
     return np.load(out)
@@ -40,14 +40,16 @@ def _check(z):
     assert z["launches"][0] > 0          # the halo went through the CUDA pack / unpack kernels
 
 
-def test_one_rank_device_halo(tmp_path, built):
-    """world = 1: periodic self-images through mtp_halo_pack_x / mtp_halo_unpack_add_f on the device."""
-    _check(_run(1, tmp_path))
+@pytest.mark.parametrize("kind", ["staged", "direct"])
+def test_one_rank_device_halo(tmp_path, built, kind):
+    """world = 1: periodic self-images through the device pack / unpack kernels."""
+    _check(_run(1, tmp_path, kind))
 
 
+@pytest.mark.parametrize("kind", ["staged", "direct"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_decomposed_cuda_equals_global(tmp_path, built, world):
+def test_decomposed_cuda_equals_global(tmp_path, built, world, kind):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    _check(_run(world, tmp_path))
+    _check(_run(world, tmp_path, kind))
