@@ -233,7 +233,9 @@ class DirectHalo:
         self.launches = 0
         self.nlocal = nlocal
         selfs = [s for s in segs if s["dest"] == rank]
-        rem = [s for s in segs if s["dest"] != rank]
+        # remote segments grouped by peer (DIRS order inside a peer): one message per peer and direction of travel
+        rem = sorted([s for s in segs if s["dest"] != rank], key=lambda s: (s["dest"], s["dir"]))
+        rem_in = sorted([s for s in segs if s["src"] != rank], key=lambda s: (s["src"], s["dir"]))
         self.remote = rem
 
         def cat(lst, key, dtype):
@@ -249,14 +251,20 @@ class DirectHalo:
         self.rem_list, self.rem_seg = t(cat(rem, "sendlist", np.int32)), t(seg_ids(rem))
         self.rem_shift = t(np.array([s["shift"] for s in rem] + [[0, 0, 0]], dtype=np.float64))
         self.nself = len(self.self_list)
-        # ghost rows: self segments first (recv_n == send n), then remote segments
-        g = nlocal + self.nself
+        # per peer: [offset, count] of its block in the send buffer and in the ghost rows
+        self.send_blocks, self.recv_blocks = {}, {}
         so = 0
         for s in rem:
-            s["send_off"], s["ghost_first"] = so, g
+            b = self.send_blocks.setdefault(s["dest"], [so, 0])
+            b[1] += len(s["sendlist"])
             so += len(s["sendlist"])
+        g = nlocal + self.nself
+        for s in rem_in:
+            b = self.recv_blocks.setdefault(s["src"], [g, 0])
+            b[1] += s["recv_n"]
             g += s["recv_n"]
         self.nall = g
+        self.ghost_order = [s["dir"] for s in selfs] + [s["dir"] for s in rem_in]
         self.sendbuf = torch.empty((so, 3), dtype=torch.float64, device=device)
         self.recvbuf = torch.empty((so, 3), dtype=torch.float64, device=device)
         self.bytes_per_step = 2 * 24 * so
@@ -289,25 +297,15 @@ class DirectHalo:
         n0 = self.nlocal
         self._pack(x, self.self_list, self.self_seg, self.self_shift, x[n0: n0 + self.nself])
         self._pack(x, self.rem_list, self.rem_seg, self.rem_shift, self.sendbuf)
-        ops = []
-        for s in self.remote:
-            if len(s["sendlist"]):
-                ops.append(dist.P2POp(dist.isend, self.sendbuf[s["send_off"]: s["send_off"] + len(s["sendlist"])], s["dest"]))
-        for s in self.remote:
-            if s["recv_n"]:
-                ops.append(dist.P2POp(dist.irecv, x[s["ghost_first"]: s["ghost_first"] + s["recv_n"]], s["src"]))
+        ops = [dist.P2POp(dist.isend, self.sendbuf[o: o + n], p) for p, (o, n) in sorted(self.send_blocks.items()) if n]
+        ops += [dist.P2POp(dist.irecv, x[o: o + n], p) for p, (o, n) in sorted(self.recv_blocks.items()) if n]
         if ops:
             for r in dist.batch_isend_irecv(ops):
                 r.wait()
 
     def reverse(self, f: torch.Tensor):
-        ops = []
-        for s in self.remote:
-            if s["recv_n"]:
-                ops.append(dist.P2POp(dist.isend, f[s["ghost_first"]: s["ghost_first"] + s["recv_n"]], s["src"]))
-        for s in self.remote:
-            if len(s["sendlist"]):
-                ops.append(dist.P2POp(dist.irecv, self.recvbuf[s["send_off"]: s["send_off"] + len(s["sendlist"])], s["dest"]))
+        ops = [dist.P2POp(dist.isend, f[o: o + n], p) for p, (o, n) in sorted(self.recv_blocks.items()) if n]
+        ops += [dist.P2POp(dist.irecv, self.recvbuf[o: o + n], p) for p, (o, n) in sorted(self.send_blocks.items()) if n]
         if ops:
             for r in dist.batch_isend_irecv(ops):
                 r.wait()
@@ -387,7 +385,7 @@ def build_rank_system_direct(x_own, types_own, sublo, subhi, grid, rank, gbox, c
     for k, rx, rt in recvs:
         ghosts_x[k], ghosts_t[k] = rx.cpu().numpy(), rt.cpu().numpy()
     halo = DirectHalo(rank, world, device, lib, nlocal, segs)
-    order = [s["dir"] for s in segs if s["dest"] == rank] + [s["dir"] for s in segs if s["dest"] != rank]
+    order = halo.ghost_order
     x = np.ascontiguousarray(np.concatenate([x] + [ghosts_x[k].reshape(-1, 3) for k in order]))
     t = np.ascontiguousarray(np.concatenate([t] + [ghosts_t[k] for k in order]).astype(np.int32))
     assert len(x) == halo.nall
