@@ -208,6 +208,8 @@ def main():
     ap.add_argument("--ref-cells", type=int, nargs=3, default=None, help="CPU-baseline sample box")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", default="large", choices=["large", "small"])
+    ap.add_argument("--grade-every", type=int, default=0,
+                    help="config 4: request per-atom extrapolation grades every K-th step (fix pair semantics); 0 = never")
     ap.add_argument("--halo", default="direct", choices=["direct", "staged"],
                     help="ghost exchange: one 26-direction stage (default) or LAMMPS's three dimension-by-dimension stages")
     ap.add_argument("--lanes", type=int, default=2, help="internal streams the super-chunks are dealt to (mtp_set_lanes)")
@@ -301,13 +303,19 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     max_nn = int(sysm.numneigh[:nlocal].max())      # what a LAMMPS-KOKKOS list knows as d_neighbors.extent(1)
 
+    t_grades = torch.zeros(nall, dtype=torch.float64, device=dev) if args.grade_every else None
+    step_no = [0]
+
     def step_device():
         # what LAMMPS does around Pair::compute every step: forward comm of x, zero f, compute, reverse comm of f,
         # and the energy/virial all-reduce
         halo.forward(t_x)
         t_f.zero_()
+        grade_step = bool(args.grade_every) and step_no[0] % args.grade_every == 0
+        step_no[0] += 1
         mtp.compute_device(t_x, t_type, t_ilist, t_nn, t_neigh, t_off, t_f, t_ev, eflag=1, vflag=1,
-                           variant=variant, stream=stream, max_numneigh=max_nn)
+                           variant=variant, stream=stream, max_numneigh=max_nn, grade=grade_step,
+                           grades=t_grades if grade_step else None)
         halo.reverse(t_f)
         halo.allreduce_ev(t_ev)
 
@@ -509,7 +517,8 @@ def main():
                        "parallelism": "brick grid %dx%dx%d, one rank per GPU, %s NCCL send/recv halo (%d B/rank/step)" % (
                            *brick_grid(world), args.halo, halo.bytes_per_step),
                        "l2": "256 MiB write between timed iterations (L2 flush), per-step CUDA events summed",
-                       "variant": args.variant, "chunksize": args.chunksize, "flags": "eflag=1 vflag=1"},
+                       "variant": args.variant, "chunksize": args.chunksize, "flags": "eflag=1 vflag=1",
+                       "grade_every": args.grade_every},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "energy": energy}
     emit(line)

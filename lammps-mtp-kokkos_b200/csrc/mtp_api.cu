@@ -190,7 +190,7 @@ struct mtp_handle {
   Lane lanes[kMaxLanes];
   cudaEvent_t ev_fork = nullptr;
   int nlanes = 2;
-  int v2_grid_g = 0, v2_grid_r = 0, v2_grid_m = 0, v2_grid_f = 0, v2_ab = 0;
+  int v2_grid_g = 0, v2_grid_r = 0, v2_grid_m = 0, v2_grid_f = 0, v2_grid_fg[2] = {0, 0}, v2_ab = 0;
   size_t v2_smem_g = 0, v2_smem_f = 0, v2_smem_m = 0;
   int v2_chunk = 0;
   // optional per-kernel-class device timing (mtp_profile_enable): CUDA events recorded on the launch stream
@@ -271,11 +271,12 @@ struct V2Entry {
   int d0, R, KF, NP;
   V2GatherKernel radial;
   V2MomentsKernel moments;
-  V2ForcesKernel forces[4];
+  V2ForcesKernel forces[2][4];    // [grade step][atoms-per-CTA choice]
 };
 #define V2_ENTRY(D)                                                                                          \
   {D, V2Shape<D>::R, V2Shape<D>::KF, V2Shape<D>::NP, mtp_radial_kernel<V2Shape<D>::R>, mtp_moments_v2<D>,    \
-   {mtp_forces_v2<D, 64>, mtp_forces_v2<D, 32>, mtp_forces_v2<D, 16>, mtp_forces_v2<D, 8>}}
+   {{mtp_forces_v2<D, 64, false>, mtp_forces_v2<D, 32, false>, mtp_forces_v2<D, 16, false>, mtp_forces_v2<D, 8, false>},   \
+    {mtp_forces_v2<D, 64, true>, mtp_forces_v2<D, 32, true>, mtp_forces_v2<D, 16, true>, mtp_forces_v2<D, 8, true>}}}
 const V2Entry kV2[] = {V2_ENTRY(0), V2_ENTRY(1), V2_ENTRY(2), V2_ENTRY(3), V2_ENTRY(4), V2_ENTRY(5),
                        V2_ENTRY(6), V2_ENTRY(7), V2_ENTRY(8), V2_ENTRY(9), V2_ENTRY(10)};
 constexpr int kV2Count = sizeof(kV2) / sizeof(kV2[0]);
@@ -437,8 +438,9 @@ void upload_potential(mtp_handle *h)
         CUDA_CHECK(cudaFuncSetAttribute((const void *) mtp_gather_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CUDA_CHECK(cudaFuncSetAttribute((const void *) E.radial, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CUDA_CHECK(cudaFuncSetAttribute((const void *) E.moments, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        for (int q = 0; q < 4; q++)
-          CUDA_CHECK(cudaFuncSetAttribute((const void *) E.forces[q], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        for (int gq = 0; gq < 2; gq++)
+          for (int q = 0; q < 4; q++)
+            CUDA_CHECK(cudaFuncSetAttribute((const void *) E.forces[gq][q], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       }
       int per_sm = 0;
       CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) mtp_gather_kernel, 256, 0));
@@ -456,7 +458,8 @@ void upload_potential(mtp_handle *h)
       h->v2_ab = -1;
       for (int q = 0; q < 4 && ok; q++) {
         const size_t need = (size_t) 2 * E.KF * kV2AB[q] * 8 + (size_t) 2 * (kV2AB[q] + 1) * 4;
-        if (need <= std::min<size_t>(110 * 1024, max_dynamic_smem((const void *) E.forces[q], smem_max))) {
+        if (need <= std::min<size_t>(110 * 1024, std::min(max_dynamic_smem((const void *) E.forces[0][q], smem_max),
+                                                           max_dynamic_smem((const void *) E.forces[1][q], smem_max)))) {
           h->v2_ab = q;
           h->v2_smem_f = need;
           break;
@@ -464,10 +467,13 @@ void upload_potential(mtp_handle *h)
       }
       ok = ok && h->v2_ab >= 0;
       if (ok) {
-        const void *fk = (const void *) E.forces[h->v2_ab];
-        CUDA_CHECK(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->v2_smem_f));
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk, 256, h->v2_smem_f));
-        h->v2_grid_f = std::max(1, per_sm) * h->sm_count;
+        for (int gq = 0; gq < 2; gq++) {
+          const void *fk = (const void *) E.forces[gq][h->v2_ab];
+          CUDA_CHECK(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->v2_smem_f));
+          CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk, 256, h->v2_smem_f));
+          h->v2_grid_fg[gq] = std::max(1, per_sm) * h->sm_count;
+        }
+        h->v2_grid_f = std::max(h->v2_grid_fg[0], h->v2_grid_fg[1]);
       }
     }
     if (!ok) h->v2_entry = -1;
@@ -558,9 +564,12 @@ struct ProfSpan {
 };
 
 // atoms per super-chunk for a call with inum centres (shared by launch_site and the host path's upload pipeline)
+// grade steps ride the v2 pair stages too (candidate kernel keeps one accumulator per neighbor species: S <= 8)
+bool v2_applies(const mtp_handle *h, bool grade) { return h->v2_entry >= 0 && (!grade || h->dpot.S <= 8); }
+
 int plan_chunk(const mtp_handle *h, int inum, bool grade)
 {
-  const bool use_v2 = h->v2_entry >= 0 && !grade;
+  const bool use_v2 = v2_applies(h, grade);
   const bool pipeline = use_v2 || h->v1_entry >= 0;
   int chunk = std::max(1, std::min(h->chunksize, inum > 0 ? inum : 1));
   if (pipeline) {
@@ -616,7 +625,7 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
 
   const int gi = grade ? 1 : 0;
   const bool cfg = grade && h->pot.configuration_mode;
-  const bool use_v2 = h->v2_entry >= 0 && !grade;
+  const bool use_v2 = v2_applies(h, grade);
   const bool pipeline = use_v2 || h->v1_entry >= 0;
   // super-chunk: bounded by the user's "chunksize"; the pipeline additionally keeps its two [K][chunk]
   // intermediates within ~48 MB so that they stay L2-resident
@@ -642,7 +651,7 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
   const int ld = (chunk + 63) / 64 * 64;
   if (grade) h->d_cand.ensure((size_t) chunk * h->qpad);
   const int nsuper = a.inum > 0 ? (a.inum + chunk - 1) / chunk : 1;
-  const int nlanes = use_v2 ? std::max(1, std::min(h->nlanes, nsuper)) : 1;
+  const int nlanes = (use_v2 && !grade) ? std::max(1, std::min(h->nlanes, nsuper)) : 1;    // grade scratch is not per lane
   if (use_v2) {
     const V2Entry &E = kV2[h->v2_entry];
     for (int l = 0; l < nlanes; l++) {
@@ -738,15 +747,21 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
       double *part_p = h->d_partials.p + (size_t) rows_used * 8;
       {
         ProfSpan sp(h, MTP_PROF_PROGRAM, ls);
-        mtp_program_kernel<false><<<gp, PROG_THREADS, smem_p, ls>>>(d, s, L.mb.p, L.gb.p, ld, na, lna, part_p);
+        if (grade) mtp_program_kernel<true><<<gp, PROG_THREADS, smem_p, ls>>>(d, s, L.mb.p, L.gb.p, ld, na, lna, part_p);
+        else
+          mtp_program_kernel<false><<<gp, PROG_THREADS, smem_p, ls>>>(d, s, L.mb.p, L.gb.p, ld, na, lna, part_p);
       }
       rows_used += gp;
       const int ab = kV2AB[h->v2_ab];
-      const int gf = std::max(1, std::min(h->v2_grid_f, (n + ab - 1) / ab));
+      const int gf = std::max(1, std::min(h->v2_grid_fg[gi], (n + ab - 1) / ab));
       double *part_f = h->d_partials.p + (size_t) rows_used * 8;
       {
         ProfSpan sp(h, MTP_PROF_FORCES, ls);
-        E.forces[h->v2_ab]<<<gf, 256, h->v2_smem_f, ls>>>(s, pb, L.gb.p, ld, part_f);
+        E.forces[gi][h->v2_ab]<<<gf, 256, h->v2_smem_f, ls>>>(s, pb, L.gb.p, ld, part_f);
+        if (grade) {
+          mtp_cand_radial_kernel<<<std::max(1, std::min(h->v2_grid_g, (n + 7) / 8)), 256, 0, ls>>>(d, s, pb);
+          g_launches++;
+        }
       }
       rows_used += gf;
       g_launches += 5;

@@ -440,37 +440,49 @@ mtp_moments_v2(SiteArgs a, PairBuf pb, double *__restrict__ mb, int ld)
 
 // ===================================================================================================== forces
 // gradient of sum_mu f_mu(d) P_mu(u), P_mu(u) = sum_q g[q][mu] u^q, by three nested Horner sweeps; g = canonical row
-template <int D0, int AB>
+template <int D0, int AB, bool GRADE>
 __device__ __forceinline__ void v2_pair_force(const double *__restrict__ gr /* g + al, row stride AB */, double ux, double uy, double uz,
                                               const double (&fvi)[V2Shape<D0>::R], const double (&fder)[V2Shape<D0>::R],
-                                              double &Fx, double &Fy, double &Fz)
+                                              double &Fx, double &Fy, double &Fz, double (&pm)[V2Shape<D0>::R])
 {
   using Sh = V2Shape<D0>;
+  constexpr int R = Sh::R;
   double Pv = 0, Px = 0, Py = 0, Pz = 0, Pd = 0;
+  double PM[R];    // GRADE: P_mu(u) = sum_q g[q][mu] u^q, one Horner chain per radial index
+#pragma unroll
+  for (int mu = 0; mu < R; mu++) PM[mu] = 0.0;
   int sl = Sh::KF;
 #pragma unroll
   for (int a = D0; a >= 0; a--) {
     double Q = 0, Qy = 0, Qz = 0, Qd = 0;
+    double QM[R];
+#pragma unroll
+    for (int mu = 0; mu < R; mu++) QM[mu] = 0.0;
 #pragma unroll
     for (int b = D0 - a; b >= 0; b--) {
       double T = 0, Tz = 0, Td = 0;
+      double TM[R];
+#pragma unroll
+      for (int mu = 0; mu < R; mu++) TM[mu] = 0.0;
 #pragma unroll
       for (int c = D0 - a - b; c >= 0; c--) {
-        constexpr int dummy = 0;
-        (void) dummy;
         const int rc = Sh::rcnt(a + b + c);
         sl -= rc;
         double W = 0, Wd = 0;
 #pragma unroll
-        for (int mu = 0; mu < rc; mu++) {
-          const double g = gr[(sl + mu) * AB];
-          if (mu == 0) {
-            W = fvi[0] * g;
-            Wd = fder[0] * g;
-          } else {
-            W = fma(fvi[mu], g, W);
-            Wd = fma(fder[mu], g, Wd);
-          }
+        for (int mu = 0; mu < R; mu++) {
+          if (mu < rc) {
+            const double g = gr[(sl + mu) * AB];
+            if (mu == 0) {
+              W = fvi[0] * g;
+              Wd = fder[0] * g;
+            } else {
+              W = fma(fvi[mu], g, W);
+              Wd = fma(fder[mu], g, Wd);
+            }
+            if (GRADE) TM[mu] = (c == D0 - a - b) ? g : fma(TM[mu], uz, g);
+          } else if (GRADE && c != D0 - a - b)
+            TM[mu] *= uz;
         }
         if (c == D0 - a - b) {    // top of the z sweep: T = Tz = Td = 0
           T = W;
@@ -485,11 +497,19 @@ __device__ __forceinline__ void v2_pair_force(const double *__restrict__ gr /* g
         Q = T;
         Qz = Tz;
         Qd = Td;
+        if (GRADE) {
+#pragma unroll
+          for (int mu = 0; mu < R; mu++) QM[mu] = TM[mu];
+        }
       } else {
         Qy = fma(Qy, uy, Q);
         Q = fma(Q, uy, T);
         Qz = fma(Qz, uy, Tz);
         Qd = fma(Qd, uy, Td);
+        if (GRADE) {
+#pragma unroll
+          for (int mu = 0; mu < R; mu++) QM[mu] = fma(QM[mu], uy, TM[mu]);
+        }
       }
     }
     if (a == D0) {
@@ -497,21 +517,31 @@ __device__ __forceinline__ void v2_pair_force(const double *__restrict__ gr /* g
       Py = Qy;
       Pz = Qz;
       Pd = Qd;
+      if (GRADE) {
+#pragma unroll
+        for (int mu = 0; mu < R; mu++) PM[mu] = QM[mu];
+      }
     } else {
       Px = fma(Px, ux, Pv);
       Pv = fma(Pv, ux, Q);
       Py = fma(Py, ux, Qy);
       Pz = fma(Pz, ux, Qz);
       Pd = fma(Pd, ux, Qd);
+      if (GRADE) {
+#pragma unroll
+        for (int mu = 0; mu < R; mu++) PM[mu] = fma(PM[mu], ux, QM[mu]);
+      }
     }
   }
   const double S = Pd - (ux * Px + uy * Py + uz * Pz);
   Fx = fma(ux, S, Px);
   Fy = fma(uy, S, Py);
   Fz = fma(uz, S, Pz);
+#pragma unroll
+  for (int mu = 0; mu < R; mu++) pm[mu] = PM[mu];
 }
 
-template <int D0, int AB>
+template <int D0, int AB, bool GRADE>
 __global__ void __launch_bounds__(256, 2)
 mtp_forces_v2(SiteArgs a, PairBuf pb, const double *__restrict__ gb, int ld, double *__restrict__ partials)
 {
@@ -615,7 +645,13 @@ mtp_forces_v2(SiteArgs a, PairBuf pb, const double *__restrict__ gb, int ld, dou
           fvi[mu] = cur.f[mu] * invd;
           fder[mu] = cur.fd[mu];
         }
-        v2_pair_force<D0, AB>(g + al, ux, uy, uz, fvi, fder, Fx, Fy, Fz);
+        double pm[R];
+        v2_pair_force<D0, AB, GRADE>(g + al, ux, uy, uz, fvi, fder, Fx, Fy, Fz, pm);
+        if (GRADE) {    // P_mu(u_n) replaces f_mu in the pair record (consumed by mtp_cand_radial_kernel)
+          const size_t sp = (size_t) (ii0 + al) * pb.ncap + (p0 + threadIdx.x - pre[al]);
+#pragma unroll
+          for (int mu = 0; mu < R; mu++) pb.fld[(4 + mu) * pb.cap + sp] = pm[mu];
+        }
         const int j = cur.j;
         atomicAdd(&a.f[3 * (size_t) j], -Fx);
         atomicAdd(&a.f[3 * (size_t) j + 1], -Fy);
@@ -677,6 +713,54 @@ mtp_forces_v2(SiteArgs a, PairBuf pb, const double *__restrict__ gb, int ld, dou
     double s = 0.0;
     for (int w = 0; w < (int) (blockDim.x >> 5); w++) s += s_part[w][threadIdx.x];
     partials[(size_t) blockIdx.x * 8 + threadIdx.x] = s;
+  }
+}
+
+// Grade steps: radial block + species one-hot of the candidate vector of every centre atom
+// (pair_mtp_extrapolation.cpp:193-198,235-252,322-329):
+//     b[(it*S + jt)*R*B + mu*B + ri] = sum_n [jt_n == jt] phi_ri(d_n) P_mu(u_n),   b[S*S*R*B + it] = 1
+// Warp per atom, lane = (mu, ri): no atomics, fixed summation order.  P_mu(u_n) was left in the f_mu fields of
+// the pair records by mtp_forces_v2<GRADE>; the linear block was written by the program kernel.
+__global__ void __launch_bounds__(256)
+mtp_cand_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  const int RB = pot.R * pot.B, nrad = pot.S * pot.S * RB;
+  for (int ii = blockIdx.x * W + warp; ii < a.inum; ii += gridDim.x * W) {
+    const int i = a.ilist ? a.ilist[a.first_ii + ii] : a.first_ii + ii;
+    int itype = (int) a.xt[i].t;
+    if (itype < 0 || itype >= pot.S) itype = 0;
+    const int cnt = pb.pcnt[ii];
+    double *row = a.cand_rows + (size_t) ii * a.cand_ld;
+    for (int q = lane; q < nrad + pot.S; q += 32) row[q] = (q == nrad + itype) ? 1.0 : 0.0;
+    for (int q = pot.Q + lane; q < a.cand_ld; q += 32) row[q] = 0.0;
+    __syncwarp();
+    for (int c = lane; c < RB; c += 32) {
+      const int mu = c / pot.B, ri = c - mu * pot.B;
+      double acc[8];
+#pragma unroll
+      for (int s = 0; s < 8; s++) acc[s] = 0.0;
+      for (int n = 0; n < cnt; n++) {
+        const size_t sp = (size_t) ii * pb.ncap + n;
+        const double d = pb.fld[3 * pb.cap + sp], pmv = pb.fld[(size_t) (4 + mu) * pb.cap + sp];
+        const int jt = pb.pjt[sp] & 0xffff;
+        const double t = d - pot.rmax;
+        const double ksi = (2 * d - (pot.rmin + pot.rmax)) / (pot.rmax - pot.rmin);
+        double v_prev = pot.scaling * (1 * t * t), v_cur = pot.scaling * (ksi * t * t);
+        double phi = ri == 0 ? v_prev : v_cur;
+        for (int k = 2; k <= ri; k++) {
+          phi = 2 * ksi * v_cur - v_prev;
+          v_prev = v_cur;
+          v_cur = phi;
+        }
+        const double val = phi * pmv;
+#pragma unroll
+        for (int s = 0; s < 8; s++)
+          if (s == jt) acc[s] += val;
+      }
+      for (int s = 0; s < pot.S && s < 8; s++) row[(size_t) (itype * pot.S + s) * RB + c] = acc[s];
+    }
+    __syncwarp();
   }
 }
 
