@@ -565,7 +565,10 @@ struct ProfSpan {
 
 // atoms per super-chunk for a call with inum centres (shared by launch_site and the host path's upload pipeline)
 // grade steps ride the v2 pair stages too (candidate kernel keeps one accumulator per neighbor species: S <= 8)
-bool v2_applies(const mtp_handle *h, bool grade) { return h->v2_entry >= 0 && (!grade || h->dpot.S <= 8); }
+bool v2_applies(const mtp_handle *h, bool grade)
+{
+  return h->v2_entry >= 0 && (!grade || (h->dpot.S <= 8 && h->dpot.B + h->dpot.R <= 22));
+}
 
 int plan_chunk(const mtp_handle *h, int inum, bool grade)
 {
@@ -759,7 +762,13 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
         ProfSpan sp(h, MTP_PROF_FORCES, ls);
         E.forces[gi][h->v2_ab]<<<gf, 256, h->v2_smem_f, ls>>>(s, pb, L.gb.p, ld, part_f);
         if (grade) {
-          mtp_cand_radial_kernel<<<std::max(1, std::min(h->v2_grid_g, (n + 7) / 8)), 256, 0, ls>>>(d, s, pb);
+          const size_t smem_c = (size_t) 8 * (CAND_TILE * (d.B + d.R) + CAND_TILE / 2) * 8;
+          const int gc = std::max(1, std::min(4 * h->sm_count, (n + 7) / 8));
+          if (d.S <= 2) mtp_cand_radial_kernel<2><<<gc, 256, smem_c, ls>>>(d, s, pb);
+          else if (d.S <= 4)
+            mtp_cand_radial_kernel<4><<<gc, 256, smem_c, ls>>>(d, s, pb);
+          else
+            mtp_cand_radial_kernel<8><<<gc, 256, smem_c, ls>>>(d, s, pb);
           g_launches++;
         }
       }
@@ -806,10 +815,24 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
         cand_colsum_kernel<<<(d.Q + 127) / 128, 128, 0, st>>>(h->d_cand.p, n, h->qpad, d.Q, h->d_cfg.p, 1);
         g_launches++;
       } else {
-        const int gb = (n + GRADE_WARPS * 8 - 1) / (GRADE_WARPS * 8);
-        h->d_blockmax.ensure((size_t) gb);
-        grade_dmma_kernel<<<gb, GRADE_WARPS * 32, 0, st>>>(h->d_cand.p, n, h->qpad, h->d_ainv.p, a.ilist, first,
-                                                           a.grades ? a.grades : nullptr, h->d_blockmax.p);
+        int gb = (n + GRADE_WARPS * 8 - 1) / (GRADE_WARPS * 8);
+        const size_t smem_g = (size_t) 2 * GRT_COLS * (h->qpad + 4) * 8;
+        if (h->qpad <= 256 && !getenv("MTP_B200_GRADE_SMEM")) {    // A operand of 8 rows fits one warp's registers
+          gb = (n + GRT_WARPS * 8 - 1) / (GRT_WARPS * 8);
+          h->d_blockmax.ensure((size_t) gb);
+          static bool attr_set = false;
+          if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute((const void *) grade_dmma_reg_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int) (2 * GRT_COLS * (256 + 4) * 8)));
+            attr_set = true;
+          }
+          grade_dmma_reg_kernel<64><<<std::min(gb, h->sm_count), GRT_WARPS * 32, smem_g, st>>>(
+              h->d_cand.p, n, h->qpad, h->d_ainv.p, a.ilist, first, a.grades ? a.grades : nullptr, h->d_blockmax.p);
+        } else {
+          h->d_blockmax.ensure((size_t) gb);
+          grade_dmma_kernel<<<gb, GRADE_WARPS * 32, 0, st>>>(h->d_cand.p, n, h->qpad, h->d_ainv.p, a.ilist, first,
+                                                             a.grades ? a.grades : nullptr, h->d_blockmax.p);
+        }
         g_launches++;
         finalize_max_kernel<<<1, 32, 0, st>>>(h->d_blockmax.p, gb, a.ev_out + 7, 1);
         g_launches++;

@@ -619,6 +619,86 @@ __global__ void cand_colsum_kernel(const double *bmat, int nrows, int ld, int q,
   cand[c] = s;
 }
 
+// Register-resident variant for Qpad <= 4 * KS (covers every level <= 16 potential with S <= 2): one warp owns 8
+// candidate rows and keeps their whole A operand (8 x Qpad, i.e. KS k-steps per lane) in registers.  The rows of
+// Ainv stream through shared memory as B tiles of GRT_COLS output columns x Qpad, double-buffered with cp.async and
+// shared by the 8 warps (64 rows) of the CTA, so every element of Ainv is fetched once per 64 rows and the DMMA
+// operands come from shared memory at LDS latency.  Four column tiles = four independent accumulator chains per
+// warp.  G is never written: |.| row-max epilogue in registers (pair_mtp_extrapolation.cpp:347-358).
+constexpr int GRT_WARPS = 8;
+constexpr int GRT_COLS = 32;
+template <int KS>
+__global__ void __launch_bounds__(GRT_WARPS * 32, 1)
+grade_dmma_reg_kernel(const double *__restrict__ bmat, int nrows, int ld /*Qpad = multiple of 8, <= 4 * KS*/,
+                      const double *__restrict__ ainv_pad /*[Qpad][Qpad]*/, const int *__restrict__ ilist, int first_ii,
+                      double *__restrict__ grades, double *__restrict__ block_max)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *tiles = reinterpret_cast<double *>(smem_raw);    // [2][GRT_COLS][ld + 4]
+  __shared__ double s_w[GRT_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lds = ld + 4;                                  // row stride: 8 columns x 4 k land in distinct banks
+  const int ksteps = ld >> 2, ntile = ld / GRT_COLS + ((ld % GRT_COLS) ? 1 : 0);
+  const int nchunk16 = ld >> 1;                            // 16-byte pieces per row of Ainv
+
+  auto stage = [&](int buf, int t) {                       // rows [t*32, t*32+32) of Ainv -> tiles[buf]
+    double *dst = tiles + (size_t) buf * GRT_COLS * lds;
+    for (int e = threadIdx.x; e < GRT_COLS * nchunk16; e += blockDim.x) {
+      const int r = e / nchunk16, c = e - r * nchunk16;
+      const int col = min(t * GRT_COLS + r, ld - 1);       // clamped rows repeat the last one (harmless for a max)
+      cp_async16(dst + (size_t) r * lds + 2 * c, ainv_pad + (size_t) col * ld + 2 * c);
+    }
+    cp_async_commit();
+  };
+
+  for (int rb = blockIdx.x; rb * GRT_WARPS * 8 < nrows; rb += gridDim.x) {
+    const int row = (rb * GRT_WARPS + warp) * 8 + (lane >> 2), kk = lane & 3;
+    double a[KS];
+#pragma unroll
+    for (int k = 0; k < KS; k++) a[k] = (k < ksteps && row < nrows) ? bmat[(size_t) row * ld + 4 * k + kk] : 0.0;
+    double rmax0 = 0.0;
+    __syncthreads();    // previous row block is done with both buffers
+    stage(0, 0);
+    for (int t = 0; t < ntile; t++) {
+      if (t + 1 < ntile) {
+        stage((t + 1) & 1, t + 1);
+        cp_async_wait<1>();
+      } else
+        cp_async_wait<0>();
+      __syncthreads();
+      const double *bt = tiles + (size_t) (t & 1) * GRT_COLS * lds + (size_t) (lane >> 2) * lds + kk;
+      double acc[4][2];
+#pragma unroll
+      for (int q = 0; q < 4; q++) acc[q][0] = acc[q][1] = 0.0;
+#pragma unroll
+      for (int k = 0; k < KS; k++) {
+        if (k < ksteps) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) dmma884(acc[q][0], acc[q][1], a[k], bt[(size_t) q * 8 * lds + 4 * k]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) rmax0 = fmax(rmax0, fmax(fabs(acc[q][0]), fabs(acc[q][1])));
+      __syncthreads();    // tile consumed before its buffer is refilled two iterations later
+    }
+    rmax0 = fmax(rmax0, __shfl_xor_sync(FULL, rmax0, 1));
+    rmax0 = fmax(rmax0, __shfl_xor_sync(FULL, rmax0, 2));
+    if (grades && kk == 0 && row < nrows) {
+      const int i = ilist ? ilist[first_ii + row] : first_ii + row;
+      grades[i] = rmax0;
+    }
+    double wmax = (row < nrows) ? rmax0 : 0.0;
+    wmax = warp_max(wmax);
+    if (lane == 0) s_w[warp] = wmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double m = 0.0;
+      for (int w = 0; w < GRT_WARPS; w++) m = fmax(m, s_w[w]);
+      block_max[rb] = m;
+    }
+  }
+}
+
 // cfg grade: max_i |Ainv[i,:] . b| / natoms  (pair_mtp_extrapolation.cpp:366-376)
 __global__ void cfg_grade_kernel(const double *ainv_pad, int ld, int q, const double *cand, double inv_natoms,
                                  double *ev7)

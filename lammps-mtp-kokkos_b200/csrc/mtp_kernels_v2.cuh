@@ -721,11 +721,18 @@ mtp_forces_v2(SiteArgs a, PairBuf pb, const double *__restrict__ gb, int ld, dou
 //     b[(it*S + jt)*R*B + mu*B + ri] = sum_n [jt_n == jt] phi_ri(d_n) P_mu(u_n),   b[S*S*R*B + it] = 1
 // Warp per atom, lane = (mu, ri): no atomics, fixed summation order.  P_mu(u_n) was left in the f_mu fields of
 // the pair records by mtp_forces_v2<GRADE>; the linear block was written by the program kernel.
+constexpr int CAND_TILE = 32;    // pairs staged per warp
+template <int SMAX>
 __global__ void __launch_bounds__(256)
 mtp_cand_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
 {
+  extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-  const int RB = pot.R * pot.B, nrad = pot.S * pot.S * RB;
+  const int R = pot.R, B = pot.B, RB = R * B, nrad = pot.S * pot.S * RB;
+  // per warp: phi[B][TILE] (lane = pair computes the Chebyshev values once), P_mu[R][TILE], neighbor species[TILE]
+  double *sphi = reinterpret_cast<double *>(smem) + (size_t) warp * (CAND_TILE * (B + R) + CAND_TILE / 2);
+  double *spm = sphi + (size_t) B * CAND_TILE;
+  int *sjt = reinterpret_cast<int *>(spm + (size_t) R * CAND_TILE);
   for (int ii = blockIdx.x * W + warp; ii < a.inum; ii += gridDim.x * W) {
     const int i = a.ilist ? a.ilist[a.first_ii + ii] : a.first_ii + ii;
     int itype = (int) a.xt[i].t;
@@ -734,31 +741,46 @@ mtp_cand_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
     double *row = a.cand_rows + (size_t) ii * a.cand_ld;
     for (int q = lane; q < nrad + pot.S; q += 32) row[q] = (q == nrad + itype) ? 1.0 : 0.0;
     for (int q = pot.Q + lane; q < a.cand_ld; q += 32) row[q] = 0.0;
-    __syncwarp();
-    for (int c = lane; c < RB; c += 32) {
-      const int mu = c / pot.B, ri = c - mu * pot.B;
-      double acc[8];
+    for (int c0 = 0; c0 < RB; c0 += 32) {
+      const int c = c0 + lane;
+      const int mu = c < RB ? c / B : 0, ri = c < RB ? c - mu * B : 0;
+      double acc[SMAX];
 #pragma unroll
-      for (int s = 0; s < 8; s++) acc[s] = 0.0;
-      for (int n = 0; n < cnt; n++) {
-        const size_t sp = (size_t) ii * pb.ncap + n;
-        const double d = pb.fld[3 * pb.cap + sp], pmv = pb.fld[(size_t) (4 + mu) * pb.cap + sp];
-        const int jt = pb.pjt[sp] & 0xffff;
-        const double t = d - pot.rmax;
-        const double ksi = (2 * d - (pot.rmin + pot.rmax)) / (pot.rmax - pot.rmin);
-        double v_prev = pot.scaling * (1 * t * t), v_cur = pot.scaling * (ksi * t * t);
-        double phi = ri == 0 ? v_prev : v_cur;
-        for (int k = 2; k <= ri; k++) {
-          phi = 2 * ksi * v_cur - v_prev;
-          v_prev = v_cur;
-          v_cur = phi;
+      for (int s = 0; s < SMAX; s++) acc[s] = 0.0;
+      for (int n0 = 0; n0 < cnt; n0 += CAND_TILE) {
+        const int nt = min(CAND_TILE, cnt - n0);
+        __syncwarp();
+        if (lane < nt) {    // lane = pair: one coalesced round of loads, the Chebyshev recurrence once per pair
+          const size_t sp = (size_t) ii * pb.ncap + n0 + lane;
+          const double d = pb.fld[3 * pb.cap + sp];
+          sjt[lane] = pb.pjt[sp] & 0xffff;
+          for (int m = 0; m < R; m++) spm[m * CAND_TILE + lane] = pb.fld[(size_t) (4 + m) * pb.cap + sp];
+          const double t = d - pot.rmax;
+          const double ksi = (2 * d - (pot.rmin + pot.rmax)) / (pot.rmax - pot.rmin);
+          double v_prev = pot.scaling * (1 * t * t), v_cur = pot.scaling * (ksi * t * t);
+          sphi[lane] = v_prev;
+          if (B > 1) sphi[CAND_TILE + lane] = v_cur;
+          for (int k = 2; k < B; k++) {
+            const double vn = 2 * ksi * v_cur - v_prev;
+            v_prev = v_cur;
+            v_cur = vn;
+            sphi[k * CAND_TILE + lane] = vn;
+          }
         }
-        const double val = phi * pmv;
+        __syncwarp();
+        const double *ph = sphi + ri * CAND_TILE, *pmv = spm + mu * CAND_TILE;
+        for (int n = 0; n < nt; n++) {
+          const double val = ph[n] * pmv[n];
+          const int jt = sjt[n];
 #pragma unroll
-        for (int s = 0; s < 8; s++)
-          if (s == jt) acc[s] += val;
+          for (int s = 0; s < SMAX; s++) acc[s] += (jt == s) ? val : 0.0;
+        }
       }
-      for (int s = 0; s < pot.S && s < 8; s++) row[(size_t) (itype * pot.S + s) * RB + c] = acc[s];
+      if (c < RB) {
+#pragma unroll
+        for (int s = 0; s < SMAX; s++)
+          if (s < pot.S) row[(size_t) (itype * pot.S + s) * RB + c] = acc[s];
+      }
     }
     __syncwarp();
   }
