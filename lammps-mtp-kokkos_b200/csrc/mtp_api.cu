@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <ctime>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -152,6 +153,9 @@ struct mtp_handle {
   DevBuf<double> d_partials, d_cand, d_blockmax, d_cfg;
   DevBuf<int> d_status;
   // host-buffer path
+  DevBuf<double> h_f0;
+  cudaEvent_t ev_f0 = nullptr;
+  size_t h_nid = 0;
   DevBuf<double> h_x, h_f, h_eatom, h_vatom, h_grades, h_ev, h_cfgc;
   DevBuf<int> h_type, h_ilist, h_numneigh, h_neigh;
   DevBuf<long long> h_offsets;
@@ -1026,6 +1030,7 @@ void mtp_destroy(mtp_handle *h)
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->ev_f0) cudaEventDestroy(h->ev_f0);
   for (cudaEvent_t e : h->copy_events) cudaEventDestroy(e);
   delete h;
 }
@@ -1143,8 +1148,18 @@ int mtp_synchronize(mtp_handle *h)
   return MTP_OK;
 }
 
+static double now_ms()
+{
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 int mtp_compute_host(mtp_handle *h, const mtp_compute_args *a, int list_changed)
 {
+  static const bool timing = getenv("MTP_B200_HOST_TIMING") != nullptr;
+  const double t_enter = now_ms();
+  double t_up = 0, t_launch = 0, t_sync = 0;
   if (!h || !a) return fail(MTP_ERR_ARG, "null argument");
   if (!a->x || !a->type || !a->numneigh || !a->neighbors || !a->f || !a->ev_out)
     return fail(MTP_ERR_ARG, "x, type, numneigh, neighbors, f and ev_out are required");
@@ -1154,31 +1169,57 @@ int mtp_compute_host(mtp_handle *h, const mtp_compute_args *a, int list_changed)
     cudaStream_t st = h->hstream;
     const size_t nall = (size_t) a->nall, inum = (size_t) a->inum;
     // id range covered by numneigh / offsets: every listed atom
+    const bool relist = list_changed || h->h_list_len == 0;
     size_t nid = inum;
-    if (a->ilist)
-      for (size_t k = 0; k < inum; k++) nid = std::max(nid, (size_t) a->ilist[k] + 1);
+    if (a->ilist) {
+      if (relist) {
+        for (size_t k = 0; k < inum; k++) nid = std::max(nid, (size_t) a->ilist[k] + 1);
+        h->h_nid = nid;
+      } else
+        nid = h->h_nid;
+    }
     mtp_compute_args d = *a;
+    if (!h->copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->ev_f0) CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_f0, cudaEventDisableTiming));
     h->h_x.upload(a->x, 3 * nall, st);
     h->h_type.upload(a->type, nall, st);
-    h->h_f.upload(a->f, 3 * nall, st);
+    // forces accumulate into the caller's f: the kernels add into a zeroed device array, the caller's values arrive
+    // on the copy stream while they run and are added at the end (keeps 24 B/atom of H2D off the critical path)
+    h->h_f.ensure(3 * nall);
+    h->h_f0.ensure(3 * nall);
+    CUDA_CHECK(cudaMemsetAsync(h->h_f.p, 0, sizeof(double) * 3 * nall, st));
     std::vector<cudaEvent_t> ready;
-    if (list_changed || h->h_list_len == 0) {
+    if (relist) {
       // one pass over the listed centres: extent of the list, max row length, and whether the CSR rows are laid out
       // in ilist order (then the list can be uploaded slice by slice, overlapped with the compute of earlier chunks)
       long long len = 0, prev_end = 0;
       int mx = 0;
       bool ordered = a->neigh_offsets != nullptr && a->stride_jj <= 1;
-      for (size_t k = 0; k < inum; k++) {
-        const size_t i = a->ilist ? (size_t) a->ilist[k] : k;
-        const int nn = a->numneigh[i];
-        mx = std::max(mx, nn);
-        if (a->neigh_offsets) {
-          const long long o = a->neigh_offsets[i];
-          len = std::max(len, o + (long long) nn * std::max(1LL, a->stride_jj));
-          if (o < prev_end) ordered = false;
+      if (a->neigh_offsets && a->stride_jj <= 1) {    // CSR: tight single pass
+        const int *il = a->ilist, *nnp = a->numneigh;
+        const long long *off = a->neigh_offsets;
+        int notordered = 0;
+        for (size_t k = 0; k < inum; k++) {
+          const size_t i = il ? (size_t) il[k] : k;
+          const int nn = nnp[i];
+          const long long o = off[i];
+          mx = nn > mx ? nn : mx;
+          notordered |= (o < prev_end);
           prev_end = o + nn;
-        } else
-          len = std::max(len, (long long) i * a->stride_i + (long long) nn * a->stride_jj + 1);
+          len = prev_end > len ? prev_end : len;
+        }
+        ordered = !notordered;
+      } else {
+        ordered = false;
+        for (size_t k = 0; k < inum; k++) {
+          const size_t i = a->ilist ? (size_t) a->ilist[k] : k;
+          const int nn = a->numneigh[i];
+          mx = std::max(mx, nn);
+          if (a->neigh_offsets)
+            len = std::max(len, a->neigh_offsets[i] + (long long) nn * std::max(1LL, a->stride_jj));
+          else
+            len = std::max(len, (long long) i * a->stride_i + (long long) nn * a->stride_jj + 1);
+        }
       }
       h->h_maxnn = mx;
       if (a->neigh_offsets) h->h_offsets.upload(a->neigh_offsets, nid, st);
@@ -1189,7 +1230,6 @@ int mtp_compute_host(mtp_handle *h, const mtp_compute_args *a, int list_changed)
       const int chunk = plan_chunk(h, a->inum, a->want_grade != 0);
       const int nsuper = a->inum > 0 ? (a->inum + chunk - 1) / chunk : 1;
       if (ordered && nsuper > 1 && !a->within_cutoff) {
-        if (!h->copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         while ((int) h->copy_events.size() < nsuper) {
           cudaEvent_t e;
           CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1208,6 +1248,8 @@ int mtp_compute_host(mtp_handle *h, const mtp_compute_args *a, int list_changed)
       } else if (len > 0)
         CUDA_CHECK(cudaMemcpyAsync(h->h_neigh.p, a->neighbors, sizeof(int) * (size_t) len, cudaMemcpyHostToDevice, st));
     }
+    if (3 * nall) CUDA_CHECK(cudaMemcpyAsync(h->h_f0.p, a->f, sizeof(double) * 3 * nall, cudaMemcpyHostToDevice, h->copy_stream));
+    CUDA_CHECK(cudaEventRecord(h->ev_f0, h->copy_stream));
     d.max_numneigh = h->h_maxnn;
     d.x = h->h_x.p;
     d.type = h->h_type.p;
@@ -1245,7 +1287,14 @@ int mtp_compute_host(mtp_handle *h, const mtp_compute_args *a, int list_changed)
       d.within_cutoff = h->h_within.p;
     }
     d.stream = st;
+    t_up = now_ms();
     launch_site(h, d, st, ready.empty() ? nullptr : &ready);
+    t_launch = now_ms();
+    CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_f0, 0));
+    if (nall) {
+      add_inplace_kernel<<<std::min<size_t>(4 * h->sm_count, (3 * nall + 255) / 256), 256, 0, st>>>(h->h_f.p, h->h_f0.p, 3 * nall);
+      g_launches++;
+    }
     CUDA_CHECK(cudaMemcpyAsync(a->f, d.f, sizeof(double) * 3 * nall, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(a->ev_out, d.ev_out, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
     if (d.eatom) CUDA_CHECK(cudaMemcpyAsync(a->eatom, d.eatom, sizeof(double) * nall, cudaMemcpyDeviceToHost, st));
@@ -1257,7 +1306,11 @@ int mtp_compute_host(mtp_handle *h, const mtp_compute_args *a, int list_changed)
     if (d.within_cutoff)
       CUDA_CHECK(cudaMemcpyAsync(a->within_cutoff, d.within_cutoff, (size_t) h->h_list_len, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
+    t_sync = now_ms();
   });
+  if (timing)
+    fprintf(stderr, "[mtp host] uploads enqueued %.3f ms, kernels enqueued %.3f ms, stream drained %.3f ms\n", t_up - t_enter,
+            t_launch - t_up, t_sync - t_launch);
   if (rc != MTP_OK) return rc;
   int status = 0;
   rc = guarded([&] {

@@ -759,6 +759,12 @@ __global__ void halo_unpack_add_f_kernel(double *__restrict__ f, const int *__re
   atomicAdd(&f[3 * (size_t) i + 2], buf[3 * (size_t) k + 2]);
 }
 
+// dst[k] += src[k]  (host path: the caller's incoming f joins the device result after the kernels)
+__global__ void add_inplace_kernel(double *__restrict__ dst, const double *__restrict__ src, size_t n)
+{
+  for (size_t k = blockIdx.x * (size_t) blockDim.x + threadIdx.x; k < n; k += (size_t) gridDim.x * blockDim.x) dst[k] += src[k];
+}
+
 // ---- FP64 roofs ---------------------------------------------------------------------------------------
 __global__ void dfma_peak_kernel(double *out, int iters, double a, double b)
 {
