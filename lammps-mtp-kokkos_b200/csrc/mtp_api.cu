@@ -270,17 +270,19 @@ bool build_v1_tables(mtp_handle *h, int e)
 typedef void (*V2GatherKernel)(DevPotential, SiteArgs, PairBuf);
 typedef void (*V2MomentsKernel)(SiteArgs, PairBuf, double *, int);
 typedef void (*V2ForcesKernel)(SiteArgs, PairBuf, const double *, int, double *);
-constexpr int kV2AB[4] = {64, 32, 16, 8};    // atoms per CTA of the force kernel
+// atoms per CTA of the force kernel: two buffers of canonical adjoints (2 x KF x AB x 8 B) stay below ~110 KB so that
+// two CTAs fit an SM; fixed per D0 at compile time so that only one variant per shape is instantiated
+constexpr int v2_ab_for(int kf) { return 2 * kf * 64 * 8 <= 110 * 1024 ? 64 : 2 * kf * 32 * 8 <= 110 * 1024 ? 32 : 2 * kf * 16 * 8 <= 110 * 1024 ? 16 : 8; }
 struct V2Entry {
-  int d0, R, KF, NP;
+  int d0, R, KF, NP, AB;
   V2GatherKernel radial;
   V2MomentsKernel moments;
-  V2ForcesKernel forces[2][4];    // [grade step][atoms-per-CTA choice]
+  V2ForcesKernel forces[2];    // [grade step]
 };
-#define V2_ENTRY(D)                                                                                          \
-  {D, V2Shape<D>::R, V2Shape<D>::KF, V2Shape<D>::NP, mtp_radial_kernel<V2Shape<D>::R>, mtp_moments_v2<D>,    \
-   {{mtp_forces_v2<D, 64, false>, mtp_forces_v2<D, 32, false>, mtp_forces_v2<D, 16, false>, mtp_forces_v2<D, 8, false>},   \
-    {mtp_forces_v2<D, 64, true>, mtp_forces_v2<D, 32, true>, mtp_forces_v2<D, 16, true>, mtp_forces_v2<D, 8, true>}}}
+#define V2_ENTRY(D)                                                                                                    \
+  {D, V2Shape<D>::R, V2Shape<D>::KF, V2Shape<D>::NP, v2_ab_for(V2Shape<D>::KF), mtp_radial_kernel<V2Shape<D>::R>,       \
+   mtp_moments_v2<D>,                                                                                                  \
+   {mtp_forces_v2<D, v2_ab_for(V2Shape<D>::KF), false>, mtp_forces_v2<D, v2_ab_for(V2Shape<D>::KF), true>}}
 const V2Entry kV2[] = {V2_ENTRY(0), V2_ENTRY(1), V2_ENTRY(2), V2_ENTRY(3), V2_ENTRY(4), V2_ENTRY(5),
                        V2_ENTRY(6), V2_ENTRY(7), V2_ENTRY(8), V2_ENTRY(9), V2_ENTRY(10)};
 constexpr int kV2Count = sizeof(kV2) / sizeof(kV2[0]);
@@ -443,8 +445,7 @@ void upload_potential(mtp_handle *h)
         CUDA_CHECK(cudaFuncSetAttribute((const void *) E.radial, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CUDA_CHECK(cudaFuncSetAttribute((const void *) E.moments, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         for (int gq = 0; gq < 2; gq++)
-          for (int q = 0; q < 4; q++)
-            CUDA_CHECK(cudaFuncSetAttribute((const void *) E.forces[gq][q], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          CUDA_CHECK(cudaFuncSetAttribute((const void *) E.forces[gq], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       }
       int per_sm = 0;
       CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) mtp_gather_kernel, 256, 0));
@@ -458,27 +459,18 @@ void upload_potential(mtp_handle *h)
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.moments, 32 * E.NP, h->v2_smem_m));
         h->v2_grid_m = std::max(1, per_sm) * h->sm_count;
       }
-      // forces: atoms per CTA so that two buffers of canonical adjoints stay below ~110 KB (two CTAs per SM)
-      h->v2_ab = -1;
-      for (int q = 0; q < 4 && ok; q++) {
-        const size_t need = (size_t) 2 * E.KF * kV2AB[q] * 8 + (size_t) 2 * (kV2AB[q] + 1) * 4;
-        if (need <= std::min<size_t>(110 * 1024, std::min(max_dynamic_smem((const void *) E.forces[0][q], smem_max),
-                                                           max_dynamic_smem((const void *) E.forces[1][q], smem_max)))) {
-          h->v2_ab = q;
-          h->v2_smem_f = need;
-          break;
-        }
+      // forces: atoms per CTA fixed per shape (v2_ab_for)
+      h->v2_ab = E.AB;
+      h->v2_smem_f = (size_t) 2 * E.KF * E.AB * 8 + (size_t) 2 * (E.AB + 1) * 4;
+      for (int gq = 0; gq < 2 && ok; gq++) {
+        const void *fk = (const void *) E.forces[gq];
+        ok = ok && h->v2_smem_f <= max_dynamic_smem(fk, smem_max);
+        if (!ok) break;
+        CUDA_CHECK(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->v2_smem_f));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk, 256, h->v2_smem_f));
+        h->v2_grid_fg[gq] = std::max(1, per_sm) * h->sm_count;
       }
-      ok = ok && h->v2_ab >= 0;
-      if (ok) {
-        for (int gq = 0; gq < 2; gq++) {
-          const void *fk = (const void *) E.forces[gq][h->v2_ab];
-          CUDA_CHECK(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->v2_smem_f));
-          CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk, 256, h->v2_smem_f));
-          h->v2_grid_fg[gq] = std::max(1, per_sm) * h->sm_count;
-        }
-        h->v2_grid_f = std::max(h->v2_grid_fg[0], h->v2_grid_fg[1]);
-      }
+      h->v2_grid_f = std::max(h->v2_grid_fg[0], h->v2_grid_fg[1]);
     }
     if (!ok) h->v2_entry = -1;
     if (const char *le = getenv("MTP_B200_LANES")) h->nlanes = std::max(1, std::min((int) mtp_handle::kMaxLanes, atoi(le)));
@@ -759,12 +751,12 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
           mtp_program_kernel<false><<<gp, PROG_THREADS, smem_p, ls>>>(d, s, L.mb.p, L.gb.p, ld, na, lna, part_p);
       }
       rows_used += gp;
-      const int ab = kV2AB[h->v2_ab];
+      const int ab = h->v2_ab;
       const int gf = std::max(1, std::min(h->v2_grid_fg[gi], (n + ab - 1) / ab));
       double *part_f = h->d_partials.p + (size_t) rows_used * 8;
       {
         ProfSpan sp(h, MTP_PROF_FORCES, ls);
-        E.forces[gi][h->v2_ab]<<<gf, 256, h->v2_smem_f, ls>>>(s, pb, L.gb.p, ld, part_f);
+        E.forces[gi]<<<gf, 256, h->v2_smem_f, ls>>>(s, pb, L.gb.p, ld, part_f);
         if (grade) {
           const size_t smem_c = (size_t) 8 * (CAND_TILE * (d.B + d.R) + CAND_TILE / 2) * 8;
           const int gc = std::max(1, std::min(4 * h->sm_count, (n + 7) / 8));
