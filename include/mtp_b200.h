@@ -186,6 +186,11 @@ int mtp_profile_read(mtp_handle *h, double *ms /*[MTP_PROF_CLASSES]*/, long long
 /* number of kernels launched by this library since load (bench.py's gpu_launches claim) */
 long long mtp_kernel_launch_count(void);
 
+/* Which kernels the last mtp_compute() of this handle launched (tests assert that the intended path ran):
+ * bits 0-3 kernel family (0 generic fused site kernel, 1 DMMA-moment pipeline, 2 register-resident pair kernels),
+ * bit 4 set when the contraction program ran in its 4-atoms-per-lane form, bits 8-15 atoms per CTA of that kernel. */
+int mtp_last_kernel_path(const mtp_handle *h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -131,6 +131,34 @@ struct FlatBufs {
   }
 };
 
+static_assert(G3_WARPS == P3_WARPS && G3_PAD_ROWS == P3_PAD_ROWS, "stream packer and program kernel disagree");
+struct Flat3Bufs {
+  DevBuf<int> rbegin, gbegin;
+  DevBuf<uint4> terms, heads;
+  DevFlat3Pass upload(const Flat3Pass &f)
+  {
+    rbegin.upload(f.row_begin, 0);
+    gbegin.upload(f.group_begin, 0);
+    terms.upload(f.terms, 0);
+    heads.upload(f.heads, 0);
+    DevFlat3Pass d;
+    d.row_begin = rbegin.p;
+    d.group_begin = gbegin.p;
+    d.terms = terms.p;
+    d.heads = heads.p;
+    d.nlevels = f.nlevels;
+    d.nterms = (int) f.terms.size();
+    d.nheads = (int) f.heads.size();
+    return d;
+  }
+};
+
+// 4-atoms-per-lane program kernel: [NA == 16][grade step][term streams in shared memory]
+typedef void (*P3Kernel)(DevPotential, SiteArgs, DevFlat3Pass, DevFlat3Pass, const double *, double *, int, double *);
+const P3Kernel kP3[2][2][2] = {
+    {{mtp_program_v3<32, false, false>, mtp_program_v3<32, false, true>}, {mtp_program_v3<32, true, false>, mtp_program_v3<32, true, true>}},
+    {{mtp_program_v3<16, false, false>, mtp_program_v3<16, false, true>}, {mtp_program_v3<16, true, false>, mtp_program_v3<16, true, true>}}};
+
 struct mtp_handle {
   Potential pot;
   Program prog;
@@ -145,6 +173,10 @@ struct mtp_handle {
   PassBufs d_fwd, d_rev;
   ChunkBufs d_cfwd, d_crev;
   FlatBufs d_ffwd[2], d_frev[2];
+  Flat3Bufs d_f3fwd, d_f3rev;
+  DevFlat3Pass f3f{}, f3r{};
+  int last_path = 0;              // mtp_last_kernel_path()
+  int p3_na = 0;                  // atoms per CTA of the 4-atoms-per-lane program kernel, 0 = not usable for this potential
   size_t prog_max = 0;
   int pl_na[2] = {0, 0};          // atoms per CTA of the program kernel: throughput shape, latency shape
   DevPotential dpot{};
@@ -340,7 +372,20 @@ void upload_potential(mtp_handle *h)
     h->pl_na[0] = std::max(2, h->pl_na_fit);
     if (const char *e = getenv("MTP_B200_PROG_NA")) h->pl_na[0] = std::max(2, std::min(h->pl_na[0], atoi(e)));
     h->pl_na[1] = std::min(h->pl_na[0], 8);
-    compile_program(p, h->prog, h->pl_na[0], h->pl_na[1]);
+    // 4-atoms-per-lane kernel: 32 or 16 atoms per CTA, whichever fits with both tables resident
+    int na_v3 = 0;
+    if (!getenv("MTP_B200_NO_PROG_V3"))
+      for (int na = 32; na >= 16 && !na_v3; na >>= 1)
+        if (program3_layout(p.alpha_moment_count, p.alpha_scalar_count, na, 2 * p.alpha_index_basic_count, 0, 0, 0, 0, false).total <= prog_max)
+          na_v3 = na;
+    compile_program(p, h->prog, h->pl_na[0], h->pl_na[1], na_v3);
+    h->p3_na = h->prog.f3_na;
+    for (int q = 0; q < 8; q++) {
+      const void *k = (const void *) kP3[q >> 2][(q >> 1) & 1][q & 1];
+      CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) prog_max));
+      if (!getenv("MTP_B200_NO_CARVEOUT"))
+        CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     CUDA_CHECK(cudaFuncSetAttribute((const void *) mtp_program_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) prog_max));
     CUDA_CHECK(cudaFuncSetAttribute((const void *) mtp_program_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) prog_max));
     // one shared-memory carve-out for every kernel of the pipeline: an SM cannot change its L1 / shared split while
@@ -405,6 +450,10 @@ void upload_potential(mtp_handle *h)
   for (int v = 0; v < 2; v++) {
     d.ffwd[v] = h->d_ffwd[v].upload(h->prog.ffwd[v]);
     d.frev[v] = h->d_frev[v].upload(h->prog.frev[v]);
+  }
+  if (h->p3_na) {
+    h->f3f = h->d_f3fwd.upload(h->prog.f3fwd);
+    h->f3r = h->d_f3rev.upload(h->prog.f3rev);
   }
   CUDA_CHECK(cudaDeviceSynchronize());
 
@@ -575,6 +624,29 @@ int plan_chunk(const mtp_handle *h, int inum, bool grade)
     long long fit = std::max(8192LL, (48LL << 20) / (16LL * h->dpot.K) / 1024 * 1024);
     if (use_v2) fit = h->v2_chunk > 0 ? h->v2_chunk : (1LL << 30);    // v2: the user's chunksize alone bounds the scratch
     chunk = (int) std::min<long long>(chunk, fit);
+    // wave quantisation: the pair kernels run persistent grids (moments: v2_grid_m CTAs x 32 atoms, forces:
+    // v2_grid_fg x AB, program: one CTA per SM x NA), so a super-chunk that is not a whole number of grid rounds of each
+    // leaves SMs idle in the last round of EVERY launch (32768 atoms at level 16: 2.3 rounds of the moment kernel
+    // cost 3).  Several super-chunks: round the size down to a common multiple of the three round sizes.
+    if (use_v2 && inum > chunk && !getenv("MTP_B200_NO_WAVE_CHUNK")) {
+      auto lcm = [](long long x, long long y) {
+        long long a = x, b = y;
+        while (b) {
+          const long long t = a % b;
+          a = b;
+          b = t;
+        }
+        return x / a * y;
+      };
+      const long long um = (long long) h->v2_grid_m * 32, uf = (long long) h->v2_grid_fg[grade ? 1 : 0] * h->v2_ab;
+      const long long up = (long long) h->sm_count * (h->p3_na ? h->p3_na : std::max(1, h->pl_na[0]));
+      long long unit = 0;
+      if (um > 0 && uf > 0) {
+        unit = lcm(um, uf);
+        if (unit <= chunk && lcm(unit, up) <= chunk) unit = lcm(unit, up);
+      }
+      if (unit > 0 && unit <= chunk) chunk = (int) (chunk / unit * unit);
+    }
   } else if (!grade) {
     chunk = inum > 0 ? inum : 1;
   }
@@ -678,6 +750,7 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
   // program kernel shape: atoms per CTA (power of two), smaller for small systems so that every SM gets work
   int na = 1, lna = 0, grid_p_cap = 1;
   size_t smem_p = 0;
+  P3Kernel p3 = nullptr;
   if (pipeline) {
     // throughput shape unless the system is too small to give every SM a chunk (or the latency variant is asked for)
     const int nfirst = std::min(chunk, std::max(a.inum, 1));
@@ -700,9 +773,25 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
     s.nslots = nslots;
     int per_sm = 0;
     const void *pk = grade ? (const void *) mtp_program_kernel<true> : (const void *) mtp_program_kernel<false>;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, PROG_THREADS, smem_p));
+    // throughput shape: the 4-atoms-per-lane kernel when the tables are expressible in its compact streams
+    if (!small && h->p3_na) {
+      auto l3 = [&](bool ds) {
+        return program3_layout(d.M, d.A, h->p3_na, nslots, h->f3f.nterms, h->f3r.nterms, h->f3f.nheads, h->f3r.nheads, ds,
+                               h->f3f.nlevels, h->f3r.nlevels).total;
+      };
+      if (l3(false) <= h->prog_max) {
+        bool ds = l3(true) <= h->prog_max;    // term streams from L1/L2 cost far more than a co-resident CTA of another lane gains
+        if (const char *e = getenv("MTP_B200_PROG_DSMEM")) ds = atoi(e) && l3(true) <= h->prog_max;
+        p3 = kP3[h->p3_na == 16][grade ? 1 : 0][ds ? 1 : 0];
+        na = h->p3_na;
+        smem_p = l3(ds);
+        pk = (const void *) p3;
+      }
+    }
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, p3 ? P3_THREADS : PROG_THREADS, smem_p));
     grid_p_cap = std::max(1, per_sm) * h->sm_count;
   }
+  h->last_path = (use_v2 ? 2 : pipeline ? 1 : 0) | (p3 ? 16 : 0) | (na << 8);
   const int rows_per_super = pipeline ? grid_p_cap + std::max(h->pl_grid_f[gi], h->v2_grid_f) : h->grid_cap[gi];
   h->d_partials.ensure((size_t) nsuper * rows_per_super * 8);
   int rows_used = 0;
@@ -746,7 +835,9 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
       double *part_p = h->d_partials.p + (size_t) rows_used * 8;
       {
         ProfSpan sp(h, MTP_PROF_PROGRAM, ls);
-        if (grade) mtp_program_kernel<true><<<gp, PROG_THREADS, smem_p, ls>>>(d, s, L.mb.p, L.gb.p, ld, na, lna, part_p);
+        if (p3) p3<<<gp, P3_THREADS, smem_p, ls>>>(d, s, h->f3f, h->f3r, L.mb.p, L.gb.p, ld, part_p);
+        else if (grade)
+          mtp_program_kernel<true><<<gp, PROG_THREADS, smem_p, ls>>>(d, s, L.mb.p, L.gb.p, ld, na, lna, part_p);
         else
           mtp_program_kernel<false><<<gp, PROG_THREADS, smem_p, ls>>>(d, s, L.mb.p, L.gb.p, ld, na, lna, part_p);
       }
@@ -781,7 +872,9 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
       double *part_p = h->d_partials.p + (size_t) rows_used * 8;
       {
         ProfSpan sp(h, MTP_PROF_PROGRAM, st);
-        if (grade) mtp_program_kernel<true><<<gp, PROG_THREADS, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, lna, part_p);
+        if (p3) p3<<<gp, P3_THREADS, smem_p, st>>>(d, s, h->f3f, h->f3r, h->d_mb.p, h->d_gb.p, ld, part_p);
+        else if (grade)
+          mtp_program_kernel<true><<<gp, PROG_THREADS, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, lna, part_p);
         else
           mtp_program_kernel<false><<<gp, PROG_THREADS, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, lna, part_p);
       }
@@ -899,6 +992,8 @@ extern "C" {
 const char *mtp_last_error(void) { return g_last_error.c_str(); }
 
 long long mtp_kernel_launch_count(void) { return g_launches.load(); }
+
+int mtp_last_kernel_path(const mtp_handle *h) { return h ? h->last_path : -1; }
 
 /* diagnostic builds only (-DMTP_PHASE_CLOCKS): per-phase SM clocks summed over warps, then reset */
 int mtp_debug_phase_clocks(unsigned long long *out8)

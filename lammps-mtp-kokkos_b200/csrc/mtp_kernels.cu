@@ -507,6 +507,7 @@ __global__ void finalize_ev_kernel(const double *partials, int nrows, double *ev
 }    // namespace mtpb200
 #include "mtp_kernels_v1.cuh"
 #include "mtp_kernels_v2.cuh"
+#include "mtp_program_v3.cuh"
 namespace mtpb200 {
 
 // max of numneigh over the listed centres (only when the caller does not know an upper bound)

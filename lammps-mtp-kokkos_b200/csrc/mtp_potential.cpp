@@ -385,7 +385,7 @@ void pack_pass(const std::vector<std::vector<NodeList>> &per_level, ProgramPass 
 
 }    // namespace
 
-void compile_program(const Potential &p, Program &prog, int na_large, int na_small)
+void compile_program(const Potential &p, Program &prog, int na_large, int na_small, int na_v3)
 {
   const int M = p.alpha_moment_count, T = p.alpha_index_times_count, A = p.alpha_scalar_count;
   const int *times = p.alpha_index_times.data();
@@ -566,6 +566,134 @@ void compile_program(const Potential &p, Program &prog, int na_large, int na_sma
   for (int v = 0; v < 2; v++) {
     pack_flat(fwd, false, v == 0 ? na_large : na_small, prog.ffwd[v]);
     pack_flat(rev, true, v == 0 ? na_large : na_small, prog.frev[v]);
+  }
+
+  // ---- grouped streams of the 4-atoms-per-lane kernel ----
+  struct Raw3 {
+    int a, b;
+    double coef;
+  };
+  auto pack_flat3 = [&](const std::vector<std::vector<NodeList>> &levels, bool reverse, int na, Flat3Pass &out) -> bool {
+    out = Flat3Pass();
+    const int vpw = 128 / na;
+    const uint32_t row_bytes = (uint32_t) na * 8;
+    const int SCRATCH = M + 1;
+    out.vpw = vpw;
+    out.na = na;
+    out.nlevels = (int) levels.size();
+    out.row_begin.push_back(0);
+    out.group_begin.push_back(0);
+    const Raw3 noop{ONE, ONE, 0.0};
+    auto emit_term = [&](const Raw3 &r) { out.terms.push_back(G3Term{(uint32_t) r.a * row_bytes, (uint32_t) r.b * row_bytes, r.coef}); };
+    struct Group {
+      std::vector<int> members;    // indices into per_node, -1 = dummy
+      int rows;
+      bool split;                  // one node, its terms dealt to all virtual warps
+    };
+    for (const auto &lv : levels) {
+      std::vector<std::vector<Raw3>> per_node;
+      for (const NodeList &l : lv) {
+        std::vector<Raw3> t;
+        if (!reverse) {
+          if (l.node < p.alpha_index_basic_count) t.push_back(Raw3{l.node, ONE, 1.0});
+          for (const ProgramTerm &q : l.terms) t.push_back(Raw3{q.a, q.b, (double) q.mult});
+        } else {
+          for (size_t qi = 0; qi < l.terms.size(); qi++) {
+            const ProgramTerm &q = l.terms[qi];
+            double mult = (double) q.mult;
+            if (qi + 1 < l.terms.size() && l.terms[qi + 1].a == q.a && l.terms[qi + 1].b == q.b &&
+                l.terms[qi + 1].mult == q.mult && q.b == (uint16_t) l.node) {
+              mult *= 2.0;    // self product: the same reverse term twice in a row (x + x == 2x)
+              qi++;
+            }
+            if (!is_source[q.a]) {
+              const double c = mult * prog.ginit[q.a];    // g[a3] stays ginit[a3]
+              if (c == 0.0) continue;
+              t.push_back(Raw3{ONE, q.b, c});
+            } else
+              t.push_back(Raw3{q.a, q.b, mult});
+          }
+        }
+        per_node.push_back(std::move(t));
+      }
+      // long lists are split over the virtual warps of a group (partial sums combined by shuffles), the others are
+      // grouped vpw at a time in order of length so that the common row count wastes little
+      std::vector<int> order;
+      std::vector<Group> groups;
+      for (size_t i = 0; i < per_node.size(); i++) {
+        if ((int) per_node[i].size() > G3_SPLIT_ABOVE) {
+          Group g;
+          g.members.assign(vpw, (int) i);
+          g.rows = ((int) per_node[i].size() + vpw - 1) / vpw;
+          g.split = true;
+          groups.push_back(std::move(g));
+        } else
+          order.push_back((int) i);
+      }
+      std::stable_sort(order.begin(), order.end(),
+                       [&](int x, int y) { return per_node[x].size() > per_node[y].size(); });
+      for (size_t i = 0; i < order.size(); i += vpw) {
+        Group g;
+        size_t mx = 0;
+        for (int v = 0; v < vpw; v++) {
+          const int idx = i + v < order.size() ? order[i + v] : -1;
+          g.members.push_back(idx);
+          if (idx >= 0) mx = std::max(mx, per_node[idx].size());
+        }
+        g.rows = std::max<int>(1, (int) mx);
+        g.split = false;
+        groups.push_back(std::move(g));
+      }
+      // longest group first onto the least loaded warp (cost: rows + the end-of-group work)
+      std::vector<int> gorder(groups.size());
+      for (size_t i = 0; i < gorder.size(); i++) gorder[i] = (int) i;
+      std::stable_sort(gorder.begin(), gorder.end(), [&](int x, int y) { return groups[x].rows > groups[y].rows; });
+      std::vector<std::vector<int>> bins(G3_WARPS);
+      std::vector<int> load(G3_WARPS, 0);
+      for (int gi : gorder) {
+        int best = 0;
+        for (int b = 1; b < G3_WARPS; b++)
+          if (load[b] < load[best]) best = b;
+        bins[best].push_back(gi);
+        load[best] += groups[gi].rows + 1;
+      }
+      for (int b = 0; b < G3_WARPS; b++) {
+        int rows = 0;
+        auto emit_group = [&](const Group &g) {
+          for (int v = 0; v < vpw; v++) {
+            const int idx = g.members[v];
+            const int node = idx >= 0 ? lv[idx].node : SCRATCH;
+            const bool seeded = reverse && idx >= 0 && (!g.split || v == 0);
+            out.heads.push_back(G3Head{(uint32_t) node * row_bytes, (uint32_t) g.rows | (g.split ? 0x80000000u : 0u),
+                                       seeded ? prog.ginit[node] : 0.0});
+          }
+          for (int r = 0; r < g.rows; r++)
+            for (int v = 0; v < vpw; v++) {
+              const int idx = g.members[v];
+              const int q = g.split ? r * vpw + v : r;    // split: terms dealt round-robin to the virtual warps
+              emit_term(idx >= 0 && q < (int) per_node[idx].size() ? per_node[idx][q] : noop);
+            }
+          rows += g.rows;
+        };
+        for (int gi : bins[b]) emit_group(groups[gi]);
+        if (rows % 4) {    // whole 4-row trips
+          Group g;
+          g.members.assign(vpw, -1);
+          g.rows = 4 - rows % 4;
+          g.split = false;
+          emit_group(g);
+        }
+        out.row_begin.push_back((int) out.terms.size() / vpw);
+        out.group_begin.push_back((int) out.heads.size() / vpw);
+      }
+    }
+    for (int i = 0; i < G3_PAD_ROWS * vpw; i++) emit_term(noop);
+    for (int i = 0; i < 2 * vpw; i++) out.heads.push_back(G3Head{(uint32_t) SCRATCH * row_bytes, 1u << 30, 0.0});
+    return true;
+  };
+  prog.f3_na = 0;
+  if (na_v3 == 32 || na_v3 == 16) {
+    if (pack_flat3(fwd, false, na_v3, prog.f3fwd) && pack_flat3(rev, true, na_v3, prog.f3rev)) prog.f3_na = na_v3;
   }
 }
 

@@ -98,16 +98,47 @@ struct FlatPass {
   std::vector<uint32_t> st;         // per term: byte offset of the destination row | 1 if the term ends its node
 };
 
+// Streams of the 4-atoms-per-lane program kernel (mtp_program_v3.cuh).  A "virtual warp" (NA/4 lanes) evaluates one
+// node at a time; the VPW = 128/NA virtual warps of a physical warp work on a GROUP of VPW nodes of the same dependency
+// level whose term lists were padded to one common length, so the end of a node is a warp-uniform event (no
+// predication, no flags); a list longer than G3_SPLIT_ABOVE terms forms a group of its own, its terms dealt to all
+// the virtual warps and the partial sums combined by shuffles (head.rows bit 31).  Per (level, physical warp) the stream is a flat sequence of term rows ([VPW] descriptors of
+// 16 bytes, one per virtual warp) and a sequence of group heads ([VPW] x {destination, rows of the group, initial
+// value}); every stream is a whole number of 4-row trips (a dummy group writing to the scratch row M+1 is appended
+// otherwise) and the arrays end with padding rows / heads because the kernel prefetches ahead.
+// Row M of both tables holds 1.0 (no-op terms: a = b = M, coef = 0), row M+1 is scratch.
+struct G3Term {
+  uint32_t a_off, b_off;    // byte offsets of the operand rows: row * NA * 8
+  double coef;
+};
+struct G3Head {
+  uint32_t dst_off, rows;
+  double init;
+};
+static_assert(sizeof(G3Term) == 16 && sizeof(G3Head) == 16, "G3 packing");
+constexpr int G3_WARPS = 8;        // physical warps per CTA of the kernel
+constexpr int G3_SPLIT_ABOVE = 8;
+constexpr int G3_PAD_ROWS = 8;     // rows readable past the end of the term array
+struct Flat3Pass {
+  int vpw = 0, nlevels = 0, na = 0;
+  std::vector<int> row_begin;      // [nlevels * G3_WARPS + 1] term-row ranges
+  std::vector<int> group_begin;    // [nlevels * G3_WARPS + 1] group ranges
+  std::vector<G3Term> terms;       // [rows + G3_PAD_ROWS][vpw]
+  std::vector<G3Head> heads;       // [groups + 2][vpw]
+};
+
 struct Program {
   int depth = 0;                  // number of waves
   ChunkPass cfwd, crev;
   FlatPass ffwd[2], frev[2];      // for the two atoms-per-CTA shapes of the program kernel (vw = 16 * 32 / NA)
+  int f3_na = 0;                  // atoms per CTA of the v3 streams (32 / 16), 0 = tables not expressible
+  Flat3Pass f3fwd, f3rev;
   std::vector<int> level;         // [M]
   ProgramPass fwd, rev;
   std::vector<double> ginit;      // [M]: dE/dm seed, g[map[s]] = xi_s (pair_mtp.cpp:217-218)
 };
 
 // Throws std::runtime_error if the table is not a topologically ordered program.
-void compile_program(const Potential &p, Program &out, int na_large = 32, int na_small = 8);
+void compile_program(const Potential &p, Program &out, int na_large = 32, int na_small = 8, int na_v3 = 0);
 
 }    // namespace mtpb200

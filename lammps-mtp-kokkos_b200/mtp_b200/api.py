@@ -54,7 +54,7 @@ class MTPComputeArgs(C.Structure):
 
 EXPORTS = ["mtp_create_from_file", "mtp_create", "mtp_destroy", "mtp_last_error", "mtp_get_info",
            "mtp_get_tables", "mtp_set_chunksize", "mtp_compute", "mtp_synchronize", "mtp_compute_host",
-           "mtp_halo_pack_x", "mtp_halo_unpack_add_f", "mtp_fp64_peak", "mtp_kernel_launch_count"]
+           "mtp_halo_pack_x", "mtp_halo_unpack_add_f", "mtp_fp64_peak", "mtp_kernel_launch_count", "mtp_last_kernel_path"]
 
 _lib = None
 
@@ -89,6 +89,7 @@ def load_library():
     lib.mtp_profile_read.argtypes = [C.c_void_p, _dp, _llp]
     lib.mtp_fp64_peak.argtypes = [C.c_int, _dp, _dp]
     lib.mtp_kernel_launch_count.restype = C.c_longlong
+    lib.mtp_last_kernel_path.argtypes = [C.c_void_p]
     _lib = lib
     return lib
 
@@ -244,6 +245,11 @@ class MTPB200:
         cnt = (C.c_longlong * 8)()
         _check(self.lib, self.lib.mtp_profile_read(self.h, ms, cnt))
         return {n: (ms[i], cnt[i]) for i, n in enumerate(self.PROF_CLASSES)}
+
+    def last_kernel_path(self) -> dict:
+        """Which kernels the last compute launched (mtp_last_kernel_path)."""
+        v = int(self.lib.mtp_last_kernel_path(self.h))
+        return {"family": v & 15, "program_v3": bool(v & 16), "program_atoms_per_cta": (v >> 8) & 255}
 
     def synchronize(self):
         _check(self.lib, self.lib.mtp_synchronize(self.h))

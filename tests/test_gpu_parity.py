@@ -139,3 +139,48 @@ def test_fp64_roofs_are_measurable(built):
     dfma, dmma = fp64_peaks()
     print("FP64 roofs TFLOP/s: DFMA", dfma, "DMMA", dmma)
     assert dfma > 5.0 and dmma > 0.5
+
+
+# systems large enough that every SM gets a chunk, so the throughput shape of the contraction program (the
+# 4-atoms-per-lane kernel, 32 or 16 atoms per CTA) is the one that runs; ilist subsets give ragged tail chunks
+@pytest.mark.parametrize("level,species,kind,a,cells,atoms_per_cta", [
+    (16, 2, "bcc", 3.165, (14, 14, 14), 32),     # config 2 shape
+    (12, 3, "fcc", 3.56, (11, 11, 11), 32),
+    (18, 1, "fcc", 4.05, (9, 9, 9), 16),
+])
+def test_program_kernel_throughput_shape(tmp_path, built, level, species, kind, a, cells, atoms_per_cta):
+    from mtp_b200.api import MTPB200
+    from oracle_py import OracleMTP
+    path, pot = util.write_potential(tmp_path, level, species)
+    sysm = util.small_system(kind, a, cells, species, seed=5)
+    orc = OracleMTP(pot)
+    mtp = MTPB200(path)
+    for lanes in (1, 2):
+        mtp.set_lanes(lanes)
+        mtp.set_chunksize(1 << 30 if lanes == 1 else 2500)
+        ilist = sysm.ilist if lanes == 1 else sysm.ilist[: sysm.nlocal - 13]
+        ref = orc.compute(sysm.x, sysm.type, ilist, sysm.numneigh, sysm.neigh, sysm.offsets)
+        gpu = mtp.compute_host(sysm.x, sysm.type, ilist, sysm.numneigh, sysm.neigh, sysm.offsets)
+        if lanes == 1:
+            path_used = mtp.last_kernel_path()
+            assert path_used["program_v3"] and path_used["program_atoms_per_cta"] == atoms_per_cta, path_used
+        assert abs(gpu.energy - ref.energy) <= TOL_E_REL * abs(ref.energy)
+        assert maxabsrel(gpu.f, ref.f) <= TOL_F_MAXABSREL
+        assert maxabsrel(gpu.virial, ref.virial) <= TOL_AUX
+        assert maxabsrel(gpu.eatom[ilist], ref.eatom[ilist]) <= TOL_AUX
+    mtp.close()
+
+
+def test_program_kernel_throughput_shape_grades(tmp_path, built):
+    from mtp_b200.api import MTPB200
+    from oracle_py import OracleMTP
+    path, pot = util.write_potential(tmp_path, 16, 2, active_set=True)
+    sysm = util.small_system("fcc", 4.05, (11, 11, 11), 2, seed=11)
+    ref = OracleMTP(pot).compute(sysm.x, sysm.type, sysm.ilist, sysm.numneigh, sysm.neigh, sysm.offsets, grade=True)
+    mtp = MTPB200(path, selection_state=True)
+    gpu = mtp.compute_system(sysm, grade=True)
+    assert mtp.last_kernel_path()["program_v3"]
+    _check(gpu, ref, sysm)
+    assert maxabsrel(gpu.grades[: sysm.nlocal], ref.grades[: sysm.nlocal]) <= TOL_AUX
+    assert abs(gpu.max_grade - ref.max_grade) <= TOL_AUX * ref.max_grade
+    mtp.close()
