@@ -37,6 +37,7 @@ extern "C" {
 #define MTP_ERR_SPECIES (-4)  /* "Too few species count in the MTP potential!" (pair_mtp.cpp:91-93) */
 #define MTP_ERR_MODE (-5)     /* request incompatible with the potential's selection mode */
 #define MTP_ERR_TABLE (-6)    /* alpha_index_times is not a topologically ordered program */
+#define MTP_ERR_CAPACITY (-7) /* mtp_neigh_build: a row needs more than `width` entries (see max_numneigh_out) */
 
 /* pair_style variants (README.md:36-40 of the reference) */
 #define MTP_VARIANT_LARGE 0   /* mtp/kk, mtp/extrapolation/kk              : throughput path */
@@ -164,6 +165,20 @@ int mtp_halo_pack_x_multi(const double *x, const int *sendlist, const unsigned c
 /* reverse: f[sendlist[k]][:] += buf[k][:]             (Comm::reverse_comm unpack, newton on) */
 int mtp_halo_unpack_add_f(double *f, const int *sendlist, int n, const double *buf, void *stream);
 
+/* ---- device neighbor-list build (the step before the path) ---------------------- */
+/* FULL neighbor list as the pair style requests it (pair_mtp.cpp:318 NeighConst::REQ_FULL; consumed through
+ * list->ilist / numneigh / firstneigh, pair_mtp.cpp:77-85, or the 2-D d_neighbors view, pair_mtp_kokkos.cpp:236-240):
+ * for every owned atom i < nlocal all atoms j != i, owned or ghost (j < nall), with |x_j - x_i|^2 <= cutneigh^2,
+ * cutneigh = cutoff + skin.  rsq is rounded exactly as the CPU builds round it, so the neighbor SET of every atom is
+ * bit-identical to a host-built list; the order within a row is deterministic (stencil order).
+ * x: DEVICE [nall][3].  Outputs (DEVICE): numneigh[nlocal] = true count of every row, neighbors = row-major table
+ * [nlocal][width]; hand it to mtp_compute with neighbors / neigh_offsets = NULL / stride_i = width / stride_jj = 1.
+ * max_numneigh_out (HOST, optional) receives the longest row.  Returns MTP_ERR_CAPACITY when that exceeds width
+ * (rows are truncated; numneigh and *max_numneigh_out are valid): rebuild with a wider table, as LAMMPS-KOKKOS does.
+ * Blocks until the list is complete (two small device -> host reads: bounding box, longest row). */
+int mtp_neigh_build(mtp_handle *h, int nlocal, int nall, const double *x, double cutneigh, int *numneigh, int *neighbors,
+                    int width, int *max_numneigh_out, void *stream);
+
 /* ---- measured roofs ----------------------------------------------------------------------------- */
 /* FP64 vector (DFMA) and FP64 tensor (mma.sync.m8n8k4.f64, DMMA) peak of the device, in TFLOP/s. */
 int mtp_fp64_peak(int device, double *dfma_tflops, double *dmma_tflops);
@@ -185,6 +200,11 @@ int mtp_profile_read(mtp_handle *h, double *ms /*[MTP_PROF_CLASSES]*/, long long
 
 /* number of kernels launched by this library since load (bench.py's gpu_launches claim) */
 long long mtp_kernel_launch_count(void);
+
+/* Host-only self-check of the contraction-program stream packer: parses the potential, builds the grouped term
+ * streams for `atoms_per_cta` (32 or 16) and interprets them on the CPU against the sequential program
+ * (pair_mtp.cpp:196-233).  *max_rel_err_out receives the largest relative deviation (moments and adjoints). */
+int mtp_program_check(const char *path, int atoms_per_cta, double *max_rel_err_out);
 
 /* Which kernels the last mtp_compute() of this handle launched (tests assert that the intended path ran):
  * bits 0-3 kernel family (0 generic fused site kernel, 1 DMMA-moment pipeline, 2 register-resident pair kernels),

@@ -2,6 +2,7 @@
 #include "../../include/mtp_b200.h"
 #include "mtp_kernels.cu"
 #include "mtp_potential.hpp"
+#include "mtp_neigh.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -176,6 +177,11 @@ struct mtp_handle {
   Flat3Bufs d_f3fwd, d_f3rev;
   DevFlat3Pass f3f{}, f3r{};
   int last_path = 0;              // mtp_last_kernel_path()
+  // mtp_neigh_build scratch
+  DevBuf<double> nb_part, nb_bounds;
+  DevBuf<int> nb_keys, nb_idx, nb_skeys, nb_sidx, nb_cell, nb_max;
+  DevBuf<AtomRec> nb_xs;
+  DevBuf<unsigned char> nb_tmp;
   int p3_na = 0;                  // atoms per CTA of the 4-atoms-per-lane program kernel, 0 = not usable for this potential
   size_t prog_max = 0;
   int pl_na[2] = {0, 0};          // atoms per CTA of the program kernel: throughput shape, latency shape
@@ -993,6 +999,19 @@ const char *mtp_last_error(void) { return g_last_error.c_str(); }
 
 long long mtp_kernel_launch_count(void) { return g_launches.load(); }
 
+int mtp_program_check(const char *path, int atoms_per_cta, double *max_rel_err_out)
+{
+  if (!path || !max_rel_err_out) return fail(MTP_ERR_ARG, "null argument");
+  if (atoms_per_cta != 32 && atoms_per_cta != 16) return fail(MTP_ERR_ARG, "atoms_per_cta must be 32 or 16");
+  return guarded([&] {
+    Potential p;
+    Program prog;
+    parse_almtp(path, false, p);
+    compile_program(p, prog, 32, 8, atoms_per_cta);
+    *max_rel_err_out = check_grouped_streams(p, prog);
+  });
+}
+
 int mtp_last_kernel_path(const mtp_handle *h) { return h ? h->last_path : -1; }
 
 /* diagnostic builds only (-DMTP_PHASE_CLOCKS): per-phase SM clocks summed over warps, then reset */
@@ -1406,6 +1425,85 @@ int mtp_compute_host(mtp_handle *h, const mtp_compute_args *a, int list_changed)
   });
   if (rc != MTP_OK) return rc;
   if (status & 1) return fail(MTP_ERR_SPECIES, "Too few species count in the MTP potential!");
+  return MTP_OK;
+}
+
+int mtp_neigh_build(mtp_handle *h, int nlocal, int nall, const double *x, double cutneigh, int *numneigh, int *neighbors,
+                    int width, int *max_numneigh_out, void *stream)
+{
+  if (!h) return fail(MTP_ERR_ARG, "null handle");
+  if (nlocal < 0 || nall < nlocal || width < 1 || !(cutneigh > 0.0)) return fail(MTP_ERR_ARG, "bad neighbor-build arguments");
+  if (nlocal > 0 && (!x || !numneigh || !neighbors)) return fail(MTP_ERR_ARG, "null neighbor-build buffer");
+  if (max_numneigh_out) *max_numneigh_out = 0;
+  if (nlocal == 0) return MTP_OK;
+  int maxnn = 0;
+  const int rc = guarded([&] {
+    CUDA_CHECK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    // bounding box of owned + ghost atoms
+    const int nbb = std::max(1, std::min(4 * h->sm_count, (nall + 255) / 256));
+    h->nb_part.ensure((size_t) nbb * 6);
+    h->nb_bounds.ensure(6);
+    neigh_bounds_kernel<<<nbb, 256, 0, st>>>(nall, x, h->nb_part.p);
+    neigh_bounds_final_kernel<<<1, 32, 0, st>>>(nbb, h->nb_part.p, h->nb_bounds.p);
+    double bb[6];
+    CUDA_CHECK(cudaMemcpyAsync(bb, h->nb_bounds.p, sizeof(bb), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    // bins no smaller than cutneigh (27-bin stencil), and no more bins than a few per atom
+    NeighGrid g;
+    long long ncell = 1;
+    for (int a = 0; a < 3; a++) {
+      const double ext = std::max(bb[3 + a] - bb[a], 0.0);
+      long long n = (long long) std::floor(ext / cutneigh);
+      if (n > 1 && ext / (double) n < cutneigh * (1.0 + 1e-9)) n--;
+      n = std::max(1LL, std::min(n, 1LL << 20));
+      g.n[a] = (int) n;
+      ncell *= n;
+    }
+    const long long cell_cap = std::max(4096LL, 4LL * nall);
+    while (ncell > cell_cap) {    // sparse systems: coarsen the longest axis
+      int a = g.n[0] >= g.n[1] && g.n[0] >= g.n[2] ? 0 : (g.n[1] >= g.n[2] ? 1 : 2);
+      ncell /= g.n[a];
+      g.n[a] = (g.n[a] + 1) / 2;
+      ncell *= g.n[a];
+    }
+    for (int a = 0; a < 3; a++) {
+      const double ext = std::max(bb[3 + a] - bb[a], 0.0);
+      g.lo[a] = bb[a];
+      g.inv[a] = ext > 0.0 ? (double) g.n[a] / ext : 0.0;
+    }
+    h->nb_keys.ensure(nall);
+    h->nb_idx.ensure(nall);
+    h->nb_skeys.ensure(nall);
+    h->nb_sidx.ensure(nall);
+    h->nb_cell.ensure((size_t) ncell + 1);
+    h->nb_xs.ensure(nall);
+    h->nb_max.ensure(1);
+    neigh_bin_kernel<<<(nall + 255) / 256, 256, 0, st>>>(nall, x, g, h->nb_keys.p, h->nb_idx.p);
+    int end_bit = 1;
+    while ((1LL << end_bit) < ncell && end_bit < 31) end_bit++;
+    size_t tmp_bytes = 0;
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->nb_keys.p, h->nb_skeys.p, h->nb_idx.p, h->nb_sidx.p, nall, 0,
+                                               end_bit, st));
+    h->nb_tmp.ensure(tmp_bytes);
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->nb_tmp.p, tmp_bytes, h->nb_keys.p, h->nb_skeys.p, h->nb_idx.p, h->nb_sidx.p, nall,
+                                               0, end_bit, st));
+    neigh_cellstart_kernel<<<(int) ((ncell + 1 + 255) / 256), 256, 0, st>>>(nall, h->nb_skeys.p, (int) ncell, h->nb_cell.p);
+    neigh_gather_sorted_kernel<<<(nall + 255) / 256, 256, 0, st>>>(nall, x, h->nb_sidx.p, h->nb_xs.p);
+    CUDA_CHECK(cudaMemsetAsync(h->nb_max.p, 0, sizeof(int), st));
+    const int gb = std::max(1, std::min(16 * h->sm_count, (nlocal + 7) / 8));
+    neigh_build_kernel<<<gb, 256, 0, st>>>(nlocal, x, g, h->nb_cell.p, h->nb_xs.p, cutneigh * cutneigh, width, numneigh, neighbors,
+                                           h->nb_max.p);
+    g_launches += 7;
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(&maxnn, h->nb_max.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+  if (rc != MTP_OK) return rc;
+  if (max_numneigh_out) *max_numneigh_out = maxnn;
+  if (maxnn > width)
+    return fail(MTP_ERR_CAPACITY, "neighbor table too narrow: the longest row has " + std::to_string(maxnn) + " entries, width is " +
+                                      std::to_string(width));
   return MTP_OK;
 }
 

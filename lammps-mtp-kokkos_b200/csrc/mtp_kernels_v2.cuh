@@ -106,7 +106,10 @@ template <int D0> struct V2Shape {
 };
 
 constexpr int V2_PEND = 64;
-constexpr int V2_NT = 16;      // pairs per staged tile of the moment kernel
+#ifndef MTP_V2_NT
+#define MTP_V2_NT 16
+#endif
+constexpr int V2_NT = MTP_V2_NT;      // pairs per staged tile of the moment kernel (power of two)
 
 
 // ===================================================================================================== gather

@@ -7,6 +7,7 @@
 #include "mtp_potential.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -695,6 +696,78 @@ void compile_program(const Potential &p, Program &prog, int na_large, int na_sma
   if (na_v3 == 32 || na_v3 == 16) {
     if (pack_flat3(fwd, false, na_v3, prog.f3fwd) && pack_flat3(rev, true, na_v3, prog.f3rev)) prog.f3_na = na_v3;
   }
+}
+
+double check_grouped_streams(const Potential &p, const Program &prog)
+{
+  if (!prog.f3_na) throw std::runtime_error("the grouped streams were not built for this potential");
+  const int M = p.alpha_moment_count, K = p.alpha_index_basic_count, T = p.alpha_index_times_count;
+  const int *times = p.alpha_index_times.data();
+  // sequential reference
+  std::vector<double> m(M, 0.0), g(M, 0.0);
+  uint64_t lcg = 0x9E3779B97F4A7C15ull;
+  for (int k = 0; k < K; k++) {
+    lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+    m[k] = ((double) (lcg >> 11) / 9007199254740992.0 - 0.5) * 1.5;
+  }
+  for (int e = 0; e < T; e++) m[times[4 * e + 3]] += times[4 * e + 2] * m[times[4 * e]] * m[times[4 * e + 1]];
+  for (int n = 0; n < M; n++) g[n] = prog.ginit[n];
+  for (int e = T - 1; e >= 0; e--) {
+    const int a0 = times[4 * e], a1 = times[4 * e + 1], a3 = times[4 * e + 3];
+    const double mult = times[4 * e + 2];
+    g[a1] += g[a3] * mult * m[a0];
+    g[a0] += g[a3] * mult * m[a1];
+  }
+  // the streams
+  const int na = prog.f3_na;
+  const uint32_t row_bytes = (uint32_t) na * 8;
+  std::vector<double> cm(M + 2, 0.0), cg(M + 2, 0.0);
+  for (int k = 0; k < K; k++) cm[k] = m[k];
+  cm[M] = cg[M] = 1.0;
+  auto run = [&](const Flat3Pass &f, std::vector<double> &A, const std::vector<double> &B) {
+    const int vpw = f.vpw;
+    for (int lv = 0; lv < f.nlevels; lv++) {
+      std::vector<std::pair<int, double>> stores;
+      for (int w = 0; w < G3_WARPS; w++) {
+        const int sidx = lv * G3_WARPS + w;
+        int row = f.row_begin[sidx];
+        if ((f.row_begin[sidx + 1] - row) % 4) throw std::runtime_error("stream is not a whole number of 4-row trips");
+        for (int gi = f.group_begin[sidx]; gi < f.group_begin[sidx + 1]; gi++) {
+          const G3Head *hd = &f.heads[(size_t) gi * vpw];
+          const int rows = (int) (hd[0].rows & 0x7FFFFFFFu);
+          const bool split = (hd[0].rows >> 31) != 0;
+          std::vector<double> acc(vpw);
+          for (int v = 0; v < vpw; v++) {
+            if (hd[v].rows != hd[0].rows) throw std::runtime_error("group heads disagree");
+            acc[v] = hd[v].init;
+            for (int r = 0; r < rows; r++) {
+              const G3Term &t = f.terms[(size_t) (row + r) * vpw + v];
+              if (t.a_off % row_bytes || t.b_off % row_bytes) throw std::runtime_error("operand offset is not a row");
+              acc[v] += t.coef * A[t.a_off / row_bytes] * B[t.b_off / row_bytes];
+            }
+          }
+          if (split) {
+            double sum = 0.0;
+            for (int v = 0; v < vpw; v++) sum += acc[v];
+            stores.push_back({(int) (hd[0].dst_off / row_bytes), sum});
+          } else
+            for (int v = 0; v < vpw; v++) stores.push_back({(int) (hd[v].dst_off / row_bytes), acc[v]});
+          row += rows;
+        }
+        if (row != f.row_begin[sidx + 1]) throw std::runtime_error("group rows do not add up to the stream length");
+      }
+      for (auto &st : stores)
+        if (st.first != M + 1) A[st.first] = st.second;    // row M + 1 is scratch
+    }
+  };
+  run(prog.f3fwd, cm, cm);
+  run(prog.f3rev, cg, cm);
+  double err = 0.0, scale_m = 1e-300, scale_g = 1e-300;
+  for (int n = 0; n < M; n++) scale_m = std::max(scale_m, std::fabs(m[n]));
+  for (int k = 0; k < K; k++) scale_g = std::max(scale_g, std::fabs(g[k]));
+  for (int n = 0; n < M; n++) err = std::max(err, std::fabs(cm[n] - m[n]) / scale_m);
+  for (int k = 0; k < K; k++) err = std::max(err, std::fabs(cg[k] - g[k]) / scale_g);
+  return err;
 }
 
 }    // namespace mtpb200

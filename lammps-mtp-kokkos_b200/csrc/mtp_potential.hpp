@@ -141,4 +141,10 @@ struct Program {
 // Throws std::runtime_error if the table is not a topologically ordered program.
 void compile_program(const Potential &p, Program &out, int na_large = 32, int na_small = 8, int na_v3 = 0);
 
+// Host interpreter of the grouped streams (Flat3Pass) for one atom with pseudo-random basic moments: runs the forward
+// and reverse passes exactly as the kernel schedules them (stores of a level become visible at its barrier) and returns
+// the largest relative deviation of all moments and basic-moment adjoints from the sequential program
+// (pair_mtp.cpp:196-233).  Test infrastructure for the stream packer; no device involved.
+double check_grouped_streams(const Potential &p, const Program &prog);
+
 }    // namespace mtpb200

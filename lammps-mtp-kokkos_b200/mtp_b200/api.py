@@ -54,7 +54,7 @@ class MTPComputeArgs(C.Structure):
 
 EXPORTS = ["mtp_create_from_file", "mtp_create", "mtp_destroy", "mtp_last_error", "mtp_get_info",
            "mtp_get_tables", "mtp_set_chunksize", "mtp_compute", "mtp_synchronize", "mtp_compute_host",
-           "mtp_halo_pack_x", "mtp_halo_unpack_add_f", "mtp_fp64_peak", "mtp_kernel_launch_count", "mtp_last_kernel_path"]
+           "mtp_halo_pack_x", "mtp_halo_unpack_add_f", "mtp_fp64_peak", "mtp_kernel_launch_count", "mtp_last_kernel_path", "mtp_neigh_build", "mtp_program_check"]
 
 _lib = None
 
@@ -90,6 +90,8 @@ def load_library():
     lib.mtp_fp64_peak.argtypes = [C.c_int, _dp, _dp]
     lib.mtp_kernel_launch_count.restype = C.c_longlong
     lib.mtp_last_kernel_path.argtypes = [C.c_void_p]
+    lib.mtp_neigh_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.POINTER(C.c_int), C.c_void_p]
     _lib = lib
     return lib
 
@@ -234,6 +236,30 @@ class MTPB200:
         a.max_numneigh = int(max_numneigh)
         _check(self.lib, self.lib.mtp_compute(self.h, C.byref(a)))
 
+    ERR_CAPACITY = -7
+
+    def neigh_build(self, x, nlocal: int, cutneigh: float, width: int | None = None, stream=None):
+        """Device build of the full neighbor list (mtp_neigh_build).  x: CUDA float64 tensor [nall, 3].
+        Returns (numneigh int32 [nlocal], table int32 [nlocal, width], longest row); pass the table to
+        compute_device(neigh=table, offsets=None, stride_i=width, stride_jj=1).  The table is rebuilt wider when a
+        row does not fit (LAMMPS-KOKKOS's resize-and-retry)."""
+        import torch
+        nall = int(x.shape[0])
+        if width is None:
+            width = getattr(self, "_neigh_width", 128)
+        numneigh = torch.empty(max(nlocal, 1), dtype=torch.int32, device=x.device)
+        while True:
+            table = torch.empty((max(nlocal, 1), width), dtype=torch.int32, device=x.device)
+            mx = C.c_int(0)
+            rc = self.lib.mtp_neigh_build(self.h, int(nlocal), nall, x.data_ptr(), float(cutneigh), numneigh.data_ptr(),
+                                          table.data_ptr(), int(width), C.byref(mx), stream)
+            if rc == self.ERR_CAPACITY:
+                width = (mx.value + 7) // 8 * 8
+                continue
+            _check(self.lib, rc)
+            self._neigh_width = width
+            return numneigh[:nlocal], table[:nlocal], mx.value
+
     PROF_CLASSES = ("pack", "gather", "moments", "program", "forces", "grade", "finalize", "site")
 
     def profile_enable(self, on: bool = True):
@@ -272,6 +298,15 @@ def potential_check(path: str, selection_state: bool = False) -> MTPInfo:
     info = MTPInfo()
     _check(lib, lib.mtp_potential_check(os.fsencode(path), int(selection_state), C.byref(info)))
     return info
+
+
+def program_check(path: str, atoms_per_cta: int = 32) -> float:
+    """Host-only check of the grouped contraction-program streams (mtp_program_check)."""
+    lib = load_library()
+    err = C.c_double(0.0)
+    lib.mtp_program_check.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_double)]
+    _check(lib, lib.mtp_program_check(os.fsencode(path), int(atoms_per_cta), C.byref(err)))
+    return float(err.value)
 
 
 def fp64_peaks(device: int = -1):

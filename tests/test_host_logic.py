@@ -189,3 +189,13 @@ def test_kat_potential_evaluates_like_generated_one(tmp_path, built):
 
     a, b = basis_values(gen), basis_values(katp)
     assert np.allclose(a, b, rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("level,atoms_per_cta", [(2, 32), (6, 32), (8, 32), (10, 32), (12, 16), (14, 32), (16, 32), (16, 16),
+                                                  (18, 16), (20, 16), (22, 32)])
+def test_grouped_program_streams_reproduce_the_sequential_program(tmp_path, level, atoms_per_cta):
+    """The stream packer of the 4-atoms-per-lane program kernel (node groups, split long lists, padding, scratch row)
+    interpreted on the host against pair_mtp.cpp:196-233 -- forward moments and reverse-mode adjoints."""
+    path, _ = util.write_potential(tmp_path, level, 2)
+    err = api.program_check(path, atoms_per_cta)
+    assert err <= 1e-13, err
