@@ -179,6 +179,19 @@ int mtp_halo_unpack_add_f(double *f, const int *sendlist, int n, const double *b
 int mtp_neigh_build(mtp_handle *h, int nlocal, int nall, const double *x, double cutneigh, int *numneigh, int *neighbors,
                     int width, int *max_numneigh_out, void *stream);
 
+/* ---- velocity-Verlet half steps on the device (the steps either side of the path) ---- */
+/* Upstream FixNVE::initial_integrate / final_integrate, which the reference's example deck runs around the pair style
+ * (`fix 1 all nve`, README.md:148-149): dtfm = dtf / mass[type[i]]; v += dtfm * f; x += dtv * v (initial) and
+ * v += dtfm * f (final) for the nlocal owned atoms.  All pointers DEVICE; mass is indexed by the 1-based type
+ * ([ntypes + 1]); dtf = 0.5 * dt * force->ftm2v, dtv = dt.  x_at_build / moved_flag (optional, both or neither):
+ * *moved_flag is set to 1 when an atom is farther than trigger_dist from x_at_build (LAMMPS's re-neighboring
+ * criterion, half the skin).  Products and sums are rounded separately, so a host replay is bit-exact. */
+int mtp_nve_initial_integrate(int nlocal, double *x, double *v, const double *f, const int *type, const double *mass,
+                              double dtf, double dtv, const double *x_at_build, double trigger_dist, int *moved_flag,
+                              void *stream);
+int mtp_nve_final_integrate(int nlocal, double *v, const double *f, const int *type, const double *mass, double dtf,
+                            void *stream);
+
 /* ---- measured roofs ----------------------------------------------------------------------------- */
 /* FP64 vector (DFMA) and FP64 tensor (mma.sync.m8n8k4.f64, DMMA) peak of the device, in TFLOP/s. */
 int mtp_fp64_peak(int device, double *dfma_tflops, double *dmma_tflops);

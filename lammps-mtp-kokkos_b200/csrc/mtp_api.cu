@@ -3,6 +3,7 @@
 #include "mtp_kernels.cu"
 #include "mtp_potential.hpp"
 #include "mtp_neigh.cuh"
+#include "mtp_md.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -381,7 +382,7 @@ void upload_potential(mtp_handle *h)
     // 4-atoms-per-lane kernel: 32 or 16 atoms per CTA, whichever fits with both tables resident
     int na_v3 = 0;
     if (!getenv("MTP_B200_NO_PROG_V3"))
-      for (int na = 32; na >= 16 && !na_v3; na >>= 1)
+      for (int na = getenv("MTP_B200_P3_NA") ? std::max(16, std::min(32, atoi(getenv("MTP_B200_P3_NA")))) : 32; na >= 16 && !na_v3; na >>= 1)
         if (program3_layout(p.alpha_moment_count, p.alpha_scalar_count, na, 2 * p.alpha_index_basic_count, 0, 0, 0, 0, false).total <= prog_max)
           na_v3 = na;
     compile_program(p, h->prog, h->pl_na[0], h->pl_na[1], na_v3);
@@ -1505,6 +1506,32 @@ int mtp_neigh_build(mtp_handle *h, int nlocal, int nall, const double *x, double
     return fail(MTP_ERR_CAPACITY, "neighbor table too narrow: the longest row has " + std::to_string(maxnn) + " entries, width is " +
                                       std::to_string(width));
   return MTP_OK;
+}
+
+int mtp_nve_initial_integrate(int nlocal, double *x, double *v, const double *f, const int *type, const double *mass,
+                              double dtf, double dtv, const double *x_at_build, double trigger_dist, int *moved_flag,
+                              void *stream)
+{
+  if (nlocal < 0 || (nlocal > 0 && (!x || !v || !f || !type || !mass))) return fail(MTP_ERR_ARG, "bad integrator arguments");
+  if ((x_at_build != nullptr) != (moved_flag != nullptr)) return fail(MTP_ERR_ARG, "x_at_build and moved_flag go together");
+  if (nlocal == 0) return MTP_OK;
+  return guarded([&] {
+    nve_initial_kernel<<<(nlocal + 255) / 256, 256, 0, (cudaStream_t) stream>>>(nlocal, x, v, f, type, mass, dtf, dtv, x_at_build,
+                                                                                 trigger_dist * trigger_dist, moved_flag);
+    g_launches++;
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
+int mtp_nve_final_integrate(int nlocal, double *v, const double *f, const int *type, const double *mass, double dtf, void *stream)
+{
+  if (nlocal < 0 || (nlocal > 0 && (!v || !f || !type || !mass))) return fail(MTP_ERR_ARG, "bad integrator arguments");
+  if (nlocal == 0) return MTP_OK;
+  return guarded([&] {
+    nve_final_kernel<<<(nlocal + 255) / 256, 256, 0, (cudaStream_t) stream>>>(nlocal, v, f, type, mass, dtf);
+    g_launches++;
+    CUDA_CHECK(cudaGetLastError());
+  });
 }
 
 int mtp_halo_pack_x(const double *x, const int *sendlist, int n, const double *shift, double *out, void *stream)

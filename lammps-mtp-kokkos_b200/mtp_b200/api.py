@@ -54,7 +54,8 @@ class MTPComputeArgs(C.Structure):
 
 EXPORTS = ["mtp_create_from_file", "mtp_create", "mtp_destroy", "mtp_last_error", "mtp_get_info",
            "mtp_get_tables", "mtp_set_chunksize", "mtp_compute", "mtp_synchronize", "mtp_compute_host",
-           "mtp_halo_pack_x", "mtp_halo_unpack_add_f", "mtp_fp64_peak", "mtp_kernel_launch_count", "mtp_last_kernel_path", "mtp_neigh_build", "mtp_program_check"]
+           "mtp_halo_pack_x", "mtp_halo_unpack_add_f", "mtp_fp64_peak", "mtp_kernel_launch_count", "mtp_last_kernel_path", "mtp_neigh_build", "mtp_program_check",
+           "mtp_nve_initial_integrate", "mtp_nve_final_integrate"]
 
 _lib = None
 
@@ -90,6 +91,9 @@ def load_library():
     lib.mtp_fp64_peak.argtypes = [C.c_int, _dp, _dp]
     lib.mtp_kernel_launch_count.restype = C.c_longlong
     lib.mtp_last_kernel_path.argtypes = [C.c_void_p]
+    lib.mtp_nve_initial_integrate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                              C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    lib.mtp_nve_final_integrate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
     lib.mtp_neigh_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int,
                                     C.POINTER(C.c_int), C.c_void_p]
     _lib = lib
