@@ -212,6 +212,8 @@ def main():
                     help="config 4: request per-atom extrapolation grades every K-th step (fix pair semantics); 0 = never")
     ap.add_argument("--halo", default="direct", choices=["direct", "staged"],
                     help="ghost exchange: one 26-direction stage (default) or LAMMPS's three dimension-by-dimension stages")
+    ap.add_argument("--md-steps", type=int, default=50,
+                    help="informational device-resident NVE run of this many steps after the bench (N = 1 only; 0 = off)")
     ap.add_argument("--lanes", type=int, default=2, help="internal streams the super-chunks are dealt to (mtp_set_lanes)")
     ap.add_argument("--chunksize", type=int, default=32768, help="pair_style ... chunksize N (README.md:44 of the reference)")
     args = ap.parse_args()
@@ -496,6 +498,40 @@ def main():
                                               "note": "informational: same call with list_changed only every 10th step"}
         e2e["device_built_list"] = devlist
 
+    # ---- informational: the reference's example deck as a device-resident MD loop (README.md:148-149: velocity
+    # create + fix nve around the pair style): integrate, ghost images, list rebuild, pair style, reverse halo, all on
+    # the device.  The random-init potential is rescaled by one factor to an RMS force of 0.05 eV/A.
+    md = None
+    if world == 1 and args.md_steps > 0:
+        try:
+            from mtp_b200.md import NVE, scale_to_rms_force
+            rms = float((t_f[:nlocal] ** 2).sum(dim=1).mean().sqrt().item())
+            pot_md = scale_to_rms_force(pot, rms, 0.05)
+            md_path = os.path.join(tmp, f"config{args.config}_md.almtp")
+            almtp.write_almtp(md_path, pot_md)
+            mtp_md = MTPB200(md_path, selection_state=False, device=local_rank)
+            mtp_md.set_chunksize(args.chunksize)
+            mtp_md.set_lanes(args.lanes)
+            nve = NVE(mtp_md, sysm, halo, masses=cfg["masses"], dt=0.001, temperature=300.0, seed=12345, variant=variant)
+            e_start = nve.potential_energy() + nve.kinetic_energy()
+            nve.run(3)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            nve.run(args.md_steps)
+            torch.cuda.synchronize()
+            md_ms = 1e3 * (time.perf_counter() - t0) / args.md_steps
+            e_end = nve.potential_energy() + nve.kinetic_energy()
+            md = {"value": nlocal / (md_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": md_ms, "steps": args.md_steps,
+                  "timestep_fs": 1.0, "temperature_K": nve.temperature(), "list_rebuilds": nve.rebuilds,
+                  "total_energy_drift_eV_per_atom": abs(e_end - e_start) / nlocal,
+                  "kinetic_energy_eV_per_atom": nve.kinetic_energy() / nlocal,
+                  "note": "informational: NVE velocity Verlet, every stage of the step on the device (mtp_nve_*_integrate, ghost "
+                          "images, mtp_neigh_build when an atom moved more than half the skin, mtp_compute, reverse halo); "
+                          "wall clock, one device sync per 10 steps"}
+            mtp_md.close()
+        except Exception as exc:
+            md = {"error": repr(exc)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -571,6 +607,8 @@ def main():
                        "grade_every": args.grade_every},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "energy": energy}
+    if md is not None:
+        line["md"] = md
     emit(line)
     if world > 1:
         dist.destroy_process_group()

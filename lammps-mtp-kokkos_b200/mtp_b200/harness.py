@@ -161,15 +161,15 @@ def random_types(n: int, fractions, seed: int) -> np.ndarray:
 # BASELINE.json configs.  ``scale`` shrinks the cell counts for tests.
 CONFIGS = {
     1: dict(name="fcc Al 4000 atoms, level 10, S=1", kind="fcc", a=4.05, cells=(10, 10, 10), level=10,
-            species=1, fractions=(1.0,), type_seed=0),
+            species=1, fractions=(1.0,), type_seed=0, masses=(26.9815,)),
     2: dict(name="bcc W/Mo 262144 atoms, level 16, S=2", kind="bcc", a=3.165, cells=(64, 64, 32), level=16,
-            species=2, fractions=(0.5, 0.5), type_seed=7),
+            species=2, fractions=(0.5, 0.5), type_seed=7, masses=(183.84, 95.95)),
     3: dict(name="diamond Si 2000 atoms, level 20, S=1", kind="diamond", a=5.431, cells=(5, 5, 10), level=20,
-            species=1, fractions=(1.0,), type_seed=0),
+            species=1, fractions=(1.0,), type_seed=0, masses=(28.0855,)),
     4: dict(name="fcc Al-Cu 256000 atoms, level 16, S=2, active set", kind="fcc", a=4.05, cells=(40, 40, 40),
-            level=16, species=2, fractions=(0.95, 0.05), type_seed=11, active_set=True),
+            level=16, species=2, fractions=(0.95, 0.05), type_seed=11, active_set=True, masses=(26.9815, 63.546)),
     5: dict(name="fcc CoCrNi 4M atoms/GPU, level 22, S=3", kind="fcc", a=3.56, cells=(100, 100, 100), level=22,
-            species=3, fractions=(1, 1, 1), type_seed=5),
+            species=3, fractions=(1, 1, 1), type_seed=5, masses=(58.9332, 51.9961, 58.6934)),
 }
 
 
