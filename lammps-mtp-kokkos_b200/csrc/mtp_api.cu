@@ -372,7 +372,7 @@ void upload_potential(mtp_handle *h)
     h->prog_max = prog_max;
     h->pl_na_fit = 0;
     for (int na = 32; na >= 2; na >>= 1)
-      if (program_layout(p.alpha_moment_count, p.alpha_scalar_count, na, 2 * p.alpha_index_basic_count, 0, 0, false).total <= prog_max) {
+      if (program_layout(p.alpha_moment_count, count_adjoint_rows(p), p.alpha_scalar_count, na, 2 * p.alpha_index_basic_count, 0, 0, false).total <= prog_max) {
         h->pl_na_fit = na;
         break;
       }
@@ -435,6 +435,7 @@ void upload_potential(mtp_handle *h)
   d.B = p.radial_basis_size;
   d.K = p.alpha_index_basic_count;
   d.M = p.alpha_moment_count;
+  d.Mg = h->prog.adjoint_rows;
   d.A = p.alpha_scalar_count;
   d.P = p.max_alpha_index_basic;
   d.Q = p.has_selection_state ? p.coeff_count : 0;
@@ -767,13 +768,13 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
     const int nslots = use_v2 ? kV2[h->v2_entry].KF : d.K;
     const int ntf = d.ffwd[s.prog_shape].nterms, ntr = d.frev[s.prog_shape].nterms;
     // shared-memory options in order of preference: prefetch staging + term streams, prefetch only, streams only
-    auto fits = [&](bool ds, bool pf) { return program_layout(d.M, d.A, na, nslots, ntf, ntr, ds, pf).total <= h->prog_max; };
+    auto fits = [&](bool ds, bool pf) { return program_layout(d.M, d.Mg, d.A, na, nslots, ntf, ntr, ds, pf).total <= h->prog_max; };
     s.prog_prefetch = 0;
     s.prog_dsmem = (nlanes == 1 && fits(true, s.prog_prefetch != 0)) ? 1 : 0;    // lanes: leave room for a co-resident CTA
     if (const char *e = getenv("MTP_B200_PROG_PREFETCH")) s.prog_prefetch = atoi(e) && fits(false, true);
     if (const char *e = getenv("MTP_B200_PROG_DSMEM")) s.prog_dsmem = atoi(e) && fits(true, s.prog_prefetch != 0);
     else if (!fits(true, s.prog_prefetch != 0)) s.prog_dsmem = 0;
-    smem_p = program_layout(d.M, d.A, na, nslots, ntf, ntr, s.prog_dsmem != 0, s.prog_prefetch != 0).total;
+    smem_p = program_layout(d.M, d.Mg, d.A, na, nslots, ntf, ntr, s.prog_dsmem != 0, s.prog_prefetch != 0).total;
     s.prog_debug = getenv("MTP_B200_PROG_DEBUG") ? atoi(getenv("MTP_B200_PROG_DEBUG")) : 0;
     for (lna = 0; (1 << lna) < na; lna++) {}
     s.slot_to_k = use_v2 ? h->d_slot_to_k.p : nullptr;

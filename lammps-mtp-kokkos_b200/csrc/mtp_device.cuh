@@ -35,6 +35,7 @@ struct DevFlatPass {
 
 struct DevPotential {
   int S, R, B, K, M, A, P, Q;
+  int Mg;                    // rows of the adjoint table of the chunk-per-CTA program kernel (Program::adjoint_rows)
   double rmin, rmax, scaling, cutsq;
   const double *radial;      // [S][S][R][B]
   const uint32_t *basic;     // [K] mu | ax << 8 | ay << 16 | az << 24

@@ -501,14 +501,14 @@ constexpr int PROG_THREADS = 256;    // 8 warps; every thread owns TWO adjacent 
 struct ProgLayout {
   size_t node_bytes, off_cg, off_epart, off_s2k, off_lin, off_map, off_stage, off_terms[2], off_st[2], total;
 };
-__host__ __device__ inline ProgLayout program_layout(int M, int A, int na, int nslots, int nterms_f, int nterms_r,
+__host__ __device__ inline ProgLayout program_layout(int M, int Mg, int A, int na, int nslots, int nterms_f, int nterms_r,
                                                      bool dsmem, bool prefetch = false)
 {
   ProgLayout L;
   const int vw = 16 * 32 / na;
-  L.node_bytes = ((size_t) (M + 1) * na * 8 + 15) & ~(size_t) 15;
+  L.node_bytes = ((size_t) (M + 1) * na * 8 + 15) & ~(size_t) 15;    // moments: M rows + the row of ones
   L.off_cg = L.node_bytes;
-  L.off_epart = 2 * L.node_bytes;
+  L.off_epart = L.node_bytes + (((size_t) Mg * na * 8 + 15) & ~(size_t) 15);    // adjoints: the compact table
   L.off_s2k = L.off_epart + (size_t) vw * na * 8;
   size_t o = (L.off_s2k + (size_t) nslots * 2 + 15) & ~(size_t) 15;
   L.off_lin = o;
@@ -593,7 +593,7 @@ mtp_program_kernel(DevPotential pot, SiteArgs a, const double *__restrict__ mb, 
   const int fi = a.prog_shape;
   const DevFlatPass &pf = pot.ffwd[fi], &pr = pot.frev[fi];
   const int nslots = a.slot_to_k ? a.nslots : pot.K;
-  const ProgLayout L = program_layout(pot.M, pot.A, NA, nslots, pf.nterms, pr.nterms, a.prog_dsmem != 0, a.prog_prefetch != 0);
+  const ProgLayout L = program_layout(pot.M, pot.Mg, pot.A, NA, nslots, pf.nterms, pr.nterms, a.prog_dsmem != 0, a.prog_prefetch != 0);
   double *s_lin = reinterpret_cast<double *>(smem + L.off_lin);
   int *s_map = reinterpret_cast<int *>(smem + L.off_map);
   double *stage = reinterpret_cast<double *>(smem + L.off_stage);
@@ -609,7 +609,7 @@ mtp_program_kernel(DevPotential pot, SiteArgs a, const double *__restrict__ mb, 
   double e_thread = 0.0;
 
   // one-time setup: constant row, slot map, term streams
-  for (int t = threadIdx.x; t < NA; t += blockDim.x) cm[pot.M * NA + t] = cg[pot.M * NA + t] = 1.0;
+  for (int t = threadIdx.x; t < NA; t += blockDim.x) cm[pot.M * NA + t] = 1.0;
   for (int t = threadIdx.x; t < nslots; t += blockDim.x) s2k[t] = a.slot_to_k ? a.slot_to_k[t] : (short) t;
   for (int t = threadIdx.x; t < pot.A; t += blockDim.x) {
     s_lin[t] = pot.lin[t];

@@ -386,6 +386,16 @@ void pack_pass(const std::vector<std::vector<NodeList>> &per_level, ProgramPass 
 
 }    // namespace
 
+int count_adjoint_rows(const Potential &p)
+{
+  const int M = p.alpha_moment_count, K = p.alpha_index_basic_count, T = p.alpha_index_times_count;
+  std::vector<char> src(std::max(M, 1), 0);
+  for (int e = 0; e < T; e++) src[p.alpha_index_times[4 * (size_t) e]] = src[p.alpha_index_times[4 * (size_t) e + 1]] = 1;
+  int rows = K;
+  for (int n = K; n < M; n++) rows += src[n];
+  return std::max(rows, 1);
+}
+
 void compile_program(const Potential &p, Program &prog, int na_large, int na_small, int na_v3)
 {
   const int M = p.alpha_moment_count, T = p.alpha_index_times_count, A = p.alpha_scalar_count;
@@ -460,6 +470,12 @@ void compile_program(const Potential &p, Program &prog, int na_large, int na_sma
   // ---- chunk form ----
   std::vector<char> is_source(M, 0);
   for (int e = 0; e < T; e++) is_source[times[4 * e]] = is_source[times[4 * e + 1]] = 1;
+  prog.grow.assign(M, -1);
+  prog.adjoint_rows = p.alpha_index_basic_count;
+  for (int n = 0; n < p.alpha_index_basic_count; n++) prog.grow[n] = n;
+  for (int n = p.alpha_index_basic_count; n < M; n++)
+    if (is_source[n]) prog.grow[n] = prog.adjoint_rows++;
+  prog.adjoint_rows = std::max(prog.adjoint_rows, 1);
   auto pack_chunk = [&](const std::vector<std::vector<NodeList>> &levels, bool reverse, ChunkPass &out) {
     out = ChunkPass();
     out.level_begin.push_back(0);
@@ -555,10 +571,15 @@ void compile_program(const Potential &p, Program &prog, int na_large, int na_sma
         while (bins[b].size() % FLAT_UNROLL) bins[b].push_back(Raw{ONE, ONE, ONE, false, 0.0});
         for (const Raw &r : bins[b]) {
           // operand flag (offsets are multiples of 8): bit 0 = the operand is the constant 1.0 (broadcast read)
-          const uint32_t ao = r.a == ONE ? 1u : (uint32_t) r.a * row_bytes;
+          // reverse pass: operand a and the destination are rows of the (compact) adjoint table
+          auto arow = [&](int node) { return reverse ? prog.grow[node] : node; };
+          if (reverse && ((r.a != ONE && prog.grow[r.a] < 0) || (r.node != ONE && prog.grow[r.node] < 0)))
+            throw std::runtime_error("internal: adjoint row missing for a node of the reverse pass");
+          const uint32_t ao = r.a == ONE ? 1u : (uint32_t) arow(r.a) * row_bytes;
           const uint32_t bo = r.b == ONE ? 1u : (uint32_t) r.b * row_bytes;
           out.terms.push_back(FlatTerm{ao, bo, r.coef});
-          out.st.push_back((uint32_t) r.node * row_bytes | (r.store ? 1u : 0u));
+          // (padding no-ops never store; their destination field is unused)
+          out.st.push_back((r.node == ONE ? 0u : (uint32_t) arow(r.node) * row_bytes) | (r.store ? 1u : 0u));
         }
         out.stream_begin.push_back((int) out.terms.size());
       }

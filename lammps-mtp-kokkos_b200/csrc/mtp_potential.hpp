@@ -134,10 +134,17 @@ struct Program {
   int f3_na = 0;                  // atoms per CTA of the v3 streams (32 / 16), 0 = tables not expressible
   Flat3Pass f3fwd, f3rev;
   std::vector<int> level;         // [M]
+  // rows of the adjoint table of the chunk-per-CTA program kernel: only basic moments and nodes that feed a product
+  // ever hold a variable adjoint (the others are constants folded into coefficients), so the table has
+  // adjoint_rows = K + (non-basic sources) rows instead of M: grow[node] = its row, or -1
+  int adjoint_rows = 0;
+  std::vector<int> grow;
   ProgramPass fwd, rev;
   std::vector<double> ginit;      // [M]: dE/dm seed, g[map[s]] = xi_s (pair_mtp.cpp:217-218)
 };
 
+// K + number of non-basic nodes that are a factor of some product (Program::adjoint_rows, without compiling)
+int count_adjoint_rows(const Potential &p);
 // Throws std::runtime_error if the table is not a topologically ordered program.
 void compile_program(const Potential &p, Program &out, int na_large = 32, int na_small = 8, int na_v3 = 0);
 
