@@ -123,6 +123,9 @@ def brick_grid(n):
     return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n]
 
 
+LIST_EVERY = 10      # e2e: steps between neighbor-list uploads (re-neighboring cadence; the default skin of 2 A gives far more)
+
+
 def pinned_like(a):
     import torch
     t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].copy()).dtype, pin_memory=True)
@@ -394,7 +397,7 @@ def main():
         t0 = time.perf_counter()
         for k in range(args.steps):
             mtp.compute_host(hx, htype, hil, hnn, hneigh, hoff, eflag=1, vflag=1, variant=variant, out=res,
-                             list_changed=(k % 10 == 0))
+                             list_changed=(k % LIST_EVERY == 0))
         e2e10_ms = 1e3 * (time.perf_counter() - t0) / args.steps
         # informational: the list never crosses PCIe -- built on the device (mtp_neigh_build) on
         # every 10th step from the positions that were just uploaded; per step H2D x/type, kernels, D2H f + EV record
@@ -446,11 +449,15 @@ def main():
         except Exception as exc:      # the headline e2e above does not depend on this variant
             devlist = {"error": repr(exc)}
         nid = nlocal
-        h2d = 24 * nall + 4 * nall + 24 * nall + 4 * sysm.neigh.size + 8 * nid + 4 * nid + 4 * nlocal
+        list_bytes = 4 * sysm.neigh.size + 8 * nid + 4 * nid + 4 * nlocal
+        h2d = 24 * nall + 4 * nall + 24 * nall + list_bytes // LIST_EVERY
         d2h = 24 * nall + 64
         e2e_energy = float(res.ev[0])
-        note = ("mtp_compute_host per step: H2D x,type,f and the full neighbor list (re-sent every step), kernels, "
-                "D2H f + energy/virial record; host buffers pinned; wall clock around the blocking call")
+        e2e_every_ms, e2e_ms = e2e_ms, e2e10_ms      # headline: LAMMPS's re-neighboring cadence; every-step kept below
+        note = ("mtp_compute_host per step: H2D x,type,f every step and the full neighbor list on every %dth step (the "
+                "list only changes when LAMMPS re-neighbors; with the default 2 A skin that is far rarer than every 10 "
+                "steps in a solid), kernels, D2H f + energy/virial record; host buffers pinned; wall clock around the "
+                "blocking call; h2d bytes averaged over the cadence" % LIST_EVERY)
     else:
         # N > 1: same metric through the public Python API: per step H2D of the owned positions, types and the
         # neighbor list from pinned host memory, device halo exchange, kernels, D2H of the owned forces + EV record
@@ -462,12 +469,13 @@ def main():
         hf_t = torch.empty((nlocal, 3), dtype=torch.float64, pin_memory=True)
         hev_t = torch.empty(8, dtype=torch.float64, pin_memory=True)
 
-        def step_e2e():
+        def step_e2e(k=0):
             t_x[:nlocal].copy_(hx_t, non_blocking=True)
             t_type.copy_(ht_t, non_blocking=True)
-            t_nn.copy_(hnn_t, non_blocking=True)
-            t_neigh.copy_(hne_t, non_blocking=True)
-            t_off.copy_(hof_t, non_blocking=True)
+            if k % LIST_EVERY == 0:      # re-neighboring step: the list crosses PCIe again
+                t_nn.copy_(hnn_t, non_blocking=True)
+                t_neigh.copy_(hne_t, non_blocking=True)
+                t_off.copy_(hof_t, non_blocking=True)
             step_device()
             hf_t.copy_(t_f[:nlocal], non_blocking=True)
             hev_t.copy_(t_ev, non_blocking=True)
@@ -477,25 +485,27 @@ def main():
             step_e2e()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
+        for k in range(args.steps):
+            step_e2e(k)
         barrier()
         e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-        h2d = 24 * nlocal + 4 * nall + 4 * nall + 4 * sysm.neigh.size + 8 * (nall + 1)
+        h2d = 24 * nlocal + 4 * nall + (4 * nall + 4 * sysm.neigh.size + 8 * (nall + 1)) // LIST_EVERY
         d2h = 24 * nlocal + 64
         e2e_energy = float(hev_t[0])
-        note = ("per rank and step: H2D owned x, type, numneigh/offsets/neighbor list from pinned memory, device halo "
-                "forward (NCCL send/recv), kernels, halo reverse, EV all-reduce, D2H owned f + EV record; wall clock, "
-                "max over ranks; bytes are per rank")
+        note = ("per rank and step: H2D owned x, type every step and numneigh/offsets/neighbor list on every %dth step "
+                "(LAMMPS's re-neighboring cadence) from pinned memory, device halo forward (NCCL send/recv), kernels, halo "
+                "reverse, EV all-reduce, D2H owned f + EV record; wall clock, max over ranks; bytes are per rank and "
+                "averaged over the cadence" % LIST_EVERY)
     e2e = {"value": world * nlocal / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "note": note,
            "energy_matches_device_path": bool(abs(e2e_energy - energy) <= 1e-9 * abs(energy))}
     if world == 1:
-        e2e["list_resent_every_10th_step"] = {"value": nlocal / (e2e10_ms * 1e-3) / 1e6, "ms_per_step": e2e10_ms,
-                                              "note": "informational: same call with list_changed only every 10th step"}
+        e2e["list_resent_every_step"] = {"value": nlocal / (e2e_every_ms * 1e-3) / 1e6, "ms_per_step": e2e_every_ms,
+                                         "h2d_bytes_per_step": int(24 * nall + 4 * nall + 24 * nall + list_bytes),
+                                         "note": "pessimistic bound: same call with the full neighbor list re-sent on EVERY step"}
         e2e["device_built_list"] = devlist
 
     # ---- informational: the reference's example deck as a device-resident MD loop (README.md:148-149: velocity
@@ -568,7 +578,17 @@ def main():
         kp["algorithmic_smem_bytes_per_atom"] = 48.0 * pot.T
         kp["achieved_smem_tbs"] = 48.0 * pot.T * nlocal / (kp["ms_per_step"] * 1e-3) / 1e12
         kp["frac_of_smem_peak"] = kp["achieved_smem_tbs"] / smem_peak_tbs
-    roofline = {"kernel": dom, "traffic": None,
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture (config 2 only: the
+    # capture is of that workload); null for any other workload
+    traffic, traffic_note = None, None
+    try:
+        if args.config == 2 and not args.cells and dom:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = tj["kernels"][dom]["bytes_per_launch"]
+            traffic_note = tj["note"]
+    except Exception:
+        traffic = None
+    roofline = {"kernel": dom, "traffic": traffic, "traffic_note": traffic_note,
                 "duration_ms": kernels[dom]["ms_per_step"] / kernels[dom]["launches_per_step"] if dom else None,
                 "duration_note": "average launch duration of the dominant kernel (largest share of the step): CUDA events "
                                  "recorded by the library on its launch stream around every launch (mtp_profile_read) in a "
