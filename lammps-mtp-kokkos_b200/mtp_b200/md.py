@@ -84,8 +84,16 @@ class NVE:
         self.moved.zero_()
         self.rebuilds += 1
 
-    def _force(self):
-        self.halo.forward(self.x)
+    def _moved_anywhere(self) -> bool:
+        """Re-neighboring is a collective decision (LAMMPS: MPI_Allreduce in Neighbor::decide)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.moved, op=dist.ReduceOp.MAX)
+        return bool(int(self.moved.item()))
+
+    def _force(self, forward: bool = True):
+        if forward:
+            self.halo.forward(self.x)
         self.f.zero_()
         self.mtp.compute_device(self.x, self.type, self.ilist, self.nn, self.table, None, self.f, self.ev,
                                 stride_i=self.table.shape[1], stride_jj=1, eflag=1, vflag=1, variant=self.variant,
@@ -100,10 +108,10 @@ class NVE:
                 self.mass.data_ptr(), dtf, self.dt, self.x_at_build.data_ptr(), self.trigger, self.moved.data_ptr(),
                 self._stream()))
             self.steps_done += 1
-            if self.steps_done % self.check_every == 0 and int(self.moved.item()):
-                self.halo.forward(self.x)       # the list is built from current ghost positions too
-                self._rebuild()
-            self._force()
+            self.halo.forward(self.x)
+            if self.steps_done % self.check_every == 0 and self._moved_anywhere():
+                self._rebuild()                 # from the current owned AND ghost positions
+            self._force(forward=False)
             api._check(self.lib, self.lib.mtp_nve_final_integrate(
                 self.nlocal, self.v.data_ptr(), self.f.data_ptr(), self.type.data_ptr(), self.mass.data_ptr(), dtf,
                 self._stream()))
