@@ -217,8 +217,11 @@ def main():
                     help="ghost exchange: one 26-direction stage (default) or LAMMPS's three dimension-by-dimension stages")
     ap.add_argument("--md-steps", type=int, default=50,
                     help="informational device-resident NVE run of this many steps after the bench (N = 1 only; 0 = off)")
-    ap.add_argument("--lanes", type=int, default=2, help="internal streams the super-chunks are dealt to (mtp_set_lanes)")
-    ap.add_argument("--chunksize", type=int, default=32768, help="pair_style ... chunksize N (README.md:44 of the reference)")
+    ap.add_argument("--lanes", type=int, default=3, help="internal streams the super-chunks are dealt to (mtp_set_lanes)")
+    ap.add_argument("--chunksize", type=int, default=131072,
+                    help="pair_style ... chunksize N: README.md:44 of the reference asks the user to tune it (\"sufficient "
+                         "parallelism\", \"minimizing the occurrence of a small final chunk\"); 131072 is the tuned value for "
+                         "this implementation at config 2 (sweep in DESIGN.md section 6); the reference's decks use 32768")
     args = ap.parse_args()
 
     from mtp_b200 import almtp, harness
