@@ -75,7 +75,8 @@ struct SiteArgs {
   int first_ii;           // chunk offset into ilist (grade steps)
   int prog_shape;         // which flat-stream table set the program kernel uses (0 throughput, 1 latency)
   int prog_dsmem;         // program kernel: term streams staged in shared memory
-  int prog_debug;         // timing experiments only: bit0 skip forward pass, bit1 skip reverse pass, bit2 skip energy
+  int prog_debug;         // timing experiments only (MTP_B200_PROG_DEBUG): bit0 skip forward pass, bit1 skip reverse pass, bit2 skip
+                          // energy, bit3 skip the basic-moment fetch, bit4 skip the adjoint store (bits 3-4: 4-atoms-per-lane kernel)
   int prog_prefetch;      // program kernel: next chunk's basic moments prefetched (cp.async) into a staging buffer
   const short *slot_to_k; // rows of mb / gb are canonical slots (v2 pipeline) instead of basic-moment indices; or NULL
   int nslots;             // rows of mb / gb

@@ -199,3 +199,24 @@ def test_grouped_program_streams_reproduce_the_sequential_program(tmp_path, leve
     path, _ = util.write_potential(tmp_path, level, 2)
     err = api.program_check(path, atoms_per_cta)
     assert err <= 1e-13, err
+
+
+def test_md_helpers_velocity_create_and_force_scaling():
+    """`velocity all create T seed mom yes` (README.md:148 of the reference) and the one-factor force rescaling."""
+    pytest.importorskip("torch")
+    from mtp_b200 import almtp
+    from mtp_b200.md import BOLTZ, MVV2E, maxwell_velocities, scale_to_rms_force
+    types = np.random.default_rng(0).integers(1, 3, size=5000)
+    mass1 = np.array([0.0, 183.84, 95.95])
+    v = maxwell_velocities(types, mass1, 300.0, 12345)
+    m = mass1[types]
+    assert np.abs((m[:, None] * v).sum(axis=0)).max() <= 1e-9 * np.abs(m[:, None] * v).sum()
+    t = MVV2E * (m[:, None] * v * v).sum() / ((3 * len(types) - 3) * BOLTZ)
+    assert abs(t - 300.0) < 1e-9
+    assert np.array_equal(v, maxwell_velocities(types, mass1, 300.0, 12345))          # seeded
+    assert np.abs(maxwell_velocities(types, mass1, 0.0, 1)).max() == 0.0
+    pot = almtp.random_potential(8, 2)
+    half = scale_to_rms_force(pot, rms_now=0.1, rms_target=0.05)
+    assert np.allclose(half.moment_coeffs, 0.5 * np.asarray(pot.moment_coeffs))
+    assert np.allclose(half.species_coeffs, 0.5 * np.asarray(pot.species_coeffs))
+    assert np.array_equal(half.radial_coeffs, pot.radial_coeffs)
