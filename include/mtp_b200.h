@@ -179,6 +179,15 @@ int mtp_halo_unpack_add_f(double *f, const int *sendlist, int n, const double *b
 int mtp_neigh_build(mtp_handle *h, int nlocal, int nall, const double *x, double cutneigh, int *numneigh, int *neighbors,
                     int width, int *max_numneigh_out, void *stream);
 
+/* ---- device-side selection of extrapolating atoms (caller side of the grade path) ---- */
+/* indices_out[0 .. *count_out) = ascending ids i < n with grades[i] >= threshold -- the comparison of
+ * PairMTPExtrapolation::evaluate_grades (pair_mtp_extrapolation.cpp:389-390) applied per atom to the neighborhood
+ * grades that `fix pair` exports (extract_peratom "extrapolation", :641-652) -- so that a caller copies only the
+ * selected atoms to the host instead of the whole per-atom array.  grades, indices_out: DEVICE ([n]); count_out: HOST.
+ * Blocks until the count is known. */
+int mtp_select_grades(mtp_handle *h, const double *grades, int n, double threshold, int *indices_out, int *count_out,
+                      void *stream);
+
 /* ---- velocity-Verlet half steps on the device (the steps either side of the path) ---- */
 /* Upstream FixNVE::initial_integrate / final_integrate, which the reference's example deck runs around the pair style
  * (`fix 1 all nve`, README.md:148-149): dtfm = dtf / mass[type[i]]; v += dtfm * f; x += dtv * v (initial) and

@@ -4,6 +4,8 @@
 #include "mtp_potential.hpp"
 #include "mtp_neigh.cuh"
 #include "mtp_md.cuh"
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 #include <algorithm>
 #include <atomic>
@@ -1507,6 +1509,36 @@ int mtp_neigh_build(mtp_handle *h, int nlocal, int nall, const double *x, double
     return fail(MTP_ERR_CAPACITY, "neighbor table too narrow: the longest row has " + std::to_string(maxnn) + " entries, width is " +
                                       std::to_string(width));
   return MTP_OK;
+}
+
+namespace {
+struct GradeAtLeast {
+  const double *grades;
+  double threshold;
+  __host__ __device__ bool operator()(const int &i) const { return grades[i] >= threshold; }
+};
+}    // namespace
+
+int mtp_select_grades(mtp_handle *h, const double *grades, int n, double threshold, int *indices_out, int *count_out, void *stream)
+{
+  if (!h || !count_out) return fail(MTP_ERR_ARG, "null argument");
+  *count_out = 0;
+  if (n < 0 || (n > 0 && (!grades || !indices_out))) return fail(MTP_ERR_ARG, "bad selection arguments");
+  if (n == 0) return MTP_OK;
+  return guarded([&] {
+    CUDA_CHECK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    h->nb_max.ensure(1);
+    cub::CountingInputIterator<int> ids(0);
+    GradeAtLeast pred{grades, threshold};
+    size_t tmp_bytes = 0;
+    CUDA_CHECK(cub::DeviceSelect::If(nullptr, tmp_bytes, ids, indices_out, h->nb_max.p, n, pred, st));
+    h->nb_tmp.ensure(tmp_bytes);
+    CUDA_CHECK(cub::DeviceSelect::If(h->nb_tmp.p, tmp_bytes, ids, indices_out, h->nb_max.p, n, pred, st));
+    g_launches += 2;
+    CUDA_CHECK(cudaMemcpyAsync(count_out, h->nb_max.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  });
 }
 
 int mtp_nve_initial_integrate(int nlocal, double *x, double *v, const double *f, const int *type, const double *mass,

@@ -55,7 +55,7 @@ class MTPComputeArgs(C.Structure):
 EXPORTS = ["mtp_create_from_file", "mtp_create", "mtp_destroy", "mtp_last_error", "mtp_get_info",
            "mtp_get_tables", "mtp_set_chunksize", "mtp_compute", "mtp_synchronize", "mtp_compute_host",
            "mtp_halo_pack_x", "mtp_halo_unpack_add_f", "mtp_fp64_peak", "mtp_kernel_launch_count", "mtp_last_kernel_path", "mtp_neigh_build", "mtp_program_check",
-           "mtp_nve_initial_integrate", "mtp_nve_final_integrate"]
+           "mtp_nve_initial_integrate", "mtp_nve_final_integrate", "mtp_select_grades"]
 
 _lib = None
 
@@ -93,6 +93,7 @@ def load_library():
     lib.mtp_last_kernel_path.argtypes = [C.c_void_p]
     lib.mtp_nve_initial_integrate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                               C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    lib.mtp_select_grades.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]
     lib.mtp_nve_final_integrate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
     lib.mtp_neigh_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int,
                                     C.POINTER(C.c_int), C.c_void_p]
@@ -263,6 +264,17 @@ class MTPB200:
             _check(self.lib, rc)
             self._neigh_width = width
             return numneigh[:nlocal], table[:nlocal], mx.value
+
+    def select_grades(self, grades, threshold: float, stream=None):
+        """Ascending ids of the atoms whose grade is >= threshold, selected on the device (mtp_select_grades).
+        grades: CUDA float64 tensor [n]; returns a CUDA int32 tensor."""
+        import torch
+        n = int(grades.shape[0])
+        idx = torch.empty(max(n, 1), dtype=torch.int32, device=grades.device)
+        cnt = C.c_int(0)
+        _check(self.lib, self.lib.mtp_select_grades(self.h, grades.data_ptr(), n, float(threshold), idx.data_ptr(), C.byref(cnt),
+                                                    stream))
+        return idx[: cnt.value]
 
     PROF_CLASSES = ("pack", "gather", "moments", "program", "forces", "grade", "finalize", "site")
 

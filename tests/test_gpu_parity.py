@@ -184,3 +184,22 @@ def test_program_kernel_throughput_shape_grades(tmp_path, built):
     assert maxabsrel(gpu.grades[: sysm.nlocal], ref.grades[: sysm.nlocal]) <= TOL_AUX
     assert abs(gpu.max_grade - ref.max_grade) <= TOL_AUX * ref.max_grade
     mtp.close()
+
+
+def test_device_side_grade_selection(tmp_path, built):
+    """Atoms with grade >= threshold compacted on the device == numpy on the oracle's grades."""
+    import torch
+    from mtp_b200.api import MTPB200
+    from oracle_py import OracleMTP
+    path, pot = util.write_potential(tmp_path, 8, 2, active_set=True)
+    sysm = util.small_system("bcc", 3.165, (6, 6, 6), 2, seed=11)
+    ref = OracleMTP(pot).compute(sysm.x, sysm.type, sysm.ilist, sysm.numneigh, sysm.neigh, sysm.offsets, grade=True)
+    mtp = MTPB200(path, selection_state=True)
+    gpu = mtp.compute_system(sysm, grade=True)
+    g = torch.from_numpy(np.ascontiguousarray(gpu.grades[: sysm.nlocal])).cuda()
+    for q in (0.0, 0.5, 0.9, 1.0, 2.0):
+        thr = float(np.quantile(ref.grades[: sysm.nlocal], min(q, 1.0))) * (2.0 if q > 1.0 else 1.0)
+        sel = mtp.select_grades(g, thr).cpu().numpy()
+        assert np.array_equal(sel, np.nonzero(gpu.grades[: sysm.nlocal] >= thr)[0])
+    assert mtp.select_grades(g[:0], 1.0).numel() == 0
+    mtp.close()
