@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MTP_B200_ABI_VERSION 2
+#define MTP_B200_ABI_VERSION 3 /* 3: + mtp_neigh_build, mtp_nve_*_integrate, mtp_select_grades, mtp_program_check, mtp_last_kernel_path */
 
 #define MTP_OK 0
 #define MTP_ERR_ARG (-1)      /* bad argument */
