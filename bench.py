@@ -626,7 +626,7 @@ def main():
                        "parallelism": "brick grid %dx%dx%d, one rank per GPU, %s NCCL send/recv halo (%d B/rank/step)" % (
                            *brick_grid(world), args.halo, halo.bytes_per_step),
                        "l2": "256 MiB write between timed iterations (L2 flush), per-step CUDA events summed",
-                       "variant": args.variant, "chunksize": args.chunksize, "flags": "eflag=1 vflag=1",
+                       "variant": args.variant, "chunksize": args.chunksize, "lanes": args.lanes, "flags": "eflag=1 vflag=1",
                        "grade_every": args.grade_every},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "energy": energy}
