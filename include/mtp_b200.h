@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MTP_B200_ABI_VERSION 3 /* 3: + mtp_neigh_build, mtp_nve_*_integrate, mtp_select_grades, mtp_program_check, mtp_last_kernel_path */
+#define MTP_B200_ABI_VERSION 4 /* 4: + mtp_codegen_source, mtp_codegen_prebuild, mtp_program_kernel_note */
 
 #define MTP_OK 0
 #define MTP_ERR_ARG (-1)      /* bad argument */
@@ -228,9 +228,24 @@ long long mtp_kernel_launch_count(void);
  * (pair_mtp.cpp:196-233).  *max_rel_err_out receives the largest relative deviation (moments and adjoints). */
 int mtp_program_check(const char *path, int atoms_per_cta, double *max_rel_err_out);
 
+/* ---- generated contraction-program kernel ------------------------------------------------------------------------
+ * The alpha_index_times program of a potential (pair_mtp.cpp:196-233; executed by the reference as a serial loop per
+ * thread, pair_mtp_kokkos.cpp:550-592, or in three atomic waves, pair_mtps_kokkos.cpp:572-639) is compiled into one
+ * straight-line sm_100a kernel per potential STRUCTURE when the potential is loaded (NVRTC; cubins are cached under
+ * $MTP_B200_KCACHE or <library directory>/kcache).  The two entry points below run the generator without a device:
+ * mtp_codegen_source returns the emitted CUDA source (tests compile it for the host and run it against the sequential
+ * program), mtp_codegen_prebuild compiles it and stores the cubin in the cache (build step).
+ * info_out[12] = atoms per CTA, warps, CTAs per SM, shared-memory rows, stages, shared-memory bytes, term steps per
+ * atom, row loads per chunk, row stores per chunk, critical-path term steps, rows of mb/gb, structure hash. */
+int mtp_codegen_source(const char *path, int latency_shape, char *buf, long long cap, long long *needed, long long *info_out);
+int mtp_codegen_prebuild(const char *path, int latency_shape, int *compiled_out);
+/* empty when the generated kernel serves this handle, else the reason it does not (the interpreting kernels run) */
+const char *mtp_program_kernel_note(const mtp_handle *h);
+
 /* Which kernels the last mtp_compute() of this handle launched (tests assert that the intended path ran):
  * bits 0-3 kernel family (0 generic fused site kernel, 1 DMMA-moment pipeline, 2 register-resident pair kernels),
- * bit 4 set when the contraction program ran in its 4-atoms-per-lane form, bits 8-15 atoms per CTA of that kernel. */
+ * bit 4 set when the contraction program ran in its 4-atoms-per-lane interpreting form, bit 5 when the generated
+ * per-potential kernel ran, bits 8-15 atoms per CTA of the program kernel. */
 int mtp_last_kernel_path(const mtp_handle *h);
 
 #ifdef __cplusplus

@@ -4,6 +4,7 @@
 #include "mtp_potential.hpp"
 #include "mtp_neigh.cuh"
 #include "mtp_md.cuh"
+#include "mtp_p4_runtime.hpp"
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 
@@ -185,6 +186,11 @@ struct mtp_handle {
   DevBuf<int> nb_keys, nb_idx, nb_skeys, nb_sidx, nb_cell, nb_max;
   DevBuf<AtomRec> nb_xs;
   DevBuf<unsigned char> nb_tmp;
+  // generated contraction-program kernel (mtp_codegen.hpp): [0] throughput shape, [1] latency shape (mtp/small/kk)
+  P4Module p4[2];
+  std::vector<short> slot_of_k;   // basic moment -> row of mb / gb
+  int p4_nslots = 0;
+  std::string p4_note;            // why the generated kernel is not in use (empty when it is)
   int p3_na = 0;                  // atoms per CTA of the 4-atoms-per-lane program kernel, 0 = not usable for this potential
   size_t prog_max = 0;
   int pl_na[2] = {0, 0};          // atoms per CTA of the program kernel: throughput shape, latency shape
@@ -328,15 +334,14 @@ const V2Entry kV2[] = {V2_ENTRY(0), V2_ENTRY(1), V2_ENTRY(2), V2_ENTRY(3), V2_EN
                        V2_ENTRY(6), V2_ENTRY(7), V2_ENTRY(8), V2_ENTRY(9), V2_ENTRY(10)};
 constexpr int kV2Count = sizeof(kV2) / sizeof(kV2[0]);
 
-// canonical slot (q lexicographic in (a,b,c), then mu) -> basic moment index of the file, -1 = absent
-bool build_v2_tables(mtp_handle *h, int e)
+// canonical slot (q lexicographic in (a,b,c), then mu) -> basic moment index of the file, -1 = absent (host only)
+bool v2_slot_table(const Potential &p, int e, std::vector<short> &s2k)
 {
-  const Potential &p = h->pot;
   const int D0 = kV2[e].d0, R = kV2[e].R;
   if (p.radial_func_count != R) return false;
   auto dmu = [&](int mu) { return std::max(D0 - 2 * mu, 0); };
   auto rcnt = [&](int d) { return d == 0 ? R : (d > D0 ? 0 : (D0 - d) / 2 + 1); };
-  std::vector<short> s2k((size_t) kV2[e].KF, (short) -1);
+  s2k.assign((size_t) kV2[e].KF, (short) -1);
   // slot prefix per monomial
   std::vector<int> prefix((size_t) tet(D0) + 1, 0);
   {
@@ -358,7 +363,39 @@ bool build_v2_tables(mtp_handle *h, int e)
     if (slot >= 0) return false;    // two basic moments with the same definition
     slot = (short) k;
   }
+  return true;
+}
+
+// v2 entry serving potential p (standard basic-moment set of degree P - 1), or -1
+int v2_entry_for(const Potential &p, std::vector<short> &s2k)
+{
+  const int pmax = p.max_alpha_index_basic - 1;
+  for (int e = 0; e < kV2Count; e++)
+    if (kV2[e].d0 == pmax) return v2_slot_table(p, e, s2k) ? e : -1;
+  return -1;
+}
+
+// basic moment -> row of the mb / gb arrays the program kernel exchanges with the pair kernels
+void p4_slot_map(const Potential &p, int v2_entry, const std::vector<short> &s2k, std::vector<short> &slot_of_k, int &nslots)
+{
+  const int K = p.alpha_index_basic_count;
+  slot_of_k.assign((size_t) K, (short) -1);
+  if (v2_entry >= 0) {
+    nslots = kV2[v2_entry].KF;
+    for (int s = 0; s < nslots; s++)
+      if (s2k[s] >= 0) slot_of_k[s2k[s]] = (short) s;
+  } else {
+    nslots = K;
+    for (int k = 0; k < K; k++) slot_of_k[k] = (short) k;
+  }
+}
+
+bool build_v2_tables(mtp_handle *h, int e)
+{
+  std::vector<short> s2k;
+  if (!v2_slot_table(h->pot, e, s2k)) return false;
   h->d_slot_to_k.upload(s2k, 0);
+  p4_slot_map(h->pot, e, s2k, h->slot_of_k, h->p4_nslots);
   return true;
 }
 
@@ -586,6 +623,33 @@ void upload_potential(mtp_handle *h)
     h->smem[gflag] = bytes;
     h->grid_cap[gflag] = per_sm * h->sm_count;
   }
+
+  // generated contraction-program kernel for the two-kernel pipelines (NVRTC, cached cubins)
+  h->p4[0].unload();
+  h->p4[1].unload();
+  h->p4_note.clear();
+  if ((h->v2_entry >= 0 || h->v1_entry >= 0) && !getenv("MTP_B200_NO_P4")) {
+    if (h->v2_entry < 0) {
+      std::vector<short> none;
+      p4_slot_map(p, -1, none, h->slot_of_k, h->p4_nslots);
+    }
+    for (int shape = 0; shape < 2; shape++) {
+      try {
+        const P4Choice ch = p4_choose(p, smem_max, shape == 1);
+        if (!ch.ok) throw std::runtime_error("potential structure or size outside the generator's range");
+        if (shape == 1 && h->p4[0].loaded() && ch.prm.na == h->p4[0].choice.prm.na) continue;    // same kernel
+        P4Module &m = h->p4[shape];
+        const std::vector<char> cubin = p4_cubin(p, ch, h->slot_of_k.data(), h->p4_nslots, m.info);
+        m.choice = ch;
+        m.load(cubin, h->device, h->sm_count);
+      } catch (const std::exception &e) {
+        h->p4[shape].unload();
+        if (shape == 0) h->p4_note = e.what();
+        if (getenv("MTP_B200_P4_REQUIRE")) throw;
+      }
+    }
+  } else
+    h->p4_note = "disabled";
 }
 
 // RAII span: records an event pair around the launches of one kernel class when profiling is on
@@ -649,7 +713,8 @@ int plan_chunk(const mtp_handle *h, int inum, bool grade)
         return x / a * y;
       };
       const long long um = (long long) h->v2_grid_m * 32, uf = (long long) h->v2_grid_fg[grade ? 1 : 0] * h->v2_ab;
-      const long long up = (long long) h->sm_count * (h->p3_na ? h->p3_na : std::max(1, h->pl_na[0]));
+      const long long up = h->p4[0].loaded() ? (long long) h->p4[0].grid_cap * h->p4[0].choice.prm.na
+                                             : (long long) h->sm_count * (h->p3_na ? h->p3_na : std::max(1, h->pl_na[0]));
       long long unit = 0;
       if (um > 0 && uf > 0) {
         unit = lcm(um, uf);
@@ -761,6 +826,7 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
   int na = 1, lna = 0, grid_p_cap = 1;
   size_t smem_p = 0;
   P3Kernel p3 = nullptr;
+  const P4Module *p4m = nullptr;
   if (pipeline) {
     // throughput shape unless the system is too small to give every SM a chunk (or the latency variant is asked for)
     const int nfirst = std::min(chunk, std::max(a.inum, 1));
@@ -800,8 +866,15 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
     }
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, p3 ? P3_THREADS : PROG_THREADS, smem_p));
     grid_p_cap = std::max(1, per_sm) * h->sm_count;
+    // the generated kernel of this potential, when it was built: latency shape for small systems if there is one
+    p4m = (small && h->p4[1].loaded()) ? &h->p4[1] : (h->p4[0].loaded() ? &h->p4[0] : nullptr);
+    if (p4m) {
+      p3 = nullptr;
+      na = p4m->choice.prm.na;
+      grid_p_cap = p4m->grid_cap;
+    }
   }
-  h->last_path = (use_v2 ? 2 : pipeline ? 1 : 0) | (p3 ? 16 : 0) | (na << 8);
+  h->last_path = (use_v2 ? 2 : pipeline ? 1 : 0) | (p3 ? 16 : 0) | (p4m ? 32 : 0) | (na << 8);
   const int rows_per_super = pipeline ? grid_p_cap + std::max(h->pl_grid_f[gi], h->v2_grid_f) : h->grid_cap[gi];
   h->d_partials.ensure((size_t) nsuper * rows_per_super * 8);
   int rows_used = 0;
@@ -809,6 +882,30 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
     CUDA_CHECK(cudaEventRecord(h->ev_fork, st));
     for (int l = 0; l < nlanes; l++) CUDA_CHECK(cudaStreamWaitEvent(h->lanes[l].stream, h->ev_fork, 0));
   }
+
+  auto launch_p4 = [&](const SiteArgs &sa, const double *mbp, double *gbp, double *part, int grid, cudaStream_t ls) {
+    P4Args pa{};
+    pa.mb = mbp;
+    pa.gb = gbp;
+    pa.ld = ld;
+    pa.inum = sa.inum;
+    pa.first_ii = sa.first_ii;
+    pa.ilist = sa.ilist;
+    pa.xt = sa.xt;
+    pa.lin = d.lin;
+    pa.species = d.species;
+    pa.S = d.S;
+    pa.eflag_global = sa.eflag_global;
+    pa.eflag_atom = sa.eflag_atom;
+    pa.grade = grade ? 1 : 0;
+    pa.eatom = sa.eatom;
+    pa.cand_rows = sa.cand_rows;
+    pa.cand_ld = sa.cand_ld;
+    pa.cand_col0 = d.S * d.S * d.R * d.B + d.S;
+    pa.partials = part;
+    void *kargs[] = {&pa};
+    CUDA_CHECK(cudaLaunchKernel((const void *) p4m->kernel, dim3(grid), dim3(p4m->info.threads), kargs, p4m->info.smem_bytes, ls));
+  };
 
   for (int sc = 0; sc < nsuper; sc++) {
     const int first = sc * chunk;
@@ -845,7 +942,9 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
       double *part_p = h->d_partials.p + (size_t) rows_used * 8;
       {
         ProfSpan sp(h, MTP_PROF_PROGRAM, ls);
-        if (p3) p3<<<gp, P3_THREADS, smem_p, ls>>>(d, s, h->f3f, h->f3r, L.mb.p, L.gb.p, ld, part_p);
+        if (p4m) launch_p4(s, L.mb.p, L.gb.p, part_p, gp, ls);
+        else if (p3)
+          p3<<<gp, P3_THREADS, smem_p, ls>>>(d, s, h->f3f, h->f3r, L.mb.p, L.gb.p, ld, part_p);
         else if (grade)
           mtp_program_kernel<true><<<gp, PROG_THREADS, smem_p, ls>>>(d, s, L.mb.p, L.gb.p, ld, na, lna, part_p);
         else
@@ -882,7 +981,9 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
       double *part_p = h->d_partials.p + (size_t) rows_used * 8;
       {
         ProfSpan sp(h, MTP_PROF_PROGRAM, st);
-        if (p3) p3<<<gp, P3_THREADS, smem_p, st>>>(d, s, h->f3f, h->f3r, h->d_mb.p, h->d_gb.p, ld, part_p);
+        if (p4m) launch_p4(s, h->d_mb.p, h->d_gb.p, part_p, gp, st);
+        else if (p3)
+          p3<<<gp, P3_THREADS, smem_p, st>>>(d, s, h->f3f, h->f3r, h->d_mb.p, h->d_gb.p, ld, part_p);
         else if (grade)
           mtp_program_kernel<true><<<gp, PROG_THREADS, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, lna, part_p);
         else
@@ -1018,6 +1119,61 @@ int mtp_program_check(const char *path, int atoms_per_cta, double *max_rel_err_o
 
 int mtp_last_kernel_path(const mtp_handle *h) { return h ? h->last_path : -1; }
 
+const char *mtp_program_kernel_note(const mtp_handle *h) { return h ? h->p4_note.c_str() : ""; }
+
+namespace {
+// host-only: the generator inputs mtp_create would use for the potential at `path`
+void p4_host_plan(const char *path, int latency_shape, Potential &p, P4Choice &ch, std::vector<short> &slot_of_k, int &nslots)
+{
+  parse_almtp(path, false, p);
+  Program prog;
+  compile_program(p, prog);    // validates the table (topological order)
+  std::vector<short> s2k;
+  const int e = v2_entry_for(p, s2k);
+  p4_slot_map(p, e, s2k, slot_of_k, nslots);
+  ch = p4_choose(p, kSm100SmemOptin, latency_shape != 0);
+  if (!ch.ok) throw std::runtime_error("potential structure or size outside the generator's range");
+}
+}    // namespace
+
+int mtp_codegen_source(const char *path, int latency_shape, char *buf, long long cap, long long *needed, long long *info_out)
+{
+  if (!path || !needed) return fail(MTP_ERR_ARG, "null argument");
+  return guarded([&] {
+    Potential p;
+    P4Choice ch;
+    std::vector<short> slot_of_k;
+    int nslots = 0;
+    p4_host_plan(path, latency_shape, p, ch, slot_of_k, nslots);
+    std::string src, why;
+    P4Info info;
+    if (!p4_generate(p, ch.prm, slot_of_k.data(), nslots, src, info, why)) throw std::runtime_error(why);
+    *needed = (long long) src.size() + 1;
+    if (buf && cap >= *needed) memcpy(buf, src.c_str(), src.size() + 1);
+    if (info_out) {
+      const long long v[12] = {ch.prm.na, ch.prm.warps, ch.min_blocks, info.rows, info.stages, (long long) info.smem_bytes, info.terms,
+                               info.loads, info.stores, info.crit_terms, nslots, (long long) info.hash};
+      memcpy(info_out, v, sizeof(v));
+    }
+  });
+}
+
+int mtp_codegen_prebuild(const char *path, int latency_shape, int *compiled_out)
+{
+  if (!path) return fail(MTP_ERR_ARG, "null argument");
+  return guarded([&] {
+    Potential p;
+    P4Choice ch;
+    std::vector<short> slot_of_k;
+    int nslots = 0;
+    p4_host_plan(path, latency_shape, p, ch, slot_of_k, nslots);
+    P4Info info;
+    bool compiled = false;
+    p4_cubin(p, ch, slot_of_k.data(), nslots, info, &compiled);
+    if (compiled_out) *compiled_out = compiled ? 1 : 0;
+  });
+}
+
 /* diagnostic builds only (-DMTP_PHASE_CLOCKS): per-phase SM clocks summed over warps, then reset */
 int mtp_debug_phase_clocks(unsigned long long *out8)
 {
@@ -1132,6 +1288,8 @@ void mtp_destroy(mtp_handle *h)
 {
   if (!h) return;
   cudaSetDevice(h->device);
+  h->p4[0].unload();
+  h->p4[1].unload();
   if (h->hstream) cudaStreamDestroy(h->hstream);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (auto &L : h->lanes) {

@@ -1,0 +1,723 @@
+// Generator of the per-potential contraction-program kernel (see mtp_codegen.hpp).
+#include "mtp_codegen.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <unordered_map>
+
+namespace mtpb200 {
+
+namespace {
+
+struct Edge {
+  int a0, a1, c;
+};
+struct RevTerm {
+  int other, coef;    // g[n] += coef * g[t] * m[other]
+};
+struct RevPair {
+  int t;
+  std::vector<RevTerm> terms;
+};
+
+struct Analysis {
+  int K = 0, M = 0, T = 0, A = 0;
+  std::vector<std::vector<Edge>> in;        // per target node: its products, file order
+  std::vector<std::vector<RevPair>> out;    // per node: consumers grouped by target, ascending target
+  std::vector<int> scalar;                  // index into linear_coeffs, or -1
+  std::vector<char> operand, target;
+  std::vector<int> mrow, grow;              // shared-memory row of m[n] / g[n], or -1
+  std::vector<int> fstage, rstage;          // stage of the forward / reverse task of node n, or -1
+  int m_rows = 0, g_rows = 0, nstages = 0;
+  long long terms = 0;
+};
+
+bool analyse(const Potential &p, Analysis &an, std::string &why)
+{
+  an.K = p.alpha_index_basic_count;
+  an.M = p.alpha_moment_count;
+  an.T = p.alpha_index_times_count;
+  an.A = p.alpha_scalar_count;
+  const int K = an.K, M = an.M, T = an.T;
+  an.in.assign(M, {});
+  an.out.assign(M, {});
+  an.scalar.assign(M, -1);
+  an.operand.assign(M, 0);
+  an.target.assign(M, 0);
+  const int *tm = p.alpha_index_times.data();
+  for (int e = 0; e < T; e++) {
+    const int a0 = tm[4 * e], a1 = tm[4 * e + 1], c = tm[4 * e + 2], t = tm[4 * e + 3];
+    if (t < K) {
+      why = "a basic moment is the target of a product";
+      return false;
+    }
+    an.in[t].push_back({a0, a1, c});
+    an.operand[a0] = an.operand[a1] = 1;
+    an.target[t] = 1;
+  }
+  for (int s = 0; s < an.A; s++) {
+    const int n = p.alpha_moment_mapping[s];
+    if (an.scalar[n] >= 0) {
+      why = "alpha_moment_mapping lists a moment twice";
+      return false;
+    }
+    an.scalar[n] = s;
+  }
+  // consumers of every node, grouped by target; a square m[a]*m[a] feeds its source twice (pair_mtp.cpp:229-232)
+  for (int t = K; t < M; t++)
+    for (const Edge &e : an.in[t]) {
+      auto add = [&](int n, int other, int coef) {
+        auto &v = an.out[n];
+        if (v.empty() || v.back().t != t) v.push_back({t, {}});
+        for (auto &rt : v.back().terms)
+          if (rt.other == other) {
+            rt.coef += coef;
+            return;
+          }
+        v.back().terms.push_back({other, coef});
+      };
+      if (e.a0 == e.a1) add(e.a0, e.a0, 2 * e.c);
+      else {
+        add(e.a0, e.a1, e.c);
+        add(e.a1, e.a0, e.c);
+      }
+    }
+  for (int n = 0; n < M; n++)
+    std::sort(an.out[n].begin(), an.out[n].end(), [](const RevPair &x, const RevPair &y) { return x.t < y.t; });
+  // (targets are visited in ascending order above, so the sort is a no-op for sorted files; kept for safety)
+  // rows
+  an.mrow.assign(M, -1);
+  an.grow.assign(M, -1);
+  int r = 0;
+  for (int n = 0; n < K; n++) an.mrow[n] = r++;
+  for (int n = K; n < M; n++)
+    if (an.operand[n]) an.mrow[n] = r++;
+  an.m_rows = r;
+  int g = 0;
+  for (int n = K; n < M; n++)
+    if (an.operand[n]) an.grow[n] = r + g++;
+  an.g_rows = g;
+  // stages.  m of a basic moment is available in stage 0; a value stored in stage s is visible from stage s + 1
+  an.fstage.assign(M, -1);
+  an.rstage.assign(M, -1);
+  for (int pass = 0; pass < M + 2; pass++) {
+    bool changed = false;
+    for (int t = K; t < M; t++) {
+      if (!an.target[t]) continue;
+      int s = 0;
+      for (const Edge &e : an.in[t])
+        for (int a : {e.a0, e.a1})
+          if (a >= K) {
+            if (!an.target[a]) continue;    // never written: stays 0
+            s = std::max(s, an.fstage[a] < 0 ? 0 : an.fstage[a] + 1);
+          }
+      if (s != an.fstage[t]) {
+        an.fstage[t] = s;
+        changed = true;
+      }
+    }
+    if (!changed) break;
+    if (pass == M + 1) {
+      why = "alpha_index_times has a dependency cycle";
+      return false;
+    }
+  }
+  for (int pass = 0; pass < M + 2; pass++) {
+    bool changed = false;
+    for (int n = M - 1; n >= 0; n--) {
+      if (n >= K && !an.operand[n]) continue;
+      int s = 0;
+      for (const RevPair &rp : an.out[n]) {
+        if (an.operand[rp.t]) s = std::max(s, an.rstage[rp.t] < 0 ? 0 : an.rstage[rp.t] + 1);
+        for (const RevTerm &rt : rp.terms)
+          if (rt.other >= K && an.target[rt.other]) s = std::max(s, an.fstage[rt.other] + 1);
+      }
+      if (s != an.rstage[n]) {
+        an.rstage[n] = s;
+        changed = true;
+      }
+    }
+    if (!changed) break;
+    if (pass == M + 1) {
+      why = "alpha_index_times has a dependency cycle";
+      return false;
+    }
+  }
+  an.nstages = 1;
+  for (int n = 0; n < M; n++) an.nstages = std::max(an.nstages, std::max(an.fstage[n], an.rstage[n]) + 1);
+  an.terms = 0;
+  for (int t = K; t < M; t++) an.terms += (long long) an.in[t].size();
+  for (int n = 0; n < M; n++)
+    for (const RevPair &rp : an.out[n]) an.terms += (long long) rp.terms.size();
+  return true;
+}
+
+struct Task {
+  int kind;    // 0 forward, 1 reverse, 2 energy of a basic moment that is a basis function
+  int node;
+  int cost;
+};
+
+// ---- emission with a register cache decided at generation time -------------------------------------------
+struct Emitter {
+  bool record = true;
+  int capacity = 48;
+  std::vector<int> seq;                 // recorded key sequence
+  std::vector<int> next_use;            // per position: next position of the same key, or INT_MAX
+  size_t pos = 0;
+  std::unordered_map<int, std::pair<std::string, int>> live;    // key -> (variable, next use)
+  std::string *out = nullptr;
+  int nvar = 0;
+  int uniform_base = 0;                 // keys >= uniform_base are uniform scalars (LIN)
+  long long loads = 0;
+
+  void begin_emit()
+  {
+    record = false;
+    next_use.assign(seq.size(), 0x7fffffff);
+    std::unordered_map<int, int> last;
+    for (int i = (int) seq.size() - 1; i >= 0; i--) {
+      auto it = last.find(seq[i]);
+      if (it != last.end()) next_use[i] = it->second;
+      last[seq[i]] = i;
+    }
+    pos = 0;
+    live.clear();
+  }
+  // returns the expression (a variable name) holding row / uniform `key`
+  std::string use(int key)
+  {
+    if (record) {
+      seq.push_back(key);
+      return "";
+    }
+    const int nu = next_use[pos++];
+    auto it = live.find(key);
+    if (it != live.end()) {
+      it->second.second = nu;
+      std::string name = it->second.first;
+      if (nu == 0x7fffffff) live.erase(it);    // dead after this use
+      return name;
+    }
+    char name[32];
+    if (key >= uniform_base) {
+      snprintf(name, sizeof(name), "u%d", nvar++);
+      *out += std::string("  const double ") + name + " = LIN(" + std::to_string(key - uniform_base) + ");\n";
+    } else {
+      snprintf(name, sizeof(name), "v%d", nvar++);
+      *out += std::string("  const T_ ") + name + " = LD(" + std::to_string(key) + ");\n";
+      loads++;
+    }
+    if (nu != 0x7fffffff) {
+      if ((int) live.size() >= capacity) {    // Belady: drop the value whose next use is farthest away
+        auto worst = live.begin();
+        for (auto j = live.begin(); j != live.end(); ++j)
+          if (j->second.second > worst->second.second) worst = j;
+        live.erase(worst);
+      }
+      live[key] = {name, nu};
+    }
+    return name;
+  }
+  void line(const std::string &s)
+  {
+    if (!record) *out += s;
+  }
+};
+
+std::string kdouble(int c)
+{
+  char b[32];
+  snprintf(b, sizeof(b), "%d.0", c);
+  return b;
+}
+
+// forward evaluation of target t (pair_mtp.cpp:196-201)
+void emit_forward(const Analysis &an, int t, Emitter &E, int &ntmp, long long &stores)
+{
+  std::map<int, std::vector<Edge>> by_coef;
+  for (const Edge &e : an.in[t]) by_coef[e.c].push_back(e);
+  const std::string acc = "a" + std::to_string(ntmp++);
+  bool have = false;
+  E.line("  T_ " + acc + ";\n");
+  auto group = [&](int c, const std::vector<Edge> &es) {
+    if (c == 1) {
+      for (const Edge &e : es) {
+        const std::string x0 = E.use(an.mrow[e.a0]), x1 = E.use(an.mrow[e.a1]);
+        E.line("  " + acc + " = " + (have ? "FMA(" + x0 + ", " + x1 + ", " + acc + ")" : "MUL(" + x0 + ", " + x1 + ")") + ";\n");
+        have = true;
+      }
+    } else if (es.size() == 1) {
+      const Edge &e = es[0];
+      const std::string x0 = E.use(an.mrow[e.a0]), x1 = E.use(an.mrow[e.a1]);
+      E.line("  " + acc + " = " + (have ? "FMA(MULK(" + kdouble(c) + ", " + x0 + "), " + x1 + ", " + acc + ")"
+                                        : "MUL(MULK(" + kdouble(c) + ", " + x0 + "), " + x1 + ")") + ";\n");
+      have = true;
+    } else {
+      const std::string pv = "p" + std::to_string(ntmp++);
+      bool hp = false;
+      E.line("  T_ " + pv + ";\n");
+      for (const Edge &e : es) {
+        const std::string x0 = E.use(an.mrow[e.a0]), x1 = E.use(an.mrow[e.a1]);
+        E.line("  " + pv + " = " + (hp ? "FMA(" + x0 + ", " + x1 + ", " + pv + ")" : "MUL(" + x0 + ", " + x1 + ")") + ";\n");
+        hp = true;
+      }
+      E.line("  " + acc + " = " + (have ? "FMAK(" + kdouble(c) + ", " + pv + ", " + acc + ")" : "MULK(" + kdouble(c) + ", " + pv + ")") + ";\n");
+      have = true;
+    }
+  };
+  auto one = by_coef.find(1);
+  if (one != by_coef.end()) group(1, one->second);
+  for (const auto &kv : by_coef)
+    if (kv.first != 1) group(kv.first, kv.second);
+  if (!have) E.line("  " + acc + " = ZERO;\n");
+  if (an.mrow[t] >= 0) {
+    E.line("  ST(" + std::to_string(an.mrow[t]) + ", " + acc + ");\n");
+    if (!E.record) stores++;
+  }
+  if (an.scalar[t] >= 0) E.line("  ESC(" + std::to_string(an.scalar[t]) + ", " + acc + ");\n");
+}
+
+// reverse-mode gather of the adjoints of `nodes` (pair_mtp.cpp:217-233 regrouped by source node)
+void emit_reverse_block(const Analysis &an, const std::vector<int> &nodes, const short *slot_of_k, Emitter &E, int &ntmp,
+                        long long &stores)
+{
+  struct Item {
+    int t, i;
+    const RevPair *rp;
+  };
+  std::vector<Item> items;
+  std::vector<std::string> acc(nodes.size());
+  std::vector<char> have(nodes.size(), 0);
+  for (size_t i = 0; i < nodes.size(); i++) {
+    const int n = nodes[i];
+    acc[i] = "a" + std::to_string(ntmp++);
+    if (an.scalar[n] >= 0) {    // g[map[s]] = xi_s  (pair_mtp.cpp:217-218)
+      const std::string u = E.use(E.uniform_base + an.scalar[n]);
+      E.line("  T_ " + acc[i] + " = SPLAT(" + u + ");\n");
+      have[i] = 1;
+    } else
+      E.line("  T_ " + acc[i] + ";\n");
+    for (const RevPair &rp : an.out[n]) {
+      const bool variable = an.operand[rp.t] != 0;
+      if (!variable && an.scalar[rp.t] < 0) continue;    // the consumer's adjoint is identically zero
+      items.push_back({rp.t, (int) i, &rp});
+    }
+  }
+  std::stable_sort(items.begin(), items.end(), [](const Item &x, const Item &y) { return x.t < y.t; });
+  for (const Item &it : items) {
+    const bool variable = an.operand[it.t] != 0;
+    const std::string g = variable ? E.use(an.grow[it.t]) : E.use(E.uniform_base + an.scalar[it.t]);
+    const std::string fma = variable ? "FMA(" : "FMAU(", mul = variable ? "MUL(" : "MULU(";
+    std::vector<RevTerm> ts = it.rp->terms;
+    std::stable_sort(ts.begin(), ts.end(), [](const RevTerm &x, const RevTerm &y) { return (x.coef != 1) < (y.coef != 1); });
+    std::string s;
+    if (ts.size() == 1) {
+      const std::string m = E.use(an.mrow[ts[0].other]);
+      s = ts[0].coef == 1 ? m : "MULK(" + kdouble(ts[0].coef) + ", " + m + ")";
+    } else {
+      s = "p" + std::to_string(ntmp++);
+      bool hs = false;
+      E.line("  T_ " + s + ";\n");
+      for (const RevTerm &rt : ts) {
+        const std::string m = E.use(an.mrow[rt.other]);
+        if (!hs) E.line("  " + s + " = " + (rt.coef == 1 ? m : "MULK(" + kdouble(rt.coef) + ", " + m + ")") + ";\n");
+        else if (rt.coef == 1)
+          E.line("  " + s + " = ADD(" + s + ", " + m + ");\n");
+        else
+          E.line("  " + s + " = FMAK(" + kdouble(rt.coef) + ", " + m + ", " + s + ");\n");
+        hs = true;
+      }
+    }
+    const std::string &a = acc[it.i];
+    E.line("  " + a + " = " + (have[it.i] ? fma + g + ", " + s + ", " + a + ")" : mul + g + ", " + s + ")") + ";\n");
+    have[it.i] = 1;
+  }
+  for (size_t i = 0; i < nodes.size(); i++) {
+    const int n = nodes[i];
+    if (!have[i]) E.line("  " + acc[i] + " = ZERO;\n");
+    if (n < an.K) E.line("  GBST(" + std::to_string(slot_of_k ? (int) slot_of_k[n] : n) + ", " + acc[i] + ");\n");
+    else
+      E.line("  ST(" + std::to_string(an.grow[n]) + ", " + acc[i] + ");\n");
+    if (!E.record) stores++;
+  }
+}
+
+unsigned long long fnv(unsigned long long h, const void *data, size_t n)
+{
+  const unsigned char *b = (const unsigned char *) data;
+  for (size_t i = 0; i < n; i++) {
+    h ^= b[i];
+    h *= 1099511628211ULL;
+  }
+  return h;
+}
+
+const char *kGeneratorVersion = "p4-r2-03";
+
+// ---- fixed text: device prelude and kernel skeleton ------------------------------------------------------
+const char *kDevicePrelude = R"P4(
+#ifndef P4_HOST
+struct P4Args {
+  const double *mb;
+  double *gb;
+  long long ld;
+  int inum, first_ii;
+  const int *ilist;
+  const void *xt;
+  const double *lin, *species;
+  int S;
+  int eflag_global, eflag_atom, grade;
+  double *eatom;
+  double *cand_rows;
+  long long cand_ld;
+  int cand_col0;
+  double *partials;
+};
+#define P4_FN __device__ __forceinline__
+#define P4_STAGE_FN __device__ __noinline__
+#define P4_TABLE __device__ const
+#if P4_APL == 1
+typedef double T_;
+struct P4Ctx {
+  double *S;
+  const double *lin;
+  double *gb, *cand;
+  long long ld;
+  T_ e;
+  bool valid;
+  int grade;
+};
+#define LD(r) (x.S[(r) * P4_NA])
+#define ST(r, v) (x.S[(r) * P4_NA] = (v))
+#define LIN(s) (x.lin[s])
+#define MUL(a, b) ((a) * (b))
+#define ADD(a, b) ((a) + (b))
+#define FMA(a, b, c) fma((a), (b), (c))
+#define MULK(k, a) ((k) * (a))
+#define FMAK(k, a, c) fma((k), (a), (c))
+#define MULU(u, a) ((u) * (a))
+#define FMAU(u, a, c) fma((u), (a), (c))
+#define SPLAT(u) (u)
+#define ZERO 0.0
+#define GBST(slot, v) do { if (x.valid) x.gb[(long long) (slot) * x.ld] = (v); } while (0)
+#define ESC(s, v) do { x.e = fma(x.lin[s], (v), x.e); if (x.grade && x.valid) x.cand[s] = (v); } while (0)
+#else
+struct T_ {
+  double x, y;
+};
+struct P4Ctx {
+  double *S;
+  const double *lin;
+  double *gb, *cand;
+  long long ld, cand_ld;
+  T_ e;
+  bool valid, valid1;
+  int grade;
+};
+P4_FN T_ p4_ld(const double *p) { const double2 v = *reinterpret_cast<const double2 *>(p); T_ r; r.x = v.x; r.y = v.y; return r; }
+P4_FN void p4_st(double *p, T_ v) { *reinterpret_cast<double2 *>(p) = make_double2(v.x, v.y); }
+P4_FN T_ p4_mul(T_ a, T_ b) { T_ r; r.x = a.x * b.x; r.y = a.y * b.y; return r; }
+P4_FN T_ p4_add(T_ a, T_ b) { T_ r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+P4_FN T_ p4_fma(T_ a, T_ b, T_ c) { T_ r; r.x = fma(a.x, b.x, c.x); r.y = fma(a.y, b.y, c.y); return r; }
+P4_FN T_ p4_mulu(double u, T_ a) { T_ r; r.x = u * a.x; r.y = u * a.y; return r; }
+P4_FN T_ p4_fmau(double u, T_ a, T_ c) { T_ r; r.x = fma(u, a.x, c.x); r.y = fma(u, a.y, c.y); return r; }
+P4_FN T_ p4_splat(double u) { T_ r; r.x = u; r.y = u; return r; }
+#define LD(r) p4_ld(x.S + (r) * P4_NA)
+#define ST(r, v) p4_st(x.S + (r) * P4_NA, (v))
+#define LIN(s) (x.lin[s])
+#define MUL(a, b) p4_mul((a), (b))
+#define ADD(a, b) p4_add((a), (b))
+#define FMA(a, b, c) p4_fma((a), (b), (c))
+#define MULK(k, a) p4_mulu((k), (a))
+#define FMAK(k, a, c) p4_fmau((k), (a), (c))
+#define MULU(u, a) p4_mulu((u), (a))
+#define FMAU(u, a, c) p4_fmau((u), (a), (c))
+#define SPLAT(u) p4_splat(u)
+#define ZERO p4_splat(0.0)
+#define GBST(slot, v) do { const T_ v_ = (v); double *q_ = x.gb + (long long) (slot) * x.ld; \
+    if (x.valid1) *reinterpret_cast<double2 *>(q_) = make_double2(v_.x, v_.y); else if (x.valid) *q_ = v_.x; } while (0)
+#define ESC(s, v) do { const T_ v_ = (v); x.e = p4_fmau(x.lin[s], v_, x.e); \
+    if (x.grade) { if (x.valid) x.cand[s] = v_.x; if (x.valid1) x.cand[x.cand_ld + (s)] = v_.y; } } while (0)
+#endif
+#endif
+)P4";
+
+const char *kKernel = R"P4(
+#ifndef P4_HOST
+extern "C" __global__ void __launch_bounds__(P4_W * 32, P4_MINB) mtp_program_p4(const P4Args a)
+{
+  extern __shared__ __align__(16) double S[];
+  double *s_lin = S + (size_t) P4_ROWS * P4_NA;
+  double *epart = s_lin + ((P4_A + 1) & ~1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int t = tid; t < P4_A; t += P4_W * 32) s_lin[t] = a.lin[t];
+  const int al = (P4_APL * lane) % P4_NA;        // first atom of this lane within the chunk
+  const bool owner = P4_APL * lane < P4_NA;      // lanes beyond the chunk width repeat the work of another lane, never write
+  double e_thread = 0.0;
+  __syncthreads();
+  for (int chunk0 = blockIdx.x * P4_NA; chunk0 < a.inum; chunk0 += gridDim.x * P4_NA) {
+    const int na = min(P4_NA, a.inum - chunk0);
+    // basic moments of the chunk -> rows 0 .. K-1 (16-byte cp.async, zero fill past the end of the list)
+    for (int t = tid; t < P4_K * (P4_NA / 2); t += P4_W * 32) {
+      const int k = t / (P4_NA / 2), c = (t % (P4_NA / 2)) * 2;
+      const int nb = max(0, min(2, na - c)) * 8;
+      const unsigned dst = (unsigned) __cvta_generic_to_shared(S + k * P4_NA + c);
+      const double *src = a.mb + (long long) p4_slot_of_k[k] * a.ld + chunk0 + (nb ? c : 0);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(nb));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+    P4Ctx x;
+    x.S = S + al;
+    x.lin = s_lin;
+    x.ld = a.ld;
+    x.gb = a.gb + chunk0 + al;
+    x.valid = owner && al < na;
+    x.grade = a.grade;
+    x.cand = a.grade ? a.cand_rows + (long long) (chunk0 + al) * a.cand_ld + a.cand_col0 : nullptr;
+#if P4_APL == 2
+    x.valid1 = owner && al + 1 < na;
+    x.cand_ld = a.cand_ld;
+    x.e.x = x.e.y = 0.0;
+#else
+    x.e = 0.0;
+#endif
+#pragma unroll 1
+    for (int st = 0; st < P4_NSTAGE; st++) {
+      p4_run_stage(st, warp, x);
+      __syncthreads();
+    }
+    for (int t = tid; t < P4_NZERO * P4_NA; t += P4_W * 32) {    // rows of gb that no basic moment owns
+      const int c = t % P4_NA;
+      if (c < na) a.gb[(long long) p4_zero_slot[t / P4_NA] * a.ld + chunk0 + c] = 0.0;
+    }
+    if (a.eflag_global || a.eflag_atom) {    // fixed-order sum over the warps, species term (pair_mtp.cpp:204-212)
+      if (owner) {
+#if P4_APL == 2
+        epart[warp * P4_NA + al] = x.e.x;
+        epart[warp * P4_NA + al + 1] = x.e.y;
+#else
+        epart[warp * P4_NA + al] = x.e;
+#endif
+      }
+      __syncthreads();
+      if (tid < na) {
+        const int i = a.ilist ? a.ilist[a.first_ii + chunk0 + tid] : a.first_ii + chunk0 + tid;
+        int itype = (int) *reinterpret_cast<const long long *>(reinterpret_cast<const char *>(a.xt) + 32 * (size_t) i + 24);
+        if (itype < 0 || itype >= a.S) itype = 0;
+        double es = 0.0;
+        for (int w = 0; w < P4_W; w++) es += epart[w * P4_NA + tid];
+        es += a.species[itype];
+        if (a.eflag_atom) a.eatom[i] = es;
+        if (a.eflag_global) e_thread += es;
+      }
+      __syncthreads();
+    }
+  }
+  // per-CTA energy partial, fixed order
+  if (tid < P4_NA) epart[tid] = e_thread;
+  __syncthreads();
+  if (tid < 8) {
+    double s = 0.0;
+    if (tid == 0)
+      for (int t = 0; t < P4_NA && t < P4_W * 32; t++) s += epart[t];
+    a.partials[(size_t) blockIdx.x * 8 + tid] = s;
+  }
+}
+#endif
+)P4";
+
+struct Plan {
+  Analysis an;
+  std::vector<std::vector<std::vector<Task>>> work;    // [stage][warp] -> tasks in order
+};
+
+bool make_plan(const Potential &p, const P4Params &prm, Plan &pl, std::string &why)
+{
+  if (!(prm.na == 8 || prm.na == 16 || prm.na == 32 || prm.na == 64) || prm.warps < 1 || prm.warps > 32 || prm.warps * 32 < prm.na) {
+    why = "bad generator parameters";
+    return false;
+  }
+  if (!analyse(p, pl.an, why)) return false;
+  const Analysis &an = pl.an;
+  pl.work.assign(an.nstages, std::vector<std::vector<Task>>(prm.warps));
+  for (int st = 0; st < an.nstages; st++) {
+    std::vector<Task> tasks;
+    if (st == 0)
+      for (int n = 0; n < an.K; n++)
+        if (an.scalar[n] >= 0) tasks.push_back({2, n, 2});
+    for (int n = an.K; n < an.M; n++)
+      if (an.target[n] && an.fstage[n] == st && (an.operand[n] || an.scalar[n] >= 0))
+        tasks.push_back({0, n, (int) an.in[n].size() + 2});
+    for (int n = 0; n < an.M; n++)
+      if ((n < an.K || an.operand[n]) && an.rstage[n] == st) {
+        int c = 2;
+        for (const RevPair &rp : an.out[n]) c += (int) rp.terms.size() + 1;
+        tasks.push_back({1, n, c});
+      }
+    long long total = 0;
+    for (const Task &t : tasks) total += t.cost;
+    long long run = 0;
+    for (const Task &t : tasks) {    // contiguous runs of (almost) equal cost
+      int w = total > 0 ? (int) ((run + t.cost / 2) * prm.warps / total) : 0;
+      w = std::min(w, prm.warps - 1);
+      pl.work[st][w].push_back(t);
+      run += t.cost;
+    }
+  }
+  return true;
+}
+
+size_t smem_of(const Analysis &an, const P4Params &prm)
+{
+  return ((size_t) (an.m_rows + an.g_rows) * prm.na + (size_t) ((an.A + 1) & ~1) + (size_t) prm.warps * prm.na) * 8;
+}
+
+}    // namespace
+
+size_t p4_smem_bytes(const Potential &p, const P4Params &prm)
+{
+  Analysis an;
+  std::string why;
+  if (!analyse(p, an, why)) return 0;
+  return smem_of(an, prm);
+}
+
+bool p4_generate(const Potential &p, const P4Params &prm, const short *slot_of_k, int nslots, std::string &src, P4Info &info,
+                 std::string &why)
+{
+  Plan pl;
+  if (!make_plan(p, prm, pl, why)) return false;
+  const Analysis &an = pl.an;
+  const int K = an.K, rows = an.m_rows + an.g_rows;
+  info = P4Info();
+  info.rows = rows;
+  info.m_rows = an.m_rows;
+  info.g_rows = an.g_rows;
+  info.stages = an.nstages;
+  info.smem_bytes = smem_of(an, prm);
+  info.terms = an.terms;
+  info.threads = prm.warps * 32;
+
+  unsigned long long h = 1469598103934665603ULL;
+  h = fnv(h, kGeneratorVersion, strlen(kGeneratorVersion));
+  const int hdr[10] = {K, an.M, an.T, an.A, prm.na, prm.warps, prm.cache, prm.acc_max, nslots, prm.fn_cost};
+  h = fnv(h, hdr, sizeof(hdr));
+  h = fnv(h, p.alpha_index_times.data(), p.alpha_index_times.size() * sizeof(int));
+  h = fnv(h, p.alpha_moment_mapping.data(), p.alpha_moment_mapping.size() * sizeof(int));
+  if (slot_of_k) h = fnv(h, slot_of_k, (size_t) K * sizeof(short));
+  info.hash = h;
+
+  const int apl = prm.na == 64 ? 2 : 1;
+  src.clear();
+  src.reserve((size_t) 64 * 1024 + (size_t) an.terms * 96);
+  char buf[512];
+  snprintf(buf, sizeof(buf),
+           "// generated by mtp_codegen (%s): contraction program of one potential structure, K=%d M=%d T=%d A=%d\n"
+           "#define P4_NA %d\n#define P4_APL %d\n#define P4_W %d\n#define P4_ROWS %d\n#define P4_MROWS %d\n#define P4_K %d\n"
+           "#define P4_A %d\n#define P4_M %d\n#define P4_NSTAGE %d\n#define P4_NSLOTS %d\n#ifndef P4_MINB\n#define P4_MINB 1\n#endif\n",
+           kGeneratorVersion, K, an.M, an.T, an.A, prm.na, apl, prm.warps, rows, an.m_rows, K, an.A, an.M, an.nstages, nslots);
+  src += buf;
+  src += kDevicePrelude;
+  // tables
+  std::vector<char> slot_used((size_t) std::max(nslots, 1), 0);
+  src += "P4_TABLE short p4_slot_of_k[P4_K] = {";
+  for (int k = 0; k < K; k++) {
+    const int s = slot_of_k ? (int) slot_of_k[k] : k;
+    if (s < 0 || s >= nslots) {
+      why = "slot map out of range";
+      return false;
+    }
+    slot_used[s] = 1;
+    src += std::to_string(s) + (k + 1 < K ? "," : "");
+  }
+  src += "};\n";
+  std::vector<int> zero;
+  for (int s = 0; s < nslots; s++)
+    if (!slot_used[s]) zero.push_back(s);
+  src += "#define P4_NZERO " + std::to_string(zero.size()) + "\nP4_TABLE short p4_zero_slot[P4_NZERO + 1] = {";
+  for (int s : zero) src += std::to_string(s) + ",";
+  src += "0};\n";
+  // m-row of every node (host harness: lets the checker read back every stored moment); -1 = not stored
+  src += "#ifdef P4_HOST\nstatic const int p4_mrow[P4_M] = {";
+  for (int n = 0; n < an.M; n++) src += std::to_string(an.mrow[n]) + (n + 1 < an.M ? "," : "");
+  src += "};\n#endif\n";
+
+  // stage functions
+  std::vector<std::pair<int, int>> present;
+  for (int st = 0; st < an.nstages; st++) {
+    long long crit = 0;
+    for (int w = 0; w < prm.warps; w++) {
+      const std::vector<Task> &tasks = pl.work[st][w];
+      if (tasks.empty()) continue;
+      long long wt = 0;
+      for (const Task &t : tasks) wt += t.cost;
+      crit = std::max(crit, wt);
+      // a warp's share of a stage is emitted as a sequence of separately compiled (noinline) functions of bounded
+      // size: ptxas allocates registers per function, and its compile time is superlinear in the function length
+      size_t i = 0;
+      int part = 0;
+      while (i < tasks.size()) {
+        size_t j = i;
+        long long c = 0;
+        while (j < tasks.size() && (j == i || c + tasks[j].cost <= prm.fn_cost)) c += tasks[j++].cost;
+        Emitter E;
+        E.capacity = std::max(4, prm.cache);
+        E.uniform_base = rows;
+        std::string body;
+        E.out = &body;
+        for (int pass = 0; pass < 2; pass++) {
+          int ntmp = 0;
+          long long st_count = 0;
+          if (pass == 1) E.begin_emit();
+          size_t q = i;
+          while (q < j) {
+            const Task &t = tasks[q];
+            if (t.kind == 2) {
+              const std::string m = E.use(an.mrow[t.node]);
+              E.line("  ESC(" + std::to_string(an.scalar[t.node]) + ", " + m + ");\n");
+              q++;
+            } else if (t.kind == 0) {
+              emit_forward(an, t.node, E, ntmp, st_count);
+              q++;
+            } else {
+              std::vector<int> blk;
+              while (q < j && tasks[q].kind == 1 && (int) blk.size() < std::max(1, prm.acc_max)) blk.push_back(tasks[q++].node);
+              emit_reverse_block(an, blk, slot_of_k, E, ntmp, st_count);
+            }
+          }
+          if (pass == 1) info.stores += st_count;
+        }
+        info.loads += E.loads;
+        snprintf(buf, sizeof(buf), "P4_STAGE_FN void p4_s%d_w%d_%d(P4Ctx &x)\n{\n", st, w, part);
+        src += buf;
+        src += body;
+        src += "}\n";
+        present.push_back({st * prm.warps + w, part});
+        part++;
+        i = j;
+      }
+    }
+    info.crit_terms += crit;
+  }
+  src += "P4_FN void p4_run_stage(int stage, int warp, P4Ctx &x)\n{\n  switch (stage * P4_W + warp) {\n";
+  for (size_t q = 0; q < present.size();) {
+    const int key = present[q].first;
+    src += "    case " + std::to_string(key) + ":\n";
+    for (; q < present.size() && present[q].first == key; q++) {
+      snprintf(buf, sizeof(buf), "      p4_s%d_w%d_%d(x);\n", key / prm.warps, key % prm.warps, present[q].second);
+      src += buf;
+    }
+    src += "      break;\n";
+  }
+  src += "    default: break;\n  }\n}\n";
+  src += kKernel;
+  return true;
+}
+
+}    // namespace mtpb200

@@ -1,0 +1,175 @@
+// NVRTC compilation, cubin cache and module loading for the generated contraction-program kernel.
+#include "mtp_p4_runtime.hpp"
+
+#include <nvrtc.h>
+
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <stdexcept>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace mtpb200 {
+
+P4Choice p4_choose(const Potential &p, size_t smem_optin, bool latency_shape)
+{
+  P4Choice ch;
+  if (const char *e = getenv(latency_shape ? "MTP_B200_P4_SMALL" : "MTP_B200_P4")) {
+    int na = 0, w = 0, c = 0, acc = 0, mb = 0;
+    if (sscanf(e, "%d,%d,%d,%d,%d", &na, &w, &c, &acc, &mb) == 5) {
+      ch.prm.na = na;
+      ch.prm.warps = w;
+      ch.prm.cache = c;
+      ch.prm.acc_max = acc;
+      ch.min_blocks = mb;
+      const size_t b = p4_smem_bytes(p, ch.prm);
+      ch.ok = b > 0 && b <= smem_optin;
+      return ch;
+    }
+  }
+  // one SM has 228 KB of shared memory, 1 KB of which is reserved per resident CTA
+  const size_t two_ctas = (smem_optin + 1024) / 2 - 1024;
+  const int nas[3] = {32, 16, 8};
+  for (int i = latency_shape ? 2 : 0; i < 3; i++) {
+    P4Params prm;
+    prm.na = nas[i];
+    prm.warps = 4;
+    size_t b = p4_smem_bytes(p, prm);
+    if (b == 0) return ch;    // structure not supported
+    if (b <= two_ctas) {      // two CTAs of four warps per SM: each warp keeps a long run of the node order
+      ch.prm = prm;
+      ch.min_blocks = 2;
+      ch.ok = true;
+      return ch;
+    }
+    prm.warps = 8;
+    b = p4_smem_bytes(p, prm);
+    if (b <= smem_optin) {
+      ch.prm = prm;
+      ch.min_blocks = 1;
+      ch.ok = true;
+      return ch;
+    }
+  }
+  return ch;
+}
+
+std::string p4_cache_dir()
+{
+  if (const char *e = getenv("MTP_B200_KCACHE")) return e;
+  Dl_info di;
+  if (dladdr((const void *) &p4_cache_dir, &di) && di.dli_fname) {
+    std::string path = di.dli_fname;
+    const size_t slash = path.rfind('/');
+    if (slash != std::string::npos) return path.substr(0, slash) + "/kcache";
+  }
+  return "/tmp/mtp_b200_kcache";
+}
+
+namespace {
+
+std::string cache_file(const P4Info &info, const P4Choice &ch)
+{
+  char name[96];
+  snprintf(name, sizeof(name), "/p4_%016llx_b%d.cubin", info.hash, ch.min_blocks);
+  return p4_cache_dir() + name;
+}
+
+bool read_file(const std::string &path, std::vector<char> &out)
+{
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  const long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  out.resize(n > 0 ? (size_t) n : 0);
+  const bool ok = n > 0 && fread(out.data(), 1, (size_t) n, f) == (size_t) n;
+  fclose(f);
+  return ok;
+}
+
+void write_file_atomic(const std::string &path, const std::vector<char> &data)
+{
+  const std::string dir = path.substr(0, path.rfind('/'));
+  mkdir(dir.c_str(), 0755);    // best effort: an unwritable cache only costs a recompilation next time
+  const std::string tmp = path + ".tmp." + std::to_string((long) getpid());
+  FILE *f = fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  const bool ok = fwrite(data.data(), 1, data.size(), f) == data.size();
+  fclose(f);
+  if (!ok || rename(tmp.c_str(), path.c_str()) != 0) unlink(tmp.c_str());
+}
+
+std::vector<char> nvrtc_compile(const std::string &src, int min_blocks)
+{
+  nvrtcProgram prog;
+  if (nvrtcCreateProgram(&prog, src.c_str(), "mtp_program_p4.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+    throw std::runtime_error("nvrtcCreateProgram failed");
+  const std::string minb = "-DP4_MINB=" + std::to_string(min_blocks);
+  const char *opts[] = {"-arch=sm_100a", "-std=c++17", "-lineinfo", minb.c_str()};
+  const nvrtcResult rc = nvrtcCompileProgram(prog, 4, opts);
+  if (rc != NVRTC_SUCCESS) {
+    size_t n = 0;
+    nvrtcGetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    if (n) nvrtcGetProgramLog(prog, &log[0]);
+    nvrtcDestroyProgram(&prog);
+    throw std::runtime_error(std::string("NVRTC failed to compile the contraction-program kernel: ") + nvrtcGetErrorString(rc) + "\n" +
+                             log.substr(0, 2000));
+  }
+  size_t n = 0;
+  nvrtcGetCUBINSize(prog, &n);
+  std::vector<char> cubin(n);
+  if (n) nvrtcGetCUBIN(prog, cubin.data());
+  nvrtcDestroyProgram(&prog);
+  if (cubin.empty()) throw std::runtime_error("NVRTC produced no cubin for sm_100a");
+  return cubin;
+}
+
+}    // namespace
+
+std::vector<char> p4_cubin(const Potential &p, const P4Choice &ch, const short *slot_of_k, int nslots, P4Info &info, bool *compiled)
+{
+  std::string src, why;
+  if (compiled) *compiled = false;
+  if (!p4_generate(p, ch.prm, slot_of_k, nslots, src, info, why))
+    throw std::runtime_error("contraction-program generator: " + why);
+  const std::string path = cache_file(info, ch);
+  std::vector<char> cubin;
+  if (!getenv("MTP_B200_KCACHE_OFF") && read_file(path, cubin)) return cubin;
+  cubin = nvrtc_compile(src, ch.min_blocks);
+  if (compiled) *compiled = true;
+  if (!getenv("MTP_B200_KCACHE_OFF")) write_file_atomic(path, cubin);
+  return cubin;
+}
+
+#define P4_CUDA(expr)                                                                                              \
+  do {                                                                                                             \
+    cudaError_t e__ = (expr);                                                                                      \
+    if (e__ != cudaSuccess) throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(e__));          \
+  } while (0)
+
+void P4Module::load(const std::vector<char> &cubin, int device, int sm_count)
+{
+  unload();
+  P4_CUDA(cudaSetDevice(device));
+  P4_CUDA(cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+  P4_CUDA(cudaLibraryGetKernel(&kernel, lib, "mtp_program_p4"));
+  P4_CUDA(cudaFuncSetAttribute((const void *) kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) info.smem_bytes));
+  P4_CUDA(cudaFuncSetAttribute((const void *) kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  int per_sm = 0;
+  P4_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) kernel, info.threads, info.smem_bytes));
+  grid_cap = (per_sm > 0 ? per_sm : 1) * sm_count;
+}
+
+void P4Module::unload()
+{
+  if (lib) cudaLibraryUnload(lib);
+  lib = nullptr;
+  kernel = nullptr;
+}
+
+}    // namespace mtpb200

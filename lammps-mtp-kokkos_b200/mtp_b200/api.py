@@ -91,6 +91,10 @@ def load_library():
     lib.mtp_fp64_peak.argtypes = [C.c_int, _dp, _dp]
     lib.mtp_kernel_launch_count.restype = C.c_longlong
     lib.mtp_last_kernel_path.argtypes = [C.c_void_p]
+    lib.mtp_program_kernel_note.argtypes = [C.c_void_p]
+    lib.mtp_program_kernel_note.restype = C.c_char_p
+    lib.mtp_codegen_source.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_longlong, _llp, _llp]
+    lib.mtp_codegen_prebuild.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int)]
     lib.mtp_nve_initial_integrate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                               C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
     lib.mtp_select_grades.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]
@@ -291,7 +295,12 @@ class MTPB200:
     def last_kernel_path(self) -> dict:
         """Which kernels the last compute launched (mtp_last_kernel_path)."""
         v = int(self.lib.mtp_last_kernel_path(self.h))
-        return {"family": v & 15, "program_v3": bool(v & 16), "program_atoms_per_cta": (v >> 8) & 255}
+        return {"family": v & 15, "program_v3": bool(v & 16), "program_generated": bool(v & 32),
+                "program_atoms_per_cta": (v >> 8) & 255}
+
+    def program_kernel_note(self) -> str:
+        """Empty when the generated contraction-program kernel serves this handle, else why it does not."""
+        return self.lib.mtp_program_kernel_note(self.h).decode()
 
     def synchronize(self):
         _check(self.lib, self.lib.mtp_synchronize(self.h))
@@ -323,6 +332,29 @@ def program_check(path: str, atoms_per_cta: int = 32) -> float:
     lib.mtp_program_check.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_double)]
     _check(lib, lib.mtp_program_check(os.fsencode(path), int(atoms_per_cta), C.byref(err)))
     return float(err.value)
+
+
+CODEGEN_INFO = ("atoms_per_cta", "warps", "ctas_per_sm", "rows", "stages", "smem_bytes", "terms", "loads", "stores",
+                "critical_terms", "nslots", "hash")
+
+
+def codegen_source(path: str, latency_shape: bool = False):
+    """Source of the generated contraction-program kernel for a potential file + generator statistics (no device)."""
+    lib = load_library()
+    need = C.c_longlong(0)
+    info = (C.c_longlong * 12)()
+    _check(lib, lib.mtp_codegen_source(os.fsencode(path), int(latency_shape), None, 0, C.byref(need), info))
+    buf = C.create_string_buffer(need.value)
+    _check(lib, lib.mtp_codegen_source(os.fsencode(path), int(latency_shape), buf, need.value, C.byref(need), info))
+    return buf.value.decode(), dict(zip(CODEGEN_INFO, [int(v) for v in info]))
+
+
+def codegen_prebuild(path: str, latency_shape: bool = False) -> bool:
+    """Compile the generated kernel of a potential with NVRTC into the cubin cache (no device). True if NVRTC ran."""
+    lib = load_library()
+    ran = C.c_int(0)
+    _check(lib, lib.mtp_codegen_prebuild(os.fsencode(path), int(latency_shape), C.byref(ran)))
+    return bool(ran.value)
 
 
 def fp64_peaks(device: int = -1):

@@ -1,0 +1,106 @@
+"""CPU tests of the contraction-program code generator (mtp_codegen.cpp): the emitted kernel source is compiled for
+the HOST and executed stage by stage / warp by warp / lane by lane against the reference's sequential program
+(pair_mtp.cpp:196-233, restated in tests/shim/p4_host_check.cpp).  No GPU."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+from mtp_b200 import almtp, api, mtp_basis
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HARNESS = os.path.join(ROOT, "tests", "shim", "p4_host_check.cpp")
+
+
+def _write_tables(path, pot):
+    times = np.asarray(pot.alpha_index_times, dtype=np.int64).reshape(-1, 4)
+    with open(path, "w") as f:
+        f.write(f"{pot.K} {pot.alpha_moments_count} {len(times)} {pot.A}\n")
+        f.write(" ".join(str(int(v)) for v in times.ravel()) + "\n")
+        f.write(" ".join(str(int(v)) for v in pot.alpha_moment_mapping) + "\n")
+        f.write(" ".join(repr(float(v)) for v in pot.moment_coeffs) + "\n")
+
+
+def _host_check(tmp_path, pot_path, pot, latency, env=None):
+    old = {}
+    for k, v in (env or {}).items():
+        old[k] = os.environ.get(k)
+        os.environ[k] = v
+    try:
+        src, info = api.codegen_source(pot_path, latency)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    gen = os.path.join(str(tmp_path), "gen_p4.cu")
+    open(gen, "w").write(src)
+    tables = os.path.join(str(tmp_path), "tables.txt")
+    _write_tables(tables, pot)
+    exe = os.path.join(str(tmp_path), "p4_host_check")
+    two = ["-DP4_TWO"] if info["atoms_per_cta"] == 64 else []
+    subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", f'-DP4_SOURCE="{gen}"'] + two + ["-o", exe, HARNESS], check=True)
+    r = subprocess.run([exe, tables], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return info
+
+
+@pytest.mark.parametrize("level,species", [(8, 1), (10, 2), (12, 3), (16, 2), (20, 1)])
+def test_generated_program_matches_the_sequential_program(tmp_path, level, species):
+    path, pot = util.write_potential(tmp_path, level, species)
+    info = _host_check(tmp_path, path, pot, False)
+    tb = mtp_basis.build_mtp_tables(level)
+    assert info["terms"] <= 3 * len(tb.alpha_index_times)           # forward T + reverse 2T, squares merged
+    assert info["loads"] < info["terms"] or level <= 10            # the register cache removes most operand loads
+
+
+def test_latency_shape_and_two_atoms_per_lane(tmp_path):
+    path, pot = util.write_potential(tmp_path, 12, 2)
+    info = _host_check(tmp_path, path, pot, True)
+    assert info["atoms_per_cta"] == 8
+    info = _host_check(tmp_path, path, pot, False, env={"MTP_B200_P4": "64,8,24,8,1"})
+    assert info["atoms_per_cta"] == 64 and info["warps"] == 8
+    info = _host_check(tmp_path, path, pot, False, env={"MTP_B200_P4": "16,3,6,2,1"})    # tiny cache, odd warp count
+    assert info["atoms_per_cta"] == 16 and info["warps"] == 3
+
+
+def test_permuted_tables_generate_a_correct_program(tmp_path):
+    """A file whose basic moments and products come in another order (as real MLIP-3 files may) is still handled."""
+    path, pot = util.write_potential(tmp_path, 12, 1)
+    rng = np.random.default_rng(5)
+    K = pot.K
+    perm = rng.permutation(K)                    # new index of old basic k
+    basic = np.asarray(pot.alpha_index_basic).reshape(K, 4)
+    new_basic = np.zeros_like(basic)
+    new_basic[perm] = basic
+    ren = np.arange(pot.alpha_moments_count)
+    ren[:K] = perm
+    times = np.asarray(pot.alpha_index_times).reshape(-1, 4).copy()
+    times[:, 0], times[:, 1], times[:, 3] = ren[times[:, 0]], ren[times[:, 1]], ren[times[:, 3]]
+    # shuffle the products within each dependency wave (any order that writes before it reads is a valid file)
+    waves = mtp_basis.prepare_waves(pot.alpha_index_times, K)
+    out, at = [], 0
+    for n in waves:
+        blk = times[at:at + n]
+        out.append(blk[rng.permutation(n)])
+        at += n
+    pot.alpha_index_basic = new_basic.astype(np.int32)
+    pot.alpha_index_times = np.concatenate(out).astype(np.int32)
+    pot.alpha_moment_mapping = np.array([int(ren[m]) for m in pot.alpha_moment_mapping], dtype=np.int32)
+    path2 = os.path.join(str(tmp_path), "permuted.almtp")
+    almtp.write_almtp(path2, pot)
+    pot2 = almtp.read_almtp(path2)
+    _host_check(tmp_path, path2, pot2, False)
+
+
+def test_prebuild_compiles_with_nvrtc_and_caches(tmp_path, monkeypatch):
+    """NVRTC needs no GPU: the cubin of a small potential is built here and found in the cache the second time."""
+    monkeypatch.setenv("MTP_B200_KCACHE", str(tmp_path / "kcache"))
+    path, _ = util.write_potential(tmp_path, 8, 1)
+    assert api.codegen_prebuild(path) is True
+    assert api.codegen_prebuild(path) is False
+    files = os.listdir(tmp_path / "kcache")
+    assert len(files) == 1 and files[0].endswith(".cubin")

@@ -24,7 +24,7 @@ def test_config2_full_size_properties(tmp_path, built):
     assert sysm.nlocal == 262144
     mtp = MTPB200(path)
     res = mtp.compute_system(sysm, eflag=3, vflag=1)
-    assert mtp.last_kernel_path()["program_v3"]
+    assert mtp.last_kernel_path()["program_generated"]
     f = sysm.reverse_comm(res.f)
     fmax = np.abs(f).max()
     # Newton's third law through the ghosts: the total force vanishes
@@ -48,17 +48,20 @@ def test_config2_full_size_properties(tmp_path, built):
     mtp.set_lanes(2)
     mtp.set_chunksize(32768)
 
-    # 2-atoms-per-lane form of the contraction program (separate handle: the choice is made at load)
-    os.environ["MTP_B200_NO_PROG_V3"] = "1"
-    try:
-        old = MTPB200(path)
-    finally:
-        del os.environ["MTP_B200_NO_PROG_V3"]
-    r3 = old.compute_system(sysm, eflag=3, vflag=1)
-    assert not old.last_kernel_path()["program_v3"]
-    assert abs(r3.energy - res.energy) <= TOL_E_REL * abs(res.energy)
-    assert maxabsrel(r3.f, res.f) <= TOL_F_MAXABSREL
-    old.close()
+    # the interpreting forms of the contraction program (separate handles: the choice is made at load)
+    for env in ({"MTP_B200_NO_P4": "1"}, {"MTP_B200_NO_P4": "1", "MTP_B200_NO_PROG_V3": "1"}):
+        os.environ.update(env)
+        try:
+            old = MTPB200(path)
+        finally:
+            for k in env:
+                del os.environ[k]
+        r3 = old.compute_system(sysm, eflag=3, vflag=1)
+        used = old.last_kernel_path()
+        assert not used["program_generated"] and used["program_v3"] == ("MTP_B200_NO_PROG_V3" not in env)
+        assert abs(r3.energy - res.energy) <= TOL_E_REL * abs(res.energy)
+        assert maxabsrel(r3.f, res.f) <= TOL_F_MAXABSREL
+        old.close()
 
     # neighbor list built on the device: same counts as the host list, same energies and forces
     x = torch.from_numpy(sysm.x).cuda()

@@ -141,20 +141,28 @@ def test_fp64_roofs_are_measurable(built):
     assert dfma > 5.0 and dmma > 0.5
 
 
-# systems large enough that every SM gets a chunk, so the throughput shape of the contraction program (the
-# 4-atoms-per-lane kernel, 32 or 16 atoms per CTA) is the one that runs; ilist subsets give ragged tail chunks
+# systems large enough that every SM gets a chunk, so the throughput shape of the contraction program is the one that
+# runs: the kernel generated for the potential (default), or -- MTP_B200_NO_P4 -- the interpreting 4-atoms-per-lane
+# kernel (32 or 16 atoms per CTA); ilist subsets give ragged tail chunks
+@pytest.mark.parametrize("generated", [True, False])
 @pytest.mark.parametrize("level,species,kind,a,cells,atoms_per_cta", [
     (16, 2, "bcc", 3.165, (14, 14, 14), 32),     # config 2 shape
     (12, 3, "fcc", 3.56, (11, 11, 11), 32),
     (18, 1, "fcc", 4.05, (9, 9, 9), 16),
 ])
-def test_program_kernel_throughput_shape(tmp_path, built, level, species, kind, a, cells, atoms_per_cta):
+def test_program_kernel_throughput_shape(tmp_path, built, monkeypatch, level, species, kind, a, cells, atoms_per_cta, generated):
+    from mtp_b200 import api
     from mtp_b200.api import MTPB200
     from oracle_py import OracleMTP
     path, pot = util.write_potential(tmp_path, level, species)
     sysm = util.small_system(kind, a, cells, species, seed=5)
     orc = OracleMTP(pot)
+    if generated:
+        atoms_per_cta = api.codegen_source(path)[1]["atoms_per_cta"]
+    else:
+        monkeypatch.setenv("MTP_B200_NO_P4", "1")
     mtp = MTPB200(path)
+    assert (mtp.program_kernel_note() == "") == generated, mtp.program_kernel_note()
     for lanes in (1, 2):
         mtp.set_lanes(lanes)
         mtp.set_chunksize(1 << 30 if lanes == 1 else 2500)
@@ -163,7 +171,8 @@ def test_program_kernel_throughput_shape(tmp_path, built, level, species, kind, 
         gpu = mtp.compute_host(sysm.x, sysm.type, ilist, sysm.numneigh, sysm.neigh, sysm.offsets)
         if lanes == 1:
             path_used = mtp.last_kernel_path()
-            assert path_used["program_v3"] and path_used["program_atoms_per_cta"] == atoms_per_cta, path_used
+            assert path_used["program_generated"] == generated and path_used["program_v3"] == (not generated), path_used
+            assert path_used["program_atoms_per_cta"] == atoms_per_cta, path_used
         assert abs(gpu.energy - ref.energy) <= TOL_E_REL * abs(ref.energy)
         assert maxabsrel(gpu.f, ref.f) <= TOL_F_MAXABSREL
         assert maxabsrel(gpu.virial, ref.virial) <= TOL_AUX
@@ -179,7 +188,7 @@ def test_program_kernel_throughput_shape_grades(tmp_path, built):
     ref = OracleMTP(pot).compute(sysm.x, sysm.type, sysm.ilist, sysm.numneigh, sysm.neigh, sysm.offsets, grade=True)
     mtp = MTPB200(path, selection_state=True)
     gpu = mtp.compute_system(sysm, grade=True)
-    assert mtp.last_kernel_path()["program_v3"]
+    assert mtp.last_kernel_path()["program_generated"]
     _check(gpu, ref, sysm)
     assert maxabsrel(gpu.grades[: sysm.nlocal], ref.grades[: sysm.nlocal]) <= TOL_AUX
     assert abs(gpu.max_grade - ref.max_grade) <= TOL_AUX * ref.max_grade
