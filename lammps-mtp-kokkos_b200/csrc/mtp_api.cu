@@ -327,7 +327,7 @@ struct V2Entry {
   V2ForcesKernel forces[2];    // [grade step]
 };
 #define V2_ENTRY(D)                                                                                                    \
-  {D, V2Shape<D>::R, V2Shape<D>::KF, V2Shape<D>::NP, v2_ab_for(V2Shape<D>::KF), mtp_radial_kernel<V2Shape<D>::R>,       \
+  {D, V2Shape<D>::R, V2Shape<D>::KF, V2Shape<D>::NP, v2_ab_for(V2Shape<D>::KF), mtp_gather_radial_kernel<V2Shape<D>::R>, \
    mtp_moments_v2<D>,                                                                                                  \
    {mtp_forces_v2<D, v2_ab_for(V2Shape<D>::KF), false>, mtp_forces_v2<D, v2_ab_for(V2Shape<D>::KF), true>}}
 const V2Entry kV2[] = {V2_ENTRY(0), V2_ENTRY(1), V2_ENTRY(2), V2_ENTRY(3), V2_ENTRY(4), V2_ENTRY(5),
@@ -532,22 +532,20 @@ void upload_potential(mtp_handle *h)
   if (h->v2_entry >= 0) {
     const V2Entry &E = kV2[h->v2_entry];
     const int nrad = d.S * d.S * d.R * d.B;
-    h->v2_smem_g = (size_t) ((nrad + 1) & ~1) * 8;
+    h->v2_smem_g = (size_t) ((nrad + 1) & ~1) * 8 + (size_t) 8 * V2_RING * 4 * 8;    // coefficients + one ring per warp
     bool ok = h->v2_smem_g <= max_dynamic_smem((const void *) E.radial, smem_max);
     if (ok) {
       CUDA_CHECK(cudaFuncSetAttribute((const void *) E.radial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->v2_smem_g));
       if (!getenv("MTP_B200_NO_CARVEOUT")) {
-        CUDA_CHECK(cudaFuncSetAttribute((const void *) mtp_gather_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CUDA_CHECK(cudaFuncSetAttribute((const void *) E.radial, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CUDA_CHECK(cudaFuncSetAttribute((const void *) E.moments, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         for (int gq = 0; gq < 2; gq++)
           CUDA_CHECK(cudaFuncSetAttribute((const void *) E.forces[gq], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       }
       int per_sm = 0;
-      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) mtp_gather_kernel, 256, 0));
-      h->v2_grid_g = std::max(1, per_sm) * h->sm_count;
       CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.radial, 256, h->v2_smem_g));
       h->v2_grid_r = std::max(1, per_sm) * h->sm_count;
+      h->v2_grid_g = h->v2_grid_r;
       h->v2_smem_m = (size_t) 2 * V2_NT * (3 + E.R) * 33 * 8;
       ok = h->v2_smem_m <= max_dynamic_smem((const void *) E.moments, smem_max);
       if (ok) {
@@ -928,8 +926,6 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
       pb.pcnt = L.pcnt.p;
       {
         ProfSpan sp(h, MTP_PROF_GATHER, ls);
-        const int gg = std::max(1, std::min(h->v2_grid_g, (n + 7) / 8));
-        mtp_gather_kernel<<<gg, 256, 0, ls>>>(d, s, pb);
         const int gr = std::max(1, std::min(h->v2_grid_r, (n + 7) / 8));
         E.radial<<<gr, 256, h->v2_smem_g, ls>>>(d, s, pb);
       }
@@ -969,7 +965,7 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
         }
       }
       rows_used += gf;
-      g_launches += 5;
+      g_launches += 4;
     } else if (pipeline) {
       const V1Entry &E = kV1[h->v1_entry];
       const int gm = std::max(1, std::min(h->pl_grid_m, (n + W - 1) / W));

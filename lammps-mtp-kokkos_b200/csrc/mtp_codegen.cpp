@@ -356,7 +356,7 @@ unsigned long long fnv(unsigned long long h, const void *data, size_t n)
   return h;
 }
 
-const char *kGeneratorVersion = "p4-r2-03";
+const char *kGeneratorVersion = "p4-r2-04";
 
 // ---- fixed text: device prelude and kernel skeleton ------------------------------------------------------
 const char *kDevicePrelude = R"P4(
@@ -380,20 +380,38 @@ struct P4Args {
 #define P4_FN __device__ __forceinline__
 #define P4_STAGE_FN __device__ __noinline__
 #define P4_TABLE __device__ const
+// Stage functions are compiled separately (noinline): everything they need arrives in registers, and shared memory is
+// addressed explicitly (32-bit shared-window address + immediate offset), never through generic pointers.
 #if P4_APL == 1
 typedef double T_;
-struct P4Ctx {
-  double *S;
-  const double *lin;
-  double *gb, *cand;
-  long long ld;
-  T_ e;
-  bool valid;
-  int grade;
+#else
+struct T_ {
+  double x, y;
 };
-#define LD(r) (x.S[(r) * P4_NA])
-#define ST(r, v) (x.S[(r) * P4_NA] = (v))
-#define LIN(s) (x.lin[s])
+#endif
+struct P4Ctx {
+  unsigned sb, lb;       // shared-window byte addresses: rows + this lane's atom offset, linear coefficients
+  double *gb, *cand;
+  long long ld, cand_ld;
+  int flags;             // bit 0: first atom of the lane is a listed centre, bit 1: second atom, bit 2: grade step
+  T_ e;
+};
+#define P4_PARAMS const unsigned sb, const unsigned lb, double *const gb, const long long ld, double *const cand, \
+                  const long long cand_ld, const int flags, T_ e
+#define P4_RET T_
+#define P4_RETURN return e
+#define P4_CALL(f) x.e = f(x.sb, x.lb, x.gb, x.ld, x.cand, x.cand_ld, x.flags, x.e)
+template <int OFF> P4_FN double p4_lds1(unsigned a)
+{
+  double v;
+  asm("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF));
+  return v;
+}
+#define LIN(s) p4_lds1<(s) * 8>(lb)
+#if P4_APL == 1
+template <int OFF> P4_FN void p4_sts(unsigned a, double v) { asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "d"(v) : "memory"); }
+#define LD(r) p4_lds1<(r) * P4_NA * 8>(sb)
+#define ST(r, v) p4_sts<(r) * P4_NA * 8>(sb, (v))
 #define MUL(a, b) ((a) * (b))
 #define ADD(a, b) ((a) + (b))
 #define FMA(a, b, c) fma((a), (b), (c))
@@ -403,32 +421,27 @@ struct P4Ctx {
 #define FMAU(u, a, c) fma((u), (a), (c))
 #define SPLAT(u) (u)
 #define ZERO 0.0
-#define GBST(slot, v) do { if (x.valid) x.gb[(long long) (slot) * x.ld] = (v); } while (0)
-#define ESC(s, v) do { x.e = fma(x.lin[s], (v), x.e); if (x.grade && x.valid) x.cand[s] = (v); } while (0)
+#define GBST(slot, v) do { if (flags & 1) __stcg(gb + (long long) (slot) * ld, (v)); } while (0)
+#define ESC(s, v) do { e = fma(LIN(s), (v), e); if ((flags & 5) == 5) cand[s] = (v); } while (0)
 #else
-struct T_ {
-  double x, y;
-};
-struct P4Ctx {
-  double *S;
-  const double *lin;
-  double *gb, *cand;
-  long long ld, cand_ld;
-  T_ e;
-  bool valid, valid1;
-  int grade;
-};
-P4_FN T_ p4_ld(const double *p) { const double2 v = *reinterpret_cast<const double2 *>(p); T_ r; r.x = v.x; r.y = v.y; return r; }
-P4_FN void p4_st(double *p, T_ v) { *reinterpret_cast<double2 *>(p) = make_double2(v.x, v.y); }
+template <int OFF> P4_FN T_ p4_lds2(unsigned a)
+{
+  T_ v;
+  asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(a), "n"(OFF));
+  return v;
+}
+template <int OFF> P4_FN void p4_sts(unsigned a, T_ v)
+{
+  asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "d"(v.x), "d"(v.y) : "memory");
+}
 P4_FN T_ p4_mul(T_ a, T_ b) { T_ r; r.x = a.x * b.x; r.y = a.y * b.y; return r; }
 P4_FN T_ p4_add(T_ a, T_ b) { T_ r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
 P4_FN T_ p4_fma(T_ a, T_ b, T_ c) { T_ r; r.x = fma(a.x, b.x, c.x); r.y = fma(a.y, b.y, c.y); return r; }
 P4_FN T_ p4_mulu(double u, T_ a) { T_ r; r.x = u * a.x; r.y = u * a.y; return r; }
 P4_FN T_ p4_fmau(double u, T_ a, T_ c) { T_ r; r.x = fma(u, a.x, c.x); r.y = fma(u, a.y, c.y); return r; }
 P4_FN T_ p4_splat(double u) { T_ r; r.x = u; r.y = u; return r; }
-#define LD(r) p4_ld(x.S + (r) * P4_NA)
-#define ST(r, v) p4_st(x.S + (r) * P4_NA, (v))
-#define LIN(s) (x.lin[s])
+#define LD(r) p4_lds2<(r) * P4_NA * 8>(sb)
+#define ST(r, v) p4_sts<(r) * P4_NA * 8>(sb, (v))
 #define MUL(a, b) p4_mul((a), (b))
 #define ADD(a, b) p4_add((a), (b))
 #define FMA(a, b, c) p4_fma((a), (b), (c))
@@ -438,10 +451,10 @@ P4_FN T_ p4_splat(double u) { T_ r; r.x = u; r.y = u; return r; }
 #define FMAU(u, a, c) p4_fmau((u), (a), (c))
 #define SPLAT(u) p4_splat(u)
 #define ZERO p4_splat(0.0)
-#define GBST(slot, v) do { const T_ v_ = (v); double *q_ = x.gb + (long long) (slot) * x.ld; \
-    if (x.valid1) *reinterpret_cast<double2 *>(q_) = make_double2(v_.x, v_.y); else if (x.valid) *q_ = v_.x; } while (0)
-#define ESC(s, v) do { const T_ v_ = (v); x.e = p4_fmau(x.lin[s], v_, x.e); \
-    if (x.grade) { if (x.valid) x.cand[s] = v_.x; if (x.valid1) x.cand[x.cand_ld + (s)] = v_.y; } } while (0)
+#define GBST(slot, v) do { const T_ v_ = (v); double *q_ = gb + (long long) (slot) * ld; \
+    if (flags & 2) __stcg(reinterpret_cast<double2 *>(q_), make_double2(v_.x, v_.y)); else if (flags & 1) __stcg(q_, v_.x); } while (0)
+#define ESC(s, v) do { const T_ v_ = (v); e = p4_fmau(LIN(s), v_, e); \
+    if (flags & 4) { if (flags & 1) cand[s] = v_.x; if (flags & 2) cand[cand_ld + (s)] = v_.y; } } while (0)
 #endif
 #endif
 )P4";
@@ -473,16 +486,14 @@ extern "C" __global__ void __launch_bounds__(P4_W * 32, P4_MINB) mtp_program_p4(
     asm volatile("cp.async.wait_group 0;\n" ::);
     __syncthreads();
     P4Ctx x;
-    x.S = S + al;
-    x.lin = s_lin;
+    x.sb = (unsigned) __cvta_generic_to_shared(S + al);
+    x.lb = (unsigned) __cvta_generic_to_shared(s_lin);
     x.ld = a.ld;
     x.gb = a.gb + chunk0 + al;
-    x.valid = owner && al < na;
-    x.grade = a.grade;
-    x.cand = a.grade ? a.cand_rows + (long long) (chunk0 + al) * a.cand_ld + a.cand_col0 : nullptr;
-#if P4_APL == 2
-    x.valid1 = owner && al + 1 < na;
     x.cand_ld = a.cand_ld;
+    x.cand = a.grade ? a.cand_rows + (long long) (chunk0 + al) * a.cand_ld + a.cand_col0 : nullptr;
+    x.flags = ((owner && al < na) ? 1 : 0) | ((P4_APL == 2 && owner && al + 1 < na) ? 2 : 0) | (a.grade ? 4 : 0);
+#if P4_APL == 2
     x.e.x = x.e.y = 0.0;
 #else
     x.e = 0.0;
@@ -694,10 +705,10 @@ bool p4_generate(const Potential &p, const P4Params &prm, const short *slot_of_k
           if (pass == 1) info.stores += st_count;
         }
         info.loads += E.loads;
-        snprintf(buf, sizeof(buf), "P4_STAGE_FN void p4_s%d_w%d_%d(P4Ctx &x)\n{\n", st, w, part);
+        snprintf(buf, sizeof(buf), "P4_STAGE_FN P4_RET p4_s%d_w%d_%d(P4_PARAMS)\n{\n", st, w, part);
         src += buf;
         src += body;
-        src += "}\n";
+        src += "  P4_RETURN;\n}\n";
         present.push_back({st * prm.warps + w, part});
         part++;
         i = j;
@@ -710,7 +721,7 @@ bool p4_generate(const Potential &p, const P4Params &prm, const short *slot_of_k
     const int key = present[q].first;
     src += "    case " + std::to_string(key) + ":\n";
     for (; q < present.size() && present[q].first == key; q++) {
-      snprintf(buf, sizeof(buf), "      p4_s%d_w%d_%d(x);\n", key / prm.warps, key % prm.warps, present[q].second);
+      snprintf(buf, sizeof(buf), "      P4_CALL(p4_s%d_w%d_%d);\n", key / prm.warps, key % prm.warps, present[q].second);
       src += buf;
     }
     src += "      break;\n";

@@ -83,6 +83,15 @@ struct SiteArgs {
   int *status;
 };
 
+// one 32-byte position record in ONE request (sm_100 256-bit load, LDG.E.ENL2.256): a gathered neighbor costs one
+// sector lookup instead of two 16-byte loads of the same sector
+__device__ __forceinline__ void ld_atomrec(const AtomRec *p, double &x, double &y, double &z, int &t)
+{
+  double tt;
+  asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(tt) : "l"(p));
+  t = (int) __double_as_longlong(tt);
+}
+
 // Ampere-style asynchronous copies global -> shared (LDGSTS): no registers, many in flight per thread
 __device__ __forceinline__ void cp_async8_zfill(void *smem_dst, const void *gsrc, int src_bytes /*8 or 0*/)
 {

@@ -5,11 +5,11 @@
 // indices mu < rcnt(d).  With D0 a compile-time constant every loop over (a, b, c, mu) below unrolls into
 // straight-line FP64 code on registers.  Canonical slot order: q lexicographic in (a, b, c), then mu.
 //
-//   mtp_gather_kernel    warp per centre atom: neighbor gather (32-byte position records), cutoff mask exactly as
-//                        pair_mtp.cpp:112-129, ballot compaction straight into the pair buffer (field-major, atom ii
-//                        owning the slots [ii * ncap, ii * ncap + pcnt[ii])).
-//   mtp_radial_kernel    lane = in-cutoff pair: Chebyshev x cutoff and the radial contraction
-//                        (mtp_rb_chevbyshev_basis.cpp:29-54, pair_mtp.cpp:139-151) -> record {u, d, f_mu, f'_mu, j}.
+//   mtp_gather_radial_kernel   warp per centre atom: neighbor gather (32-byte position records), cutoff mask exactly as
+//                        pair_mtp.cpp:112-129, ballot compaction into a ring in shared memory; then lane = in-cutoff
+//                        pair: Chebyshev x cutoff and the radial contraction (mtp_rb_chevbyshev_basis.cpp:29-54,
+//                        pair_mtp.cpp:139-151) -> record {u, d, f_mu, f'_mu, j} in the pair buffer (field-major,
+//                        atom ii owning the slots [ii * ncap, ii * ncap + pcnt[ii])).
 //   mtp_moments_v2       CTA = 32 atoms x NP warps, lane = atom, warp = "pass" (a contiguous range of canonical
 //                        slots, <= ~48 accumulators held in registers).  Pair records are staged through shared
 //                        memory (coalesced read, transposed so that lane = atom reads are conflict free);
@@ -112,63 +112,13 @@ constexpr int V2_PEND = 64;
 constexpr int V2_NT = MTP_V2_NT;      // pairs per staged tile of the moment kernel (power of two)
 
 
-// ===================================================================================================== gather
-// stage 1: warp per centre atom, lane = listed neighbor.  Gather the 32-byte position records, apply the cutoff mask
-// exactly as pair_mtp.cpp:112-129 and write the in-cutoff displacements, compacted in list order, straight to the
-// pair buffer (fields 0..2 hold r until stage 2 turns them into the unit vector).  No shared memory, few registers:
-// the whole SM's worth of warps hides the gather latency.
-__global__ void __launch_bounds__(256)
-mtp_gather_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
-{
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-  for (int ii = blockIdx.x * W + warp; ii < a.inum; ii += gridDim.x * W) {
-    V1Atom at;
-    v1_load_atom(pot, a, ii, lane, at);
-    const long long slot0 = (long long) ii * pb.ncap;
-    int done = 0;
-    for (int base = 0; base < at.jnum; base += 32) {
-      const int jj = base + lane;
-      bool within = false;
-      int j = 0, jt = 0;
-      double r0 = 0, r1 = 0, r2 = 0;
-      if (jj < at.jnum) {
-        const long long pos = at.row0 + (long long) jj * a.stride_jj;
-        j = a.neighbors[pos] & a.neighmask;
-        const double2 *nrec = reinterpret_cast<const double2 *>(a.xt + j);
-        const double2 nxy = __ldg(nrec);
-        const double2 nzt = __ldg(nrec + 1);
-        jt = (int) __double_as_longlong(nzt.y);
-        r0 = nxy.x - at.xi0;
-        r1 = nxy.y - at.xi1;
-        r2 = nzt.x - at.xi2;
-        // separately rounded, left to right, exactly pair_mtp.cpp:121-123 (no FMA contraction)
-        const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2));
-        within = !(rsq > pot.cutsq);
-        if (jt < 0 || jt >= pot.S) {    // pair_mtp.cpp:116-118
-          atomicOr(a.status, 1);
-          within = false;
-        }
-        if (a.within) a.within[pos] = within ? 1 : 0;
-      }
-      const unsigned bal = __ballot_sync(FULL, within);
-      if (within) {
-        const long long s = slot0 + done + __popc(bal & ((1u << lane) - 1u));
-        pb.fld[s] = r0;
-        pb.fld[pb.cap + s] = r1;
-        pb.fld[2 * pb.cap + s] = r2;
-        pb.pj[s] = j;
-        pb.pjt[s] = jt | (at.itype << 16);    // neighbor species | centre species
-      }
-      done += __popc(bal);
-    }
-    if (lane == 0) pb.pcnt[ii] = done;
-  }
-}
-
+// ===================================================================================================== gather + radial
 // Chebyshev x cutoff (mtp_rb_chevbyshev_basis.cpp:29-54) contracted with the radial coefficients of one species
-// pair (pair_mtp.cpp:139-151), fully unrolled; ct = coefficients transposed to [ri][mu]
+// pair (pair_mtp.cpp:139-151), fully unrolled.  ct = coefficient table in shared memory, element (ri, mu) of species
+// pair pt at ct[(ri * R + mu) * SP + pt]: the lanes of a warp that differ in their species pair read adjacent words
+// (no bank conflict), lanes with the same pair read one word (broadcast).
 template <int R, int B>
-__device__ __forceinline__ void radial_unrolled(const DevPotential &pot, const double *__restrict__ ct, double d,
+__device__ __forceinline__ void radial_unrolled(const DevPotential &pot, const double *__restrict__ ct, int SP, double d,
                                                 double (&F)[R], double (&Fd)[R])
 {
   const double t = d - pot.rmax;
@@ -177,8 +127,8 @@ __device__ __forceinline__ void radial_unrolled(const DevPotential &pot, const d
   double v_prev = pot.scaling * (1 * t * t), d_prev = pot.scaling * 2 * t;
 #pragma unroll
   for (int mu = 0; mu < R; mu++) {
-    F[mu] = ct[mu] * v_prev;
-    Fd[mu] = ct[mu] * d_prev;
+    F[mu] = ct[mu * SP] * v_prev;
+    Fd[mu] = ct[mu * SP] * d_prev;
   }
   if (B == 1) return;
   double v_cur = pot.scaling * (ksi * t * t), d_cur = pot.scaling * (mult * t * t + 2 * ksi * t);
@@ -194,45 +144,53 @@ __device__ __forceinline__ void radial_unrolled(const DevPotential &pot, const d
     }
 #pragma unroll
     for (int mu = 0; mu < R; mu++) {
-      const double cc = ct[ri * R + mu];
+      const double cc = ct[(ri * R + mu) * SP];
       F[mu] = fma(cc, v_cur, F[mu]);
       Fd[mu] = fma(cc, d_cur, Fd[mu]);
     }
   }
 }
 
-// stage 2: lane = in-cutoff pair (perfectly parallel): distance, unit vector, radial functions -> the remaining
-// fields of the record
+// stages 1 + 2 in one kernel, warp per centre atom.
+//   gather: lane = listed neighbor; 32-byte position records, cutoff mask exactly as pair_mtp.cpp:112-129; the
+//           in-cutoff displacements are compacted, in list order, into a 64-entry ring of the warp in shared memory;
+//   radial: whenever the ring holds 32 entries (and once more at the end of the list) lane = in-cutoff pair: distance,
+//           unit vector, Chebyshev x cutoff, radial contraction -> the pair record {u, d, f_mu, f'_mu, j, jt}.
+// The displacement never travels through global memory, every lane of the radial phase is busy, and the FP64 work of
+// one warp runs under the gather latency of the others.
+constexpr int V2_RING = 64;
 template <int R>
-__global__ void __launch_bounds__(256)
-mtp_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
+__global__ void __launch_bounds__(256, 3)
+mtp_gather_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  double *s_ct = reinterpret_cast<double *>(smem);    // [S*S][B][R]: transposed radial coefficients
-  const int nrad = pot.S * pot.S * pot.R * pot.B, RB = pot.R * pot.B;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  const int SS = pot.S * pot.S, RB = pot.R * pot.B, nrad = SS * RB;
+  double *s_ct = reinterpret_cast<double *>(smem);                                     // [B][R][S*S]
+  double *ring = s_ct + ((nrad + 1) & ~1) + (size_t) warp * (V2_RING * 4);             // per warp: r0, r1, r2, {j, jt}
   for (int t = threadIdx.x; t < nrad; t += blockDim.x) {
     const int pt = t / RB, r = t - pt * RB, mu = r / pot.B, ri = r - mu * pot.B;
-    s_ct[pt * RB + ri * pot.R + mu] = pot.radial[t];
+    s_ct[(ri * pot.R + mu) * SS + pt] = pot.radial[t];
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
   for (int ii = blockIdx.x * W + warp; ii < a.inum; ii += gridDim.x * W) {
-    // the record loads do not wait for the pair count: slots beyond it hold stale but readable data
-    const long long s0 = (long long) ii * pb.ncap;
-    const int cnt = pb.pcnt[ii];
-    for (int n0 = 0; n0 < pb.ncap; n0 += 32) {
-      const int n = n0 + lane;
-      const long long s = s0 + (n < pb.ncap ? n : 0);
-      const double r0 = pb.fld[s], r1 = pb.fld[pb.cap + s], r2 = pb.fld[2 * pb.cap + s];
-      const int tt = pb.pjt[s];
-      if (n0 >= cnt) break;    // warp-uniform
-      if (n < cnt) {
-        const int jt = tt & 0xffff, itype = tt >> 16;
+    V1Atom at;
+    v1_load_atom(pot, a, ii, lane, at);
+    const long long slot0 = (long long) ii * pb.ncap;
+    int head = 0, count = 0, done = 0;
+    // lane = entry `head + lane` of the ring -> record `done + lane` of this centre
+    auto flush = [&](int n) {
+      __syncwarp();
+      if (lane < n) {
+        const int e = (head + lane) & (V2_RING - 1);
+        const double r0 = ring[e], r1 = ring[V2_RING + e], r2 = ring[2 * V2_RING + e];
+        const int2 jj = reinterpret_cast<const int2 *>(ring + 3 * V2_RING)[e];
+        const int jt = jj.y;
         const double dist = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2)));
         const double invd = 1.0 / dist;
         double F[R], Fd[R];
-        const double *ct = s_ct + (size_t) (itype * pot.S + jt) * RB;
-        if (pot.B == 8) radial_unrolled<R, 8>(pot, ct, dist, F, Fd);
+        const double *ct = s_ct + (at.itype * pot.S + jt);
+        if (pot.B == 8) radial_unrolled<R, 8>(pot, ct, SS, dist, F, Fd);
         else {    // any other basis size: same recurrence with a run-time trip count
           const double t = dist - pot.rmax;
           const double ksi = (2 * dist - (pot.rmin + pot.rmax)) / (pot.rmax - pot.rmin);
@@ -256,12 +214,13 @@ mtp_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
             }
 #pragma unroll
             for (int mu = 0; mu < R; mu++) {
-              const double cc = ct[ri * R + mu];
+              const double cc = ct[(ri * R + mu) * SS];
               F[mu] += cc * v_cur;
               Fd[mu] += cc * d_cur;
             }
           }
         }
+        const long long s = slot0 + done + lane;
         pb.fld[s] = r0 * invd;
         pb.fld[pb.cap + s] = r1 * invd;
         pb.fld[2 * pb.cap + s] = r2 * invd;
@@ -271,8 +230,49 @@ mtp_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
           pb.fld[(4 + mu) * pb.cap + s] = F[mu];
           pb.fld[(4 + R + mu) * pb.cap + s] = Fd[mu];
         }
+        pb.pj[s] = jj.x;
+        pb.pjt[s] = jt | (at.itype << 16);    // neighbor species | centre species
       }
+      __syncwarp();
+      head = (head + n) & (V2_RING - 1);
+      count -= n;
+      done += n;
+    };
+    for (int base = 0; base < at.jnum; base += 32) {
+      const int jj = base + lane;
+      bool within = false;
+      int j = 0, jt = 0;
+      double r0 = 0, r1 = 0, r2 = 0;
+      if (jj < at.jnum) {
+        const long long pos = at.row0 + (long long) jj * a.stride_jj;
+        j = a.neighbors[pos] & a.neighmask;
+        double nx, ny, nz;
+        ld_atomrec(a.xt + j, nx, ny, nz, jt);
+        r0 = nx - at.xi0;
+        r1 = ny - at.xi1;
+        r2 = nz - at.xi2;
+        // separately rounded, left to right, exactly pair_mtp.cpp:121-123 (no FMA contraction)
+        const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2));
+        within = !(rsq > pot.cutsq);
+        if (jt < 0 || jt >= pot.S) {    // pair_mtp.cpp:116-118
+          atomicOr(a.status, 1);
+          within = false;
+        }
+        if (a.within) a.within[pos] = within ? 1 : 0;
+      }
+      const unsigned bal = __ballot_sync(FULL, within);
+      if (within) {
+        const int e = (head + count + __popc(bal & ((1u << lane) - 1u))) & (V2_RING - 1);
+        ring[e] = r0;
+        ring[V2_RING + e] = r1;
+        ring[2 * V2_RING + e] = r2;
+        reinterpret_cast<int2 *>(ring + 3 * V2_RING)[e] = make_int2(j, jt);
+      }
+      count += __popc(bal);
+      if (count >= 32) flush(32);
     }
+    if (count > 0) flush(count);
+    if (lane == 0) pb.pcnt[ii] = done;
   }
 }
 

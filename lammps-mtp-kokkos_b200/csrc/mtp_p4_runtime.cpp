@@ -32,27 +32,29 @@ P4Choice p4_choose(const Potential &p, size_t smem_optin, bool latency_shape)
   }
   // one SM has 228 KB of shared memory, 1 KB of which is reserved per resident CTA
   const size_t two_ctas = (smem_optin + 1024) / 2 - 1024;
-  const int nas[3] = {32, 16, 8};
-  for (int i = latency_shape ? 2 : 0; i < 3; i++) {
-    P4Params prm;
-    prm.na = nas[i];
-    prm.warps = 4;
-    size_t b = p4_smem_bytes(p, prm);
-    if (b == 0) return ch;    // structure not supported
-    if (b <= two_ctas) {      // two CTAs of four warps per SM: each warp keeps a long run of the node order
-      ch.prm = prm;
-      ch.min_blocks = 2;
-      ch.ok = true;
-      return ch;
-    }
-    prm.warps = 8;
-    b = p4_smem_bytes(p, prm);
-    if (b <= smem_optin) {
-      ch.prm = prm;
-      ch.min_blocks = 1;
-      ch.ok = true;
-      return ch;
-    }
+  // The emitted code is straight-line and executed once per chunk, so it streams through the instruction cache:
+  // measured on B200 it issues ~0.5 instructions/clk/SM whatever the warp count (instruction-fetch bound, ~8 B/clk/SM).
+  // What matters is therefore atoms per instruction: the throughput shape is only worth it with a full warp of atoms
+  // per row (32 per CTA); potentials whose tables do not fit that (levels >= 20) keep the interpreting kernels, whose
+  // loop stays in the instruction cache.  The latency shape (mtp/small/kk: few atoms, every SM must get a chunk) takes
+  // 8 atoms per CTA and 8 warps: the chunk's critical path is what counts there.
+  P4Params prm;
+  prm.na = latency_shape ? 8 : 32;
+  prm.warps = latency_shape ? 8 : 4;
+  size_t b = p4_smem_bytes(p, prm);
+  if (b == 0) return ch;    // structure not supported
+  if (b <= two_ctas) {      // two CTAs per SM: their instruction streams overlap
+    ch.prm = prm;
+    ch.min_blocks = 2;
+    ch.ok = true;
+    return ch;
+  }
+  prm.warps = 8;
+  b = p4_smem_bytes(p, prm);
+  if (b <= smem_optin) {
+    ch.prm = prm;
+    ch.min_blocks = 1;
+    ch.ok = true;
   }
   return ch;
 }

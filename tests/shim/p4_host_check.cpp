@@ -17,6 +17,10 @@
 #define P4_FN static inline
 #define P4_STAGE_FN static
 #define P4_TABLE static const
+#define P4_PARAMS P4Ctx &x
+#define P4_RET void
+#define P4_RETURN return
+#define P4_CALL(f) f(x)
 
 #ifdef P4_TWO
 struct T_ {
