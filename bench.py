@@ -61,6 +61,26 @@ def algorithmic_flops_split(pot, n_list, n_cut):
     return {"gather": gather, "moments": moments, "forces": forces, "program": program}
 
 
+def executed_flops_split(pot, n_list, n_cut, program_terms):
+    """FP64 operations this design actually executes per atom (fma = 2 flop), kernel by kernel -- next to the
+    reference-convention count above, which charges the Jacobian the reference forms (pair_mtp.cpp:175-191) and this
+    design never does.  Standard basic-moment sets only (degree D0 = P - 1).
+      gather+radial: r, rsq per listed neighbor; per in-cutoff pair sqrt, 1/d, u, Chebyshev values + derivatives by
+                     recurrence and the two radial contractions (2 x R x B fma);
+      moments:       one fma per (pair, basic moment) + one multiply per monomial u^q;
+      forces:        Horner gradient of sum_mu f_mu(d) P_mu(u): two fma per (pair, basic moment) for W / W', 3 / 4 / 5 fma
+                     per monomial / (a, b) column / a level, ~30 for the epilogue, scatter and virial;
+      program:       one fma per term step of the generated kernel (forward T + reverse 2T with squares merged)."""
+    B, R, P, K = pot.radial_basis_size, pot.radial_funcs_count, pot.max_alpha_index_basic, pot.K
+    d0 = P - 1
+    nq, nab, na = (d0 + 1) * (d0 + 2) * (d0 + 3) // 6, (d0 + 1) * (d0 + 2) // 2, d0 + 1
+    gather = 8.0 * n_list + n_cut * (2 + 3 + 10 + 9.0 * max(B - 2, 0) + 4.0 * R * B)
+    moments = n_cut * (2.0 * K + nq)
+    forces = n_cut * (4.0 * K + 6.0 * nq + 8.0 * nab + 10.0 * na + 30.0)
+    program = 2.0 * program_terms
+    return {"gather": gather, "moments": moments, "forces": forces, "program": program}
+
+
 def algorithmic_bytes_per_atom(n_list):
     return 4.0 * n_list + 84.0
 
@@ -359,8 +379,14 @@ def main():
         flush.fill_(s & 0xff)
         step_device()
     prof = mtp.profile_read()
-    mtp.profile_enable(False)
     mtp.set_lanes(args.lanes)
+    step_device()
+    mtp.profile_read()
+    for s in range(prof_steps):
+        flush.fill_(s & 0xff)
+        step_device()
+    prof_lanes = mtp.profile_read()      # same events with the lanes of `value`: spans of different lanes overlap
+    mtp.profile_enable(False)
     step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
     total_ms = float(sum(step_ms))
     if world > 1:
@@ -386,21 +412,20 @@ def main():
         res = api.HostResult(nall, mtp.info.coeff_count)
         k7, res.f = pinned_like(res.f)
         k8, res.ev = pinned_like(res.ev)
+        # f_overwrite: LAMMPS's force_clear zeroes f before Pair::compute, and a lone pair style is the first contributor
+        # (PairMTPB200::compute sets the flag when force->pair is this style): the result is stored, f is not uploaded
         for _ in range(2):
-            res.f[:] = 0.0
-            mtp.compute_host(hx, htype, hil, hnn, hneigh, hoff, eflag=1, vflag=1, variant=variant, out=res)
-        # (the pair style ADDS into the caller's f, pair_mtp.cpp:248-254: f is left to accumulate over the timed
-        # steps instead of paying a host-side memset that LAMMPS's own force_clear would own)
+            mtp.compute_host(hx, htype, hil, hnn, hneigh, hoff, eflag=1, vflag=1, variant=variant, out=res, f_overwrite=True)
         t0 = time.perf_counter()
         for _ in range(args.steps):
             mtp.compute_host(hx, htype, hil, hnn, hneigh, hoff, eflag=1, vflag=1, variant=variant, out=res,
-                             list_changed=True)
+                             list_changed=True, f_overwrite=True)
         e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
-        # informational: LAMMPS re-neighbors every ~10 steps; between rebuilds the list stays resident on the device
+        # LAMMPS re-neighbors every ~10 steps at most; between rebuilds the list and the types stay resident on the device
         t0 = time.perf_counter()
         for k in range(args.steps):
             mtp.compute_host(hx, htype, hil, hnn, hneigh, hoff, eflag=1, vflag=1, variant=variant, out=res,
-                             list_changed=(k % LIST_EVERY == 0))
+                             list_changed=(k % LIST_EVERY == 0), f_overwrite=True)
         e2e10_ms = 1e3 * (time.perf_counter() - t0) / args.steps
         # informational: the list never crosses PCIe -- built on the device (mtp_neigh_build) on
         # every 10th step from the positions that were just uploaded; per step H2D x/type, kernels, D2H f + EV record
@@ -452,15 +477,13 @@ def main():
         except Exception as exc:      # the headline e2e above does not depend on this variant
             devlist = {"error": repr(exc)}
         nid = nlocal
-        list_bytes = 4 * sysm.neigh.size + 8 * nid + 4 * nid + 4 * nlocal
-        h2d = 24 * nall + 4 * nall + 24 * nall + list_bytes // LIST_EVERY
+        list_bytes = 4 * sysm.neigh.size + 8 * nid + 4 * nid + 4 * nlocal + 4 * nall      # list + offsets + numneigh + ilist + type
+        h2d = 24 * nall + list_bytes
         d2h = 24 * nall + 64
         e2e_energy = float(res.ev[0])
-        e2e_every_ms, e2e_ms = e2e_ms, e2e10_ms      # headline: LAMMPS's re-neighboring cadence; every-step kept below
-        note = ("mtp_compute_host per step: H2D x,type,f every step and the full neighbor list on every %dth step (the "
-                "list only changes when LAMMPS re-neighbors; with the default 2 A skin that is far rarer than every 10 "
-                "steps in a solid), kernels, D2H f + energy/virial record; host buffers pinned; wall clock around the "
-                "blocking call; h2d bytes averaged over the cadence" % LIST_EVERY)
+        note = ("mtp_compute_host per step with the neighbor list re-sent on EVERY step (worst case: LAMMPS re-neighbors far less "
+                "often): H2D x, type, full neighbor list; kernels; D2H f + energy/virial record; f_overwrite (f is zero on entry, "
+                "as after LAMMPS's force_clear); host buffers pinned; wall clock around the blocking call")
     else:
         # N > 1: same metric through the public Python API: per step H2D of the owned positions, types and the
         # neighbor list from pinned host memory, device halo exchange, kernels, D2H of the owned forces + EV record
@@ -472,10 +495,11 @@ def main():
         hf_t = torch.empty((nlocal, 3), dtype=torch.float64, pin_memory=True)
         hev_t = torch.empty(8, dtype=torch.float64, pin_memory=True)
 
-        def step_e2e(k=0):
+        def step_e2e(k=0, list_every=1):
             t_x[:nlocal].copy_(hx_t, non_blocking=True)
-            t_type.copy_(ht_t, non_blocking=True)
-            if k % LIST_EVERY == 0:      # re-neighboring step: the list crosses PCIe again
+            if k % list_every == 0:
+                t_type.copy_(ht_t, non_blocking=True)
+            if k % list_every == 0:      # re-neighboring step: the list crosses PCIe again
                 t_nn.copy_(hnn_t, non_blocking=True)
                 t_neigh.copy_(hne_t, non_blocking=True)
                 t_off.copy_(hof_t, non_blocking=True)
@@ -487,28 +511,32 @@ def main():
         for _ in range(2):
             step_e2e()
         barrier()
-        t0 = time.perf_counter()
-        for k in range(args.steps):
-            step_e2e(k)
-        barrier()
-        e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-        h2d = 24 * nlocal + 4 * nall + (4 * nall + 4 * sysm.neigh.size + 8 * (nall + 1)) // LIST_EVERY
+        e2e_n = {}
+        for every in (1, LIST_EVERY):
+            t0 = time.perf_counter()
+            for k in range(args.steps):
+                step_e2e(k, every)
+            barrier()
+            ms = 1e3 * (time.perf_counter() - t0) / args.steps
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_n[every] = float(t.item())
+        e2e_ms, e2e10_ms = e2e_n[1], e2e_n[LIST_EVERY]
+        list_bytes = 4 * nall + 4 * nall + 4 * sysm.neigh.size + 8 * (nall + 1)
+        h2d = 24 * nlocal + list_bytes
         d2h = 24 * nlocal + 64
         e2e_energy = float(hev_t[0])
-        note = ("per rank and step: H2D owned x, type every step and numneigh/offsets/neighbor list on every %dth step "
-                "(LAMMPS's re-neighboring cadence) from pinned memory, device halo forward (NCCL send/recv), kernels, halo "
-                "reverse, EV all-reduce, D2H owned f + EV record; wall clock, max over ranks; bytes are per rank and "
-                "averaged over the cadence" % LIST_EVERY)
+        note = ("per rank and step, neighbor list re-sent on EVERY step (worst case): H2D owned x, type, numneigh/offsets/neighbor "
+                "list from pinned memory, device halo forward (NCCL send/recv), kernels, halo reverse, EV all-reduce, D2H owned "
+                "f + EV record; wall clock, max over ranks; bytes are per rank")
     e2e = {"value": world * nlocal / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "note": note,
            "energy_matches_device_path": bool(abs(e2e_energy - energy) <= 1e-9 * abs(energy))}
+    e2e["list_resident"] = {"value": world * nlocal / (e2e10_ms * 1e-3) / 1e6, "ms_per_step": e2e10_ms,
+                            "h2d_bytes_per_step": int(h2d - list_bytes + list_bytes // LIST_EVERY), "d2h_bytes_per_step": int(d2h),
+                            "note": "same step with the list (and types) re-sent on every %dth step only -- LAMMPS's "
+                                    "re-neighboring cadence is at most that in a solid with the default 2 A skin" % LIST_EVERY}
     if world == 1:
-        e2e["list_resent_every_step"] = {"value": nlocal / (e2e_every_ms * 1e-3) / 1e6, "ms_per_step": e2e_every_ms,
-                                         "h2d_bytes_per_step": int(24 * nall + 4 * nall + 24 * nall + list_bytes),
-                                         "note": "pessimistic bound: same call with the full neighbor list re-sent on EVERY step"}
         e2e["device_built_list"] = devlist
 
     # ---- informational: the reference's example deck as a device-resident MD loop (README.md:148-149: velocity
@@ -557,32 +585,44 @@ def main():
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     split = algorithmic_flops_split(pot, n_list, n_cut)
-    kernels = {}
-    for cls, (ms, spans) in prof.items():
-        if spans == 0:
-            continue
-        k = {"ms_per_step": ms / prof_steps, "launches_per_step": spans / prof_steps}
-        if cls in split:
-            k["algorithmic_flops_per_atom"] = split[cls]
-            k["achieved_tflops"] = split[cls] * nlocal / (ms / prof_steps * 1e-3) / 1e12
-            k["frac_of_fp64_peak"] = k["achieved_tflops"] / dfma
-        kernels[cls] = k
+    try:
+        cg_info = api.codegen_source(pot_path, args.variant == "small")[1]
+        program_terms = cg_info["terms"]
+    except Exception:
+        cg_info, program_terms = None, 3 * pot.T
+    executed = executed_flops_split(pot, n_list, n_cut, program_terms)
+
+    def kernel_table(p):
+        out = {}
+        for cls, (ms, spans) in p.items():
+            if spans == 0:
+                continue
+            k = {"ms_per_step": ms / prof_steps, "launches_per_step": spans / prof_steps}
+            if cls in split:
+                k["algorithmic_flops_per_atom"] = split[cls]
+                k["achieved_tflops"] = split[cls] * nlocal / (ms / prof_steps * 1e-3) / 1e12
+                k["frac_of_fp64_peak"] = k["achieved_tflops"] / dfma
+                k["executed_flops_per_atom"] = executed[cls]
+                k["executed_tflops"] = executed[cls] * nlocal / (ms / prof_steps * 1e-3) / 1e12
+                k["executed_frac_of_fp64_peak"] = k["executed_tflops"] / dfma
+            out[cls] = k
+        return out
+
+    kernels = kernel_table(prof)
+    kernels_lanes = kernel_table(prof_lanes)
     dom = max((c for c in kernels if c in split), key=lambda c: kernels[c]["ms_per_step"], default=None)
     pipe_ms = sum(k["ms_per_step"] for k in kernels.values())
     achieved_tf = flops_atom * nlocal / (pipe_ms * 1e-3) / 1e12 if pipe_ms else 0.0
+    executed_atom = sum(executed.values())
     achieved_gbs = bytes_atom * nlocal / (ms_per_step * 1e-3) / 1e9
-    # the contraction-program kernel moves two FP64 operands per term through shared memory and is bound by that
-    # pipe (128 B/clk/SM), not by FP64: forward T terms + reverse 2T terms -> 6T operand reads of 8 B per atom
-    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
-    sm_mhz = clocks.get("sm_max_mhz") or 1965.0
-    smem_peak_tbs = 128.0 * sm_count * sm_mhz * 1e6 / 1e12
-    if "program" in kernels:
-        kp = kernels["program"]
-        kp["algorithmic_smem_bytes_per_atom"] = 48.0 * pot.T
-        kp["achieved_smem_tbs"] = 48.0 * pot.T * nlocal / (kp["ms_per_step"] * 1e-3) / 1e12
-        kp["frac_of_smem_peak"] = kp["achieved_smem_tbs"] / smem_peak_tbs
+    if "program" in kernels and cg_info:
+        # the generated program kernel is straight-line code executed once per 32-atom chunk: it streams through the
+        # instruction cache and is bound by instruction fetch (ncu: ~0.5 instructions/clk/SM, profiles/r2_*), not by
+        # the FP64 or the shared-memory pipe; reported for what it is
+        kernels["program"]["generated"] = {k: cg_info[k] for k in ("atoms_per_cta", "warps", "ctas_per_sm", "rows", "stages",
+                                                                   "smem_bytes", "terms", "loads", "stores")}
     # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture (config 2 only: the
-    # capture is of that workload); null for any other workload
+    # capture is of that workload, bench defaults); null for any other workload
     traffic, traffic_note = None, None
     try:
         if args.config == 2 and not args.cells and dom:
@@ -591,25 +631,31 @@ def main():
             traffic_note = tj["note"]
     except Exception:
         traffic = None
-    roofline = {"kernel": dom, "traffic": traffic, "traffic_note": traffic_note,
+    roofline = {"bound": "fp64", "unit": "TFLOP/s", "kernel": dom,
+                "achieved": kernels[dom]["achieved_tflops"] if dom else None, "peak": dfma,
+                "frac": kernels[dom]["frac_of_fp64_peak"] if dom else None,
+                "achieved_executed": kernels[dom]["executed_tflops"] if dom else None,
+                "frac_executed": kernels[dom]["executed_frac_of_fp64_peak"] if dom else None,
+                "frac_note": "dominant kernel (largest share of the step) on the FP64 roof: `frac` counts the flops as written in "
+                             "pair_mtp.cpp (SURVEY.md 8d, includes forming the Jacobian, which this design never does -- it can "
+                             "exceed 1), `frac_executed` counts the FP64 operations the kernel actually executes",
+                "traffic": traffic, "traffic_note": traffic_note,
                 "duration_ms": kernels[dom]["ms_per_step"] / kernels[dom]["launches_per_step"] if dom else None,
-                "duration_note": "average launch duration of the dominant kernel (largest share of the step): CUDA events "
-                                 "recorded by the library on its launch stream around every launch (mtp_profile_read) in a "
-                                 "pass with the kernels serialised (lanes = 1) right after the timed region",
-                "fp64_peak_tflops": dfma,
-                "fp64_peak_source": "FP64 DFMA peak measured in this run by mtp_fp64_peak (DMMA m8n8k4: %.2f TFLOP/s); "
-                                    "MEASURED_PEAKS.json has no FP64 entry" % dmma,
-                "smem_peak_tbs": smem_peak_tbs,
-                "smem_peak_source": "128 B/clk/SM x %d SMs x %.0f MHz" % (sm_count, sm_mhz),
-                **({"bound": "smem", "unit": "TB/s", "achieved": kernels[dom]["achieved_smem_tbs"], "peak": smem_peak_tbs,
-                    "frac": kernels[dom]["frac_of_smem_peak"]} if dom == "program" else
-                   {"bound": "fp64", "unit": "TFLOP/s", "achieved": kernels[dom]["achieved_tflops"] if dom else None,
-                    "peak": dfma, "frac": kernels[dom]["frac_of_fp64_peak"] if dom else None}),
-                "kernels": kernels,
+                "duration_note": "average launch duration of the dominant kernel: CUDA events recorded by the library on its "
+                                 "launch stream around every launch (mtp_profile_read), kernels serialised (lanes = 1) in a pass "
+                                 "right after the timed region; `kernels_lanes_on` holds the same events with the lanes of `value` "
+                                 "(spans of different lanes overlap there, so they sum to more than the step)",
+                "peak_source": "FP64 DFMA peak measured in this run by mtp_fp64_peak (DMMA m8n8k4: %.2f TFLOP/s); "
+                               "MEASURED_PEAKS.json has no FP64 entry" % dmma,
+                "kernels": kernels, "kernels_lanes_on": kernels_lanes,
                 "pipeline": {"ms_per_step_kernels": pipe_ms, "algorithmic_flops_per_atom": flops_atom,
                              "achieved": achieved_tf, "frac": achieved_tf / dfma,
-                             "note": "all kernels of one force evaluation; flops counted as written in pair_mtp.cpp "
-                                     "(SURVEY.md 8d), i.e. including the Jacobian the reference forms and this design never does"},
+                             "executed_flops_per_atom": executed_atom,
+                             "frac_executed": executed_atom * nlocal / (pipe_ms * 1e-3) / 1e12 / dfma if pipe_ms else None,
+                             "frac_of_value": flops_atom * nlocal / (ms_per_step * 1e-3) / 1e12 / dfma,
+                             "note": "all kernels of one force evaluation, serialised (`frac`, `frac_executed`) and as timed for "
+                                     "`value` with the lanes on (`frac_of_value`); flops counted as written in pair_mtp.cpp "
+                                     "(SURVEY.md 8d) unless marked executed"},
                 "algorithmic_bytes_per_atom": bytes_atom, "neighbors_listed": n_list, "neighbors_in_cutoff": n_cut,
                 "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                         "peak_source": hbm_src}}

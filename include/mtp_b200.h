@@ -115,6 +115,9 @@ typedef struct {
   int max_numneigh;               /* upper bound of numneigh[] over the listed centres, e.g. d_neighbors.extent(1)
                                      of the LAMMPS-KOKKOS list; 0 = unknown (mtp_compute then reduces numneigh on the
                                      device and waits for that one integer) */
+  int f_overwrite;                /* mtp_compute_host only: != 0 = the caller's f holds zeros on entry (LAMMPS's
+                                     force_clear precedes Pair::compute and this style is the first contributor), so the
+                                     result is STORED into f instead of added and f is never uploaded */
 } mtp_compute_args;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -150,9 +153,10 @@ int mtp_set_lanes(mtp_handle *h, int lanes);
 int mtp_compute(mtp_handle *h, const mtp_compute_args *device_args);
 /* Waits for the device and reports deferred errors (species bound check, pair_mtp.cpp:91-93). */
 int mtp_synchronize(mtp_handle *h);
-/* Same evaluation with HOST buffers: copies x/type (and the neighbor list when list_changed != 0,
- * i.e. on LAMMPS re-neighboring steps, neighbor->ago == 0) to the device, runs mtp_compute, adds the
- * result into the host f / eatom / vatom / grades and returns after the copies complete. */
+/* Same evaluation with HOST buffers: copies x (every call) and, when list_changed != 0 -- LAMMPS re-neighboring
+ * steps, neighbor->ago == 0, the only steps on which atoms migrate, are sorted or change type -- also type and the
+ * neighbor list to the device, runs mtp_compute, adds the result into the host f / eatom / vatom / grades and returns
+ * after the copies complete.  Between re-neighboring steps the list and the types stay resident on the device. */
 int mtp_compute_host(mtp_handle *h, const mtp_compute_args *host_args, int list_changed);
 
 /* ---- ghost-atom halo helpers (device) ---------------------------------------------------------- */

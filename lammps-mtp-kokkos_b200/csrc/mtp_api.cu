@@ -202,7 +202,7 @@ struct mtp_handle {
   // host-buffer path
   DevBuf<double> h_f0;
   cudaEvent_t ev_f0 = nullptr;
-  size_t h_nid = 0;
+  size_t h_nid = 0, h_ntype = 0;
   DevBuf<double> h_x, h_f, h_eatom, h_vatom, h_grades, h_ev, h_cfgc;
   DevBuf<int> h_type, h_ilist, h_numneigh, h_neigh;
   DevBuf<long long> h_offsets;
@@ -1446,11 +1446,17 @@ int mtp_compute_host(mtp_handle *h, const mtp_compute_args *a, int list_changed)
     if (!h->copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     if (!h->ev_f0) CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_f0, cudaEventDisableTiming));
     h->h_x.upload(a->x, 3 * nall, st);
-    h->h_type.upload(a->type, nall, st);
+    // types (like the list) only change on re-neighboring steps: atoms migrate / are sorted only then
+    if (relist || h->h_type.cap < nall || h->h_ntype != nall) {
+      h->h_type.upload(a->type, nall, st);
+      h->h_ntype = nall;
+    }
     // forces accumulate into the caller's f: the kernels add into a zeroed device array, the caller's values arrive
-    // on the copy stream while they run and are added at the end (keeps 24 B/atom of H2D off the critical path)
+    // on the copy stream while they run and are added at the end (keeps 24 B/atom of H2D off the critical path);
+    // f_overwrite: the caller's f is known to be zero, nothing to upload or add
+    const bool add_f = !a->f_overwrite;
     h->h_f.ensure(3 * nall);
-    h->h_f0.ensure(3 * nall);
+    if (add_f) h->h_f0.ensure(3 * nall);
     CUDA_CHECK(cudaMemsetAsync(h->h_f.p, 0, sizeof(double) * 3 * nall, st));
     std::vector<cudaEvent_t> ready;
     if (relist) {
@@ -1512,8 +1518,10 @@ int mtp_compute_host(mtp_handle *h, const mtp_compute_args *a, int list_changed)
       } else if (len > 0)
         CUDA_CHECK(cudaMemcpyAsync(h->h_neigh.p, a->neighbors, sizeof(int) * (size_t) len, cudaMemcpyHostToDevice, st));
     }
-    if (3 * nall) CUDA_CHECK(cudaMemcpyAsync(h->h_f0.p, a->f, sizeof(double) * 3 * nall, cudaMemcpyHostToDevice, h->copy_stream));
-    CUDA_CHECK(cudaEventRecord(h->ev_f0, h->copy_stream));
+    if (add_f) {
+      if (3 * nall) CUDA_CHECK(cudaMemcpyAsync(h->h_f0.p, a->f, sizeof(double) * 3 * nall, cudaMemcpyHostToDevice, h->copy_stream));
+      CUDA_CHECK(cudaEventRecord(h->ev_f0, h->copy_stream));
+    }
     d.max_numneigh = h->h_maxnn;
     d.x = h->h_x.p;
     d.type = h->h_type.p;
@@ -1554,8 +1562,8 @@ int mtp_compute_host(mtp_handle *h, const mtp_compute_args *a, int list_changed)
     t_up = now_ms();
     launch_site(h, d, st, ready.empty() ? nullptr : &ready);
     t_launch = now_ms();
-    CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_f0, 0));
-    if (nall) {
+    if (add_f) CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_f0, 0));
+    if (nall && add_f) {
       add_inplace_kernel<<<std::min<size_t>(4 * h->sm_count, (3 * nall + 255) / 256), 256, 0, st>>>(h->h_f.p, h->h_f0.p, 3 * nall);
       g_launches++;
     }

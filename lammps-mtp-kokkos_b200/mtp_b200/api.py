@@ -49,7 +49,7 @@ class MTPComputeArgs(C.Structure):
                 ("eflag", C.c_int), ("vflag", C.c_int), ("want_grade", C.c_int), ("natoms_total", C.c_longlong),
                 ("f", C.c_void_p), ("eatom", C.c_void_p), ("vatom", C.c_void_p), ("ev_out", C.c_void_p),
                 ("grades", C.c_void_p), ("cfg_candidate", C.c_void_p), ("within_cutoff", C.c_void_p),
-                ("stream", C.c_void_p), ("max_numneigh", C.c_int)]
+                ("stream", C.c_void_p), ("max_numneigh", C.c_int), ("f_overwrite", C.c_int)]
 
 
 EXPORTS = ["mtp_create_from_file", "mtp_create", "mtp_destroy", "mtp_last_error", "mtp_get_info",
@@ -192,7 +192,7 @@ class MTPB200:
     # ---- host buffers ---------------------------------------------------------------------------
     def compute_host(self, x, type_, ilist, numneigh, neigh, offsets=None, *, stride_i=0, stride_jj=1, eflag=3,
                      vflag=5, grade=False, natoms_total=0, want_mask=False, variant=VARIANT_LARGE, f_init=None,
-                     list_changed=True, out: HostResult | None = None) -> HostResult:
+                     list_changed=True, f_overwrite=False, out: HostResult | None = None) -> HostResult:
         x = np.ascontiguousarray(x, dtype=np.float64)
         type_ = np.ascontiguousarray(type_, dtype=np.int32)
         numneigh = np.ascontiguousarray(numneigh, dtype=np.int32)
@@ -218,6 +218,7 @@ class MTPB200:
         a.grades, a.cfg_candidate = r.grades.ctypes.data, r.candidate.ctypes.data
         a.within_cutoff = r.mask.ctypes.data if want_mask else None
         a.max_numneigh = 0          # mtp_compute_host derives it from the host numneigh array
+        a.f_overwrite = int(f_overwrite)
         self._keep = (x, type_, numneigh, neigh, il, off)
         _check(self.lib, self.lib.mtp_compute_host(self.h, C.byref(a), int(list_changed)))
         return r

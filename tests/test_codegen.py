@@ -48,13 +48,22 @@ def _host_check(tmp_path, pot_path, pot, latency, env=None):
     return info
 
 
-@pytest.mark.parametrize("level,species", [(8, 1), (10, 2), (12, 3), (16, 2), (20, 1)])
-def test_generated_program_matches_the_sequential_program(tmp_path, level, species):
+@pytest.mark.parametrize("level,species,latency", [(8, 1, False), (10, 2, False), (12, 3, False), (16, 2, False),
+                                                   (20, 1, True)])
+def test_generated_program_matches_the_sequential_program(tmp_path, level, species, latency):
     path, pot = util.write_potential(tmp_path, level, species)
-    info = _host_check(tmp_path, path, pot, False)
+    info = _host_check(tmp_path, path, pot, latency)
     tb = mtp_basis.build_mtp_tables(level)
     assert info["terms"] <= 3 * len(tb.alpha_index_times)           # forward T + reverse 2T, squares merged
     assert info["loads"] < info["terms"] or level <= 10            # the register cache removes most operand loads
+
+
+def test_throughput_shape_is_refused_when_a_warp_of_atoms_does_not_fit(tmp_path):
+    """Levels >= 20 keep the interpreting kernels for the throughput shape (see p4_choose): the generator says so."""
+    path, _ = util.write_potential(tmp_path, 20, 1)
+    with pytest.raises(api.MTPError, match="outside the generator's range"):
+        api.codegen_source(path, False)
+    assert api.codegen_source(path, True)[1]["atoms_per_cta"] == 8
 
 
 def test_latency_shape_and_two_atoms_per_lane(tmp_path):
