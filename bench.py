@@ -231,6 +231,9 @@ def main():
     ap.add_argument("--ref-cells", type=int, nargs=3, default=None, help="CPU-baseline sample box")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", default="large", choices=["large", "small"])
+    ap.add_argument("--device-list", default="auto", choices=["auto", "on", "off"],
+                    help="build the neighbor list on the device (mtp_neigh_build) instead of on the host; auto = on above 1.5 M "
+                         "atoms per GPU (config 5), where a host build and a host copy of the list make no sense")
     ap.add_argument("--grade-every", type=int, default=0,
                     help="config 4: request per-atom extrapolation grades every K-th step (fix pair semantics); 0 = never")
     ap.add_argument("--halo", default="direct", choices=["direct", "staged"],
@@ -305,45 +308,68 @@ def main():
 
     # one brick per rank on the grid {1, 2x1x1, 2x2x1, 2x2x2}; at N = 1 all six swaps are periodic self-images
     from mtp_b200 import decomp
+    per_cell = {"sc": 1, "bcc": 2, "fcc": 4, "diamond": 8}[cfg["kind"]]
+    devlist_mode = args.device_list == "on" or (args.device_list == "auto" and per_cell * cells[0] * cells[1] * cells[2] > 1500000)
     sysm, halo = decomp.make_rank_system(args.config, cells, brick_grid(world), rank, dev, mtp.lib,
-                                         direct=args.halo == "direct")
+                                         direct=args.halo == "direct", with_list=not devlist_mode)
     nlocal, nall = sysm.nlocal, sysm.nall
-
-    # workload statistics for the roofline (listed / in-cutoff neighbors per atom)
-    n_list = float(sysm.numneigh[:nlocal].mean())
-    ii = np.repeat(np.arange(nlocal), sysm.numneigh[:nlocal])
-    d2 = ((sysm.x[sysm.neigh] - sysm.x[ii]) ** 2).sum(axis=1)
-    n_cut = float((d2 <= pot.max_dist ** 2).sum() / nlocal)
-    del ii, d2
-    flops_atom = algorithmic_flops_per_atom(pot, n_list, n_cut)
-    bytes_atom = algorithmic_bytes_per_atom(n_list)
 
     # device-resident inputs
     t_x = torch.from_numpy(sysm.x).to(dev)
     t_type = torch.from_numpy(sysm.type).to(dev)
     t_ilist = torch.from_numpy(sysm.ilist).to(dev)
-    t_nn = torch.from_numpy(sysm.numneigh).to(dev)
-    t_neigh = torch.from_numpy(sysm.neigh).to(dev)
-    t_off = torch.from_numpy(sysm.offsets).to(dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    if devlist_mode:
+        # the list is built on the device from the uploaded positions (ghost rows included); row-major table
+        nn_d, t_neigh, max_nn = mtp.neigh_build(t_x, nlocal, sysm.rlist, stream=stream)
+        t_nn = torch.zeros(nall, dtype=torch.int32, device=dev)
+        t_nn[:nlocal] = nn_d
+        t_off, list_stride = None, int(t_neigh.shape[1])
+        n_list = float(nn_d.double().mean().item())
+        ns = min(nlocal, 65536)      # in-cutoff neighbors per atom from the first 65536 rows
+        rows = t_neigh[:ns].long().clamp_(0, nall - 1)
+        d2 = ((t_x[rows] - t_x[:ns, None, :]) ** 2).sum(dim=2)
+        live = torch.arange(list_stride, device=dev)[None, :] < nn_d[:ns, None]
+        n_cut = float(((d2 <= pot.max_dist ** 2) & live).sum().item() / ns)
+        del rows, d2, live
+    else:
+        t_nn = torch.from_numpy(sysm.numneigh).to(dev)
+        t_neigh = torch.from_numpy(sysm.neigh).to(dev)
+        t_off = torch.from_numpy(sysm.offsets).to(dev)
+        list_stride = 0
+        max_nn = int(sysm.numneigh[:nlocal].max())      # what a LAMMPS-KOKKOS list knows as d_neighbors.extent(1)
+        # workload statistics for the roofline (listed / in-cutoff neighbors per atom)
+        n_list = float(sysm.numneigh[:nlocal].mean())
+        ii = np.repeat(np.arange(nlocal), sysm.numneigh[:nlocal])
+        d2 = ((sysm.x[sysm.neigh] - sysm.x[ii]) ** 2).sum(axis=1)
+        n_cut = float((d2 <= pot.max_dist ** 2).sum() / nlocal)
+        del ii, d2
+    flops_atom = algorithmic_flops_per_atom(pot, n_list, n_cut)
+    bytes_atom = algorithmic_bytes_per_atom(n_list)
     t_f = torch.zeros((nall, 3), dtype=torch.float64, device=dev)
     t_ev = torch.zeros(8, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    stream = torch.cuda.current_stream().cuda_stream
-    max_nn = int(sysm.numneigh[:nlocal].max())      # what a LAMMPS-KOKKOS list knows as d_neighbors.extent(1)
 
     t_grades = torch.zeros(nall, dtype=torch.float64, device=dev) if args.grade_every else None
     step_no = [0]
 
-    def step_device():
+    lst = {"nn": t_nn, "neigh": t_neigh, "mx": max_nn}
+
+    def step_device(rebuild=False):
         # what LAMMPS does around Pair::compute every step: forward comm of x, zero f, compute, reverse comm of f,
-        # and the energy/virial all-reduce
+        # and the energy/virial all-reduce (rebuild: a re-neighboring step, list built on the device after the halo)
         halo.forward(t_x)
+        if rebuild:
+            nn_new, tab, mx = mtp.neigh_build(t_x, nlocal, sysm.rlist, stream=stream)
+            lst["nn"][:nlocal] = nn_new
+            lst["neigh"], lst["mx"] = tab, mx
         t_f.zero_()
         grade_step = bool(args.grade_every) and step_no[0] % args.grade_every == 0
         step_no[0] += 1
-        mtp.compute_device(t_x, t_type, t_ilist, t_nn, t_neigh, t_off, t_f, t_ev, eflag=1, vflag=1,
-                           variant=variant, stream=stream, max_numneigh=max_nn, grade=grade_step,
-                           grades=t_grades if grade_step else None)
+        mtp.compute_device(t_x, t_type, t_ilist, lst["nn"], lst["neigh"], t_off, t_f, t_ev, eflag=1, vflag=1,
+                           variant=variant, stream=stream, max_numneigh=lst["mx"], grade=grade_step,
+                           grades=t_grades if grade_step else None,
+                           stride_i=int(lst["neigh"].shape[1]) if devlist_mode else 0, stride_jj=1)
         halo.reverse(t_f)
         halo.allreduce_ev(t_ev)
 
@@ -401,7 +427,50 @@ def main():
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
     e2e = None
-    if world == 1:
+    devlist = None
+    if devlist_mode:
+        # large systems: the list never exists on the host.  Per rank and step: H2D of the owned positions (and types on
+        # re-neighboring steps) from pinned memory, halo forward, list rebuilt on the device (mtp_neigh_build), kernels,
+        # halo reverse, EV all-reduce, D2H of the owned forces + EV record
+        hx_t, _ = pinned_like(sysm.x[:nlocal])
+        ht_t, _ = pinned_like(sysm.type)
+        hf_t = torch.empty((nlocal, 3), dtype=torch.float64, pin_memory=True)
+        hev_t = torch.empty(8, dtype=torch.float64, pin_memory=True)
+
+        def step_e2e(k=0, list_every=1):
+            t_x[:nlocal].copy_(hx_t, non_blocking=True)
+            relist = k % list_every == 0
+            if relist:
+                t_type.copy_(ht_t, non_blocking=True)
+            step_device(rebuild=relist)
+            hf_t.copy_(t_f[:nlocal], non_blocking=True)
+            hev_t.copy_(t_ev, non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        e2e_n = {}
+        for every in (1, LIST_EVERY):
+            t0 = time.perf_counter()
+            for k in range(args.steps):
+                step_e2e(k, every)
+            barrier()
+            ms = 1e3 * (time.perf_counter() - t0) / args.steps
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            e2e_n[every] = ms
+        e2e_ms, e2e10_ms = e2e_n[1], e2e_n[LIST_EVERY]
+        list_bytes = 4 * nall
+        h2d = 24 * nlocal + list_bytes
+        d2h = 24 * nlocal + 64
+        e2e_energy = float(hev_t[0])
+        note = ("per rank and step, re-neighboring on EVERY step (worst case): H2D owned x, type from pinned memory, device halo "
+                "forward, full neighbor list rebuilt on the device (mtp_neigh_build), kernels, halo reverse, EV all-reduce, D2H "
+                "owned f + EV record; wall clock, max over ranks; bytes are per rank")
+    elif world == 1:
         # N = 1: the reference-facing C-ABI call with HOST buffers (what a host-resident LAMMPS hands the pair style)
         keep, hx = pinned_like(sysm.x)
         k2, htype = pinned_like(sysm.type)
@@ -429,7 +498,6 @@ def main():
         e2e10_ms = 1e3 * (time.perf_counter() - t0) / args.steps
         # informational: the list never crosses PCIe -- built on the device (mtp_neigh_build) on
         # every 10th step from the positions that were just uploaded; per step H2D x/type, kernels, D2H f + EV record
-        devlist = None
         try:
             hf_p = torch.empty((nall, 3), dtype=torch.float64, pin_memory=True)
             hev_p = torch.empty(8, dtype=torch.float64, pin_memory=True)
@@ -536,14 +604,14 @@ def main():
                             "h2d_bytes_per_step": int(h2d - list_bytes + list_bytes // LIST_EVERY), "d2h_bytes_per_step": int(d2h),
                             "note": "same step with the list (and types) re-sent on every %dth step only -- LAMMPS's "
                                     "re-neighboring cadence is at most that in a solid with the default 2 A skin" % LIST_EVERY}
-    if world == 1:
+    if devlist is not None:
         e2e["device_built_list"] = devlist
 
     # ---- informational: the reference's example deck as a device-resident MD loop (README.md:148-149: velocity
     # create + fix nve around the pair style): integrate, ghost images, list rebuild, pair style, reverse halo, all on
     # the device.  The random-init potential is rescaled by one factor to an RMS force of 0.05 eV/A.
     md = None
-    if world == 1 and args.md_steps > 0:
+    if world == 1 and args.md_steps > 0 and not devlist_mode:
         try:
             from mtp_b200.md import NVE, scale_to_rms_force
             rms = float((t_f[:nlocal] ** 2).sum(dim=1).mean().sqrt().item())
@@ -673,6 +741,7 @@ def main():
                            *brick_grid(world), args.halo, halo.bytes_per_step),
                        "l2": "256 MiB write between timed iterations (L2 flush), per-step CUDA events summed",
                        "variant": args.variant, "chunksize": args.chunksize, "lanes": args.lanes, "flags": "eflag=1 vflag=1",
+                       "neighbor_list": "built on the device (mtp_neigh_build)" if devlist_mode else "built on the host, resident on the device",
                        "grade_every": args.grade_every},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "energy": energy}

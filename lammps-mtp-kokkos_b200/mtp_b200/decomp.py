@@ -168,7 +168,7 @@ def _exchange_arrays(send_to, recv_from, arrays, device, rank):
     return [t.cpu().numpy() for t in recvs]
 
 
-def build_rank_system(x_own, types_own, sublo, subhi, grid, rank, gbox, cutoff, skin, device, lib=None):
+def build_rank_system(x_own, types_own, sublo, subhi, grid, rank, gbox, cutoff, skin, device, lib=None, with_list=True):
     """Ghost shell + send lists for this rank's brick [sublo, subhi) of the periodic global box ``gbox``."""
     world = grid[0] * grid[1] * grid[2]
     me = rank_coords(rank, grid)
@@ -207,7 +207,9 @@ def build_rank_system(x_own, types_own, sublo, subhi, grid, rank, gbox, cutoff, 
         t = np.concatenate([t, got[0][1], got[1][1]])
     x = np.ascontiguousarray(x)
     t = np.ascontiguousarray(t.astype(np.int32))
-    numneigh, offsets, flat = harness.neighbor_list(x, nlocal, rghost)
+    # with_list=False: the caller builds the list on the device (mtp_neigh_build); host arrays stay empty
+    numneigh, offsets, flat = harness.neighbor_list(x, nlocal, rghost) if with_list else (
+        np.zeros(len(x), np.int32), np.zeros(len(x) + 1, np.int64), np.zeros(0, np.int32))
     owner = np.full(len(x), -1, dtype=np.int32)
     owner[:nlocal] = np.arange(nlocal, dtype=np.int32)
     sysm = harness.System(box=np.asarray(gbox, dtype=np.float64), nlocal=nlocal, x=x, type=t, owner=owner,
@@ -316,7 +318,7 @@ class DirectHalo:
     allreduce_ev = Halo.allreduce_ev
 
 
-def build_rank_system_direct(x_own, types_own, sublo, subhi, grid, rank, gbox, cutoff, skin, device, lib=None):
+def build_rank_system_direct(x_own, types_own, sublo, subhi, grid, rank, gbox, cutoff, skin, device, lib=None, with_list=True):
     """Same ghost shell as ``build_rank_system`` (possibly in a different row order), built for ``DirectHalo``."""
     world = grid[0] * grid[1] * grid[2]
     me = rank_coords(rank, grid)
@@ -389,7 +391,9 @@ def build_rank_system_direct(x_own, types_own, sublo, subhi, grid, rank, gbox, c
     x = np.ascontiguousarray(np.concatenate([x] + [ghosts_x[k].reshape(-1, 3) for k in order]))
     t = np.ascontiguousarray(np.concatenate([t] + [ghosts_t[k] for k in order]).astype(np.int32))
     assert len(x) == halo.nall
-    numneigh, offsets, flat = harness.neighbor_list(x, nlocal, rghost)
+    # with_list=False: the caller builds the list on the device (mtp_neigh_build); host arrays stay empty
+    numneigh, offsets, flat = harness.neighbor_list(x, nlocal, rghost) if with_list else (
+        np.zeros(len(x), np.int32), np.zeros(len(x) + 1, np.int64), np.zeros(0, np.int32))
     owner = np.full(len(x), -1, dtype=np.int32)
     owner[:nlocal] = np.arange(nlocal, dtype=np.int32)
     sysm = harness.System(box=np.asarray(gbox, dtype=np.float64), nlocal=nlocal, x=x, type=t, owner=owner,
@@ -398,7 +402,8 @@ def build_rank_system_direct(x_own, types_own, sublo, subhi, grid, rank, gbox, c
     return sysm, halo
 
 
-def make_rank_system(config, cells, grid, rank, device, lib=None, cutoff=5.0, skin=2.0, jitter=0.05, direct=False):
+def make_rank_system(config, cells, grid, rank, device, lib=None, cutoff=5.0, skin=2.0, jitter=0.05, direct=False,
+                     with_list=True):
     """BASELINE.json weak-scaling layout: the per-GPU box of ``config`` replicated on the brick grid."""
     cfg = harness.CONFIGS[config]
     x, box = harness.lattice(cfg["kind"], cfg["a"], cells or cfg["cells"], jitter=jitter, seed=2024)
@@ -406,4 +411,5 @@ def make_rank_system(config, cells, grid, rank, device, lib=None, cutoff=5.0, sk
     me = np.array(rank_coords(rank, grid), dtype=np.float64)
     sublo = me * box
     build = build_rank_system_direct if direct else build_rank_system
-    return build(x + sublo, types, sublo, sublo + box, grid, rank, box * np.array(grid), cutoff, skin, device, lib)
+    return build(x + sublo, types, sublo, sublo + box, grid, rank, box * np.array(grid), cutoff, skin, device, lib,
+                 with_list=with_list)
