@@ -240,6 +240,7 @@ def main():
                     help="ghost exchange: one 26-direction stage (default) or LAMMPS's three dimension-by-dimension stages")
     ap.add_argument("--md-steps", type=int, default=50,
                     help="informational device-resident NVE run of this many steps after the bench (N = 1 only; 0 = off)")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: do not hide the halo exchange behind the interior atoms")
     ap.add_argument("--lanes", type=int, default=3, help="internal streams the super-chunks are dealt to (mtp_set_lanes)")
     ap.add_argument("--chunksize", type=int, default=131072,
                     help="pair_style ... chunksize N: README.md:44 of the reference asks the user to tune it (\"sufficient "
@@ -354,24 +355,36 @@ def main():
     step_no = [0]
 
     lst = {"nn": t_nn, "neigh": t_neigh, "mx": max_nn}
+    overlap = None
+    if world > 1 and args.halo == "direct" and not args.no_overlap:
+        overlap = decomp.OverlappedStep(halo, sysm.x[:nlocal], halo.sublo, halo.subhi, halo.rghost, dev)
+        if not overlap.enabled:
+            overlap = None
+
+    def compute_part(il, evbuf, grade_step=False):
+        mtp.compute_device(t_x, t_type, il, lst["nn"], lst["neigh"], t_off, t_f, evbuf, eflag=1, vflag=1,
+                           variant=variant, stream=stream, max_numneigh=lst["mx"], grade=grade_step,
+                           grades=t_grades if grade_step else None,
+                           stride_i=int(lst["neigh"].shape[1]) if devlist_mode else 0, stride_jj=1)
 
     def step_device(rebuild=False):
         # what LAMMPS does around Pair::compute every step: forward comm of x, zero f, compute, reverse comm of f,
-        # and the energy/virial all-reduce (rebuild: a re-neighboring step, list built on the device after the halo)
+        # and the energy/virial all-reduce (rebuild: a re-neighboring step, list built on the device after the halo).
+        # N > 1: the halo exchange runs behind the interior atoms (decomp.OverlappedStep)
+        grade_step = bool(args.grade_every) and step_no[0] % args.grade_every == 0
+        step_no[0] += 1
+        if overlap is not None and not rebuild and not grade_step:
+            overlap.run(t_x, t_f, t_ev, compute_part, t_ilist)
+            return
         halo.forward(t_x)
         if rebuild:
             nn_new, tab, mx = mtp.neigh_build(t_x, nlocal, sysm.rlist, stream=stream)
             lst["nn"][:nlocal] = nn_new
             lst["neigh"], lst["mx"] = tab, mx
         t_f.zero_()
-        grade_step = bool(args.grade_every) and step_no[0] % args.grade_every == 0
-        step_no[0] += 1
-        mtp.compute_device(t_x, t_type, t_ilist, lst["nn"], lst["neigh"], t_off, t_f, t_ev, eflag=1, vflag=1,
-                           variant=variant, stream=stream, max_numneigh=lst["mx"], grade=grade_step,
-                           grades=t_grades if grade_step else None,
-                           stride_i=int(lst["neigh"].shape[1]) if devlist_mode else 0, stride_jj=1)
+        compute_part(t_ilist, t_ev, grade_step)
         halo.reverse(t_f)
-        halo.allreduce_ev(t_ev)
+        halo.allreduce_ev(t_ev, grade_step)
 
     def barrier():
         if world > 1:
@@ -737,8 +750,10 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload, "atoms_per_gpu": nlocal, "ghosts_per_gpu": nall - nlocal,
-                       "parallelism": "brick grid %dx%dx%d, one rank per GPU, %s NCCL send/recv halo (%d B/rank/step)" % (
-                           *brick_grid(world), args.halo, halo.bytes_per_step),
+                       "parallelism": "brick grid %dx%dx%d, one rank per GPU, %s NCCL send/recv halo (%d B/rank/step)%s" % (
+                           *brick_grid(world), args.halo, halo.bytes_per_step,
+                           ", exchange overlapped with the interior atoms (%d + %d interior, %d boundary centres)" % (
+                               overlap.counts[0], overlap.counts[2], overlap.counts[1]) if overlap is not None else ""),
                        "l2": "256 MiB write between timed iterations (L2 flush), per-step CUDA events summed",
                        "variant": args.variant, "chunksize": args.chunksize, "lanes": args.lanes, "flags": "eflag=1 vflag=1",
                        "neighbor_list": "built on the device (mtp_neigh_build)" if devlist_mode else "built on the host, resident on the device",

@@ -138,11 +138,14 @@ class Halo:
                 else:
                     self._unpack_add(f, s, s.recvbuf)
 
-    def allreduce_ev(self, ev: torch.Tensor):
-        """E + 6 virial components: SUM over ranks; ev[7] (max grade): MAX (pair_mtp_extrapolation.cpp:369)."""
+    def allreduce_ev(self, ev: torch.Tensor, grade: bool = True):
+        """E + 6 virial components: SUM over ranks; ev[7] (max grade, grade steps only): MAX
+        (pair_mtp_extrapolation.cpp:379).  Neighbourhood mode only: in configuration mode the candidate VECTOR is summed
+        over ranks and the grade re-evaluated (pair_mtp_extrapolation.cpp:366-376), see allreduce_cfg_grade."""
         if self.world > 1:
             dist.all_reduce(ev[:7], op=dist.ReduceOp.SUM)
-            dist.all_reduce(ev[7:8], op=dist.ReduceOp.MAX)
+            if grade:
+                dist.all_reduce(ev[7:8], op=dist.ReduceOp.MAX)
 
 
 def _exchange_arrays(send_to, recv_from, arrays, device, rank):
@@ -270,6 +273,7 @@ class DirectHalo:
         self.sendbuf = torch.empty((so, 3), dtype=torch.float64, device=device)
         self.recvbuf = torch.empty((so, 3), dtype=torch.float64, device=device)
         self.bytes_per_step = 2 * 24 * so
+        self._ops = {}
 
     def _pack(self, x, lst, seg, shifts, out):
         n = len(lst)
@@ -295,27 +299,108 @@ class DirectHalo:
         else:
             f.index_add_(0, lst.long(), buf.clone())
 
-    def forward(self, x: torch.Tensor):
+    # The exchange is split in two halves so that a caller can put work between them: *_begin packs and posts the grouped
+    # NCCL send/recv (which run on NCCL's own stream), *_end makes the current stream wait for them and unpacks.
+    def forward_begin(self, x: torch.Tensor):
         n0 = self.nlocal
         self._pack(x, self.self_list, self.self_seg, self.self_shift, x[n0: n0 + self.nself])
         self._pack(x, self.rem_list, self.rem_seg, self.rem_shift, self.sendbuf)
-        ops = [dist.P2POp(dist.isend, self.sendbuf[o: o + n], p) for p, (o, n) in sorted(self.send_blocks.items()) if n]
-        ops += [dist.P2POp(dist.irecv, x[o: o + n], p) for p, (o, n) in sorted(self.recv_blocks.items()) if n]
-        if ops:
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
+        key = ("fwd", x.data_ptr())
+        ops = self._ops.get(key)
+        if ops is None:      # the P2P descriptors only depend on the buffers: built once per x tensor
+            ops = [dist.P2POp(dist.isend, self.sendbuf[o: o + n], p) for p, (o, n) in sorted(self.send_blocks.items()) if n]
+            ops += [dist.P2POp(dist.irecv, x[o: o + n], p) for p, (o, n) in sorted(self.recv_blocks.items()) if n]
+            self._ops[key] = ops
+        return dist.batch_isend_irecv(ops) if ops else []
 
-    def reverse(self, f: torch.Tensor):
-        ops = [dist.P2POp(dist.isend, f[o: o + n], p) for p, (o, n) in sorted(self.recv_blocks.items()) if n]
-        ops += [dist.P2POp(dist.irecv, self.recvbuf[o: o + n], p) for p, (o, n) in sorted(self.send_blocks.items()) if n]
-        if ops:
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
+    def forward_end(self, works):
+        for r in works:
+            r.wait()
+
+    def forward(self, x: torch.Tensor):
+        self.forward_end(self.forward_begin(x))
+
+    def reverse_begin(self, f: torch.Tensor):
+        key = ("rev", f.data_ptr())
+        ops = self._ops.get(key)
+        if ops is None:
+            ops = [dist.P2POp(dist.isend, f[o: o + n], p) for p, (o, n) in sorted(self.recv_blocks.items()) if n]
+            ops += [dist.P2POp(dist.irecv, self.recvbuf[o: o + n], p) for p, (o, n) in sorted(self.send_blocks.items()) if n]
+            self._ops[key] = ops
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def reverse_end(self, f: torch.Tensor, works):
+        for r in works:
+            r.wait()
         n0 = self.nlocal
         self._unpack_add(f, self.self_list, f[n0: n0 + self.nself])
         self._unpack_add(f, self.rem_list, self.recvbuf)
 
-    allreduce_ev = Halo.allreduce_ev
+    def reverse(self, f: torch.Tensor):
+        self.reverse_end(f, self.reverse_begin(f))
+
+    def allreduce_ev(self, ev: torch.Tensor, grade: bool = True):
+        """E + 6 virial components: one SUM over ranks; the max grade ev[7] (pair_mtp_extrapolation.cpp:379) only on
+        grade steps."""
+        if self.world > 1:
+            dist.all_reduce(ev[:7], op=dist.ReduceOp.SUM)
+            if grade:
+                dist.all_reduce(ev[7:8], op=dist.ReduceOp.MAX)
+
+
+def split_interior(x_own: np.ndarray, sublo, subhi, rghost: float):
+    """Owned atoms whose whole neighbor list (radius rghost = cutoff + skin) lies inside the brick cannot have a ghost
+    neighbor: their forces need no halo.  Returns (interior ids, boundary ids), both ascending int32."""
+    lo, hi = np.asarray(sublo, dtype=np.float64), np.asarray(subhi, dtype=np.float64)
+    inside = np.all((x_own > lo + rghost) & (x_own < hi - rghost), axis=1)
+    ids = np.arange(len(x_own), dtype=np.int32)
+    return ids[inside], ids[~inside]
+
+
+class OverlappedStep:
+    """One force evaluation of a rank with the halo exchange hidden behind the interior atoms:
+
+        forward halo posted  ||  pair style on the first half of the interior atoms
+        pair style on the boundary atoms (needs the ghosts)
+        reverse halo posted  ||  pair style on the second half of the interior atoms
+        ghost forces added, one 7-double all-reduce
+
+    ``compute(ilist, ev)`` is the caller's closure around ``MTPB200.compute_device`` for a list of centre atoms; the
+    three partial energy / virial records are summed before the all-reduce.  With one rank (no remote peers) the plain
+    sequence forward / compute / reverse is used."""
+
+    def __init__(self, halo, x_own, sublo, subhi, rghost, device, min_part=16384):
+        self.halo = halo
+        interior, boundary = split_interior(x_own, sublo, subhi, rghost)
+        self.enabled = isinstance(halo, DirectHalo) and halo.world > 1 and len(interior) >= 2 * min_part and len(boundary) > 0
+        half = len(interior) // 2
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)  # noqa: E731
+        self.parts = [t(interior[:half]), t(boundary), t(interior[half:])] if self.enabled else []
+        self.counts = (int(half), int(len(boundary)), int(len(interior) - half))
+        self.evs = [torch.zeros(8, dtype=torch.float64, device=device) for _ in range(3)]
+
+    def run(self, x, f, ev, compute, all_ilist, grade=False):
+        h = self.halo
+        if not self.enabled:
+            h.forward(x)
+            f.zero_()
+            compute(all_ilist, ev)
+            h.reverse(f)
+            h.allreduce_ev(ev, grade) if isinstance(h, DirectHalo) else h.allreduce_ev(ev)
+            return
+        works = h.forward_begin(x)
+        f.zero_()
+        compute(self.parts[0], self.evs[0])
+        h.forward_end(works)
+        compute(self.parts[1], self.evs[1])
+        works = h.reverse_begin(f)
+        compute(self.parts[2], self.evs[2])
+        h.reverse_end(f, works)
+        torch.add(self.evs[0], self.evs[1], out=ev)
+        ev.add_(self.evs[2])
+        if grade:
+            ev[7] = torch.maximum(torch.maximum(self.evs[0][7], self.evs[1][7]), self.evs[2][7])
+        h.allreduce_ev(ev, grade)
 
 
 def build_rank_system_direct(x_own, types_own, sublo, subhi, grid, rank, gbox, cutoff, skin, device, lib=None, with_list=True):
@@ -387,6 +472,7 @@ def build_rank_system_direct(x_own, types_own, sublo, subhi, grid, rank, gbox, c
     for k, rx, rt in recvs:
         ghosts_x[k], ghosts_t[k] = rx.cpu().numpy(), rt.cpu().numpy()
     halo = DirectHalo(rank, world, device, lib, nlocal, segs)
+    halo.sublo, halo.subhi, halo.rghost = np.asarray(sublo, dtype=np.float64), np.asarray(subhi, dtype=np.float64), rghost
     order = halo.ghost_order
     x = np.ascontiguousarray(np.concatenate([x] + [ghosts_x[k].reshape(-1, 3) for k in order]))
     t = np.ascontiguousarray(np.concatenate([t] + [ghosts_t[k] for k in order]).astype(np.int32))

@@ -21,12 +21,13 @@ from oracle_py import OracleMTP  # noqa: E402
 
 def main():
     out = sys.argv[1]
-    direct = len(sys.argv) > 2 and sys.argv[2] == "direct"
+    kind = sys.argv[2] if len(sys.argv) > 2 else "staged"
+    direct = kind in ("direct", "overlap")
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     grid = decomp.brick_grid(world)
     dev = torch.device("cpu")
-    cells = (5, 5, 5)
+    cells = (7, 7, 7) if kind == "overlap" else (5, 5, 5)
     pot = almtp.random_potential(10, 2)
     sysm, halo = decomp.make_rank_system(2, cells, grid, rank, dev, direct=direct)
     nlocal = sysm.nlocal
@@ -38,11 +39,38 @@ def main():
     halo.forward(x)
     assert not torch.equal(stale_ghosts, x[nlocal:])
     orc = OracleMTP(pot)
-    r = orc.compute(x.numpy(), sysm.type, sysm.ilist, sysm.numneigh, sysm.neigh, sysm.offsets, eflag=3, vflag=5)
-    f = torch.from_numpy(r.f.copy())
-    halo.reverse(f)
-    ev = torch.from_numpy(r.ev.copy())
-    halo.allreduce_ev(ev)
+    if kind == "overlap":
+        # the split-phase exchange with the interior / boundary partition (the oracle stands in for the kernels)
+        x[nlocal:] = stale_ghosts
+        ov = decomp.OverlappedStep(halo, sysm.x[:nlocal], halo.sublo, halo.subhi, halo.rghost, dev, min_part=1)
+        assert ov.enabled and min(ov.counts) > 0 and sum(ov.counts) == nlocal, ov.counts
+        f = torch.zeros((sysm.nall, 3), dtype=torch.float64)
+        ev = torch.zeros(8, dtype=torch.float64)
+        eatom = np.zeros(sysm.nall)
+
+        def part(il, evbuf):
+            ids = il.numpy()
+            if il is ov.parts[0]:      # interior atoms must not need the halo: evaluate them on the STALE ghosts
+                xs = x.numpy().copy()
+                xs[nlocal:] = stale_ghosts.numpy()
+            else:
+                xs = x.numpy()
+            r = orc.compute(xs, sysm.type, ids, sysm.numneigh, sysm.neigh, sysm.offsets, eflag=3, vflag=5)
+            f.add_(torch.from_numpy(r.f))
+            evbuf.copy_(torch.from_numpy(r.ev))
+            eatom[ids] = r.eatom[ids]
+        ov.run(x, f, ev, part, torch.from_numpy(sysm.ilist))
+
+        class R:      # what the gather below expects
+            pass
+        r = R()
+        r.eatom = eatom
+    else:
+        r = orc.compute(x.numpy(), sysm.type, sysm.ilist, sysm.numneigh, sysm.neigh, sysm.offsets, eflag=3, vflag=5)
+        f = torch.from_numpy(r.f.copy())
+        halo.reverse(f)
+        ev = torch.from_numpy(r.ev.copy())
+        halo.allreduce_ev(ev)
     gathered = [None] * world
     dist.all_gather_object(gathered, (x[:nlocal].numpy(), sysm.type[:nlocal], f[:nlocal].numpy(), r.eatom[:nlocal]))
     if rank == 0:

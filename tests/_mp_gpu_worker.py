@@ -18,14 +18,15 @@ from mtp_b200.api import MTPB200  # noqa: E402
 
 def main():
     out, tmp = sys.argv[1], sys.argv[2]
-    direct = len(sys.argv) > 3 and sys.argv[3] == "direct"
+    kind = sys.argv[3] if len(sys.argv) > 3 else "staged"
+    direct = kind in ("direct", "overlap")
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     rank, world = dist.get_rank(), dist.get_world_size()
     grid = decomp.brick_grid(world)
-    cells = (5, 5, 5)
+    cells = (7, 7, 7) if kind == "overlap" else (5, 5, 5)
     pot = almtp.random_potential(10, 2)
     path = os.path.join(tmp, f"p{rank}.almtp")
     almtp.write_almtp(path, pot)
@@ -40,11 +41,22 @@ def main():
     f = torch.zeros((nall, 3), dtype=torch.float64, device=dev)
     ev = torch.zeros(8, dtype=torch.float64, device=dev)
     eatom = torch.zeros(nall, dtype=torch.float64, device=dev)
-    halo.forward(x)
-    mtp.compute_device(x, t_type, t_il, t_nn, t_ne, t_off, f, ev, eatom=eatom, eflag=3, vflag=1,
-                       stream=torch.cuda.current_stream().cuda_stream)
-    halo.reverse(f)
-    halo.allreduce_ev(ev)
+    if kind == "overlap":
+        # halo exchange hidden behind the interior atoms: three partial evaluations, one reduction
+        ov = decomp.OverlappedStep(halo, sysm.x[:nlocal], halo.sublo, halo.subhi, halo.rghost, dev, min_part=1)
+        assert ov.enabled == (world > 1) and (world == 1 or min(ov.counts) > 0), ov.counts
+
+        def part(il, evbuf):
+            mtp.compute_device(x, t_type, il, t_nn, t_ne, t_off, f, evbuf, eatom=eatom, eflag=3, vflag=1,
+                               stream=torch.cuda.current_stream().cuda_stream)
+        f.fill_(7.0)      # run() zeroes f itself
+        ov.run(x, f, ev, part, t_il)
+    else:
+        halo.forward(x)
+        mtp.compute_device(x, t_type, t_il, t_nn, t_ne, t_off, f, ev, eatom=eatom, eflag=3, vflag=1,
+                           stream=torch.cuda.current_stream().cuda_stream)
+        halo.reverse(f)
+        halo.allreduce_ev(ev)
     mtp.synchronize()
     gathered = [None] * world
     dist.all_gather_object(gathered, (x[:nlocal].cpu().numpy(), sysm.type[:nlocal], f[:nlocal].cpu().numpy(),

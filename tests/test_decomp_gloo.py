@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("kind", ["staged", "direct"])
+@pytest.mark.parametrize("kind", ["staged", "direct", "overlap"])
 @pytest.mark.parametrize("world", [2, 4])
 def test_decomposed_equals_global(tmp_path, built, world, kind):
     out = str(tmp_path / "res.npz")

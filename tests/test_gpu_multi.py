@@ -46,7 +46,7 @@ def test_one_rank_device_halo(tmp_path, built, kind):
     _check(_run(1, tmp_path, kind))
 
 
-@pytest.mark.parametrize("kind", ["staged", "direct"])
+@pytest.mark.parametrize("kind", ["staged", "direct", "overlap"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_decomposed_cuda_equals_global(tmp_path, built, world, kind):
     import torch
