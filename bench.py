@@ -240,7 +240,9 @@ def main():
                     help="ghost exchange: one 26-direction stage (default) or LAMMPS's three dimension-by-dimension stages")
     ap.add_argument("--md-steps", type=int, default=50,
                     help="informational device-resident NVE run of this many steps after the bench (N = 1 only; 0 = off)")
-    ap.add_argument("--no-overlap", action="store_true", help="N > 1: do not hide the halo exchange behind the interior atoms")
+    ap.add_argument("--overlap", action="store_true",
+                    help="N > 1: hide the halo exchange behind the interior atoms (decomp.OverlappedStep: three partial "
+                         "evaluations per step; measured slower than the plain sequence at config 2, see DESIGN.md)")
     ap.add_argument("--lanes", type=int, default=3, help="internal streams the super-chunks are dealt to (mtp_set_lanes)")
     ap.add_argument("--chunksize", type=int, default=131072,
                     help="pair_style ... chunksize N: README.md:44 of the reference asks the user to tune it (\"sufficient "
@@ -356,7 +358,7 @@ def main():
 
     lst = {"nn": t_nn, "neigh": t_neigh, "mx": max_nn}
     overlap = None
-    if world > 1 and args.halo == "direct" and not args.no_overlap:
+    if world > 1 and args.halo == "direct" and args.overlap:
         overlap = decomp.OverlappedStep(halo, sysm.x[:nlocal], halo.sublo, halo.subhi, halo.rghost, dev)
         if not overlap.enabled:
             overlap = None
