@@ -91,6 +91,7 @@ struct PassBufs {
 
 }    // namespace
 
+typedef void (*V2GatherFn)(mtpb200::DevPotential, mtpb200::SiteArgs, mtpb200::PairBuf);
 struct ChunkBufs {
   DevBuf<int> level_begin, node, term_begin;
   DevBuf<uint32_t> term_idx;
@@ -241,6 +242,7 @@ struct mtp_handle {
   Lane lanes[kMaxLanes];
   cudaEvent_t ev_fork = nullptr;
   int nlanes = 2;
+  V2GatherFn v2_radial = nullptr;
   int v2_grid_g = 0, v2_grid_r = 0, v2_grid_m = 0, v2_grid_f = 0, v2_grid_fg[2] = {0, 0}, v2_ab = 0;
   size_t v2_smem_g = 0, v2_smem_f = 0, v2_smem_m = 0;
   int v2_chunk = 0;
@@ -322,12 +324,12 @@ typedef void (*V2ForcesKernel)(SiteArgs, PairBuf, const double *, int, double *)
 constexpr int v2_ab_for(int kf) { return 2 * kf * 64 * 8 <= 110 * 1024 ? 64 : 2 * kf * 32 * 8 <= 110 * 1024 ? 32 : 2 * kf * 16 * 8 <= 110 * 1024 ? 16 : 8; }
 struct V2Entry {
   int d0, R, KF, NP, AB;
-  V2GatherKernel radial;
+  V2GatherKernel radial_v[3];    // {resident CTAs per SM, batches of 32 neighbors in flight}: {2, 3}, {3, 1}, {3, 2}
   V2MomentsKernel moments;
   V2ForcesKernel forces[2];    // [grade step]
 };
 #define V2_ENTRY(D)                                                                                                    \
-  {D, V2Shape<D>::R, V2Shape<D>::KF, V2Shape<D>::NP, v2_ab_for(V2Shape<D>::KF), mtp_gather_radial_kernel<V2Shape<D>::R>, \
+  {D, V2Shape<D>::R, V2Shape<D>::KF, V2Shape<D>::NP, v2_ab_for(V2Shape<D>::KF), {mtp_gather_radial_kernel<V2Shape<D>::R, 2, 3>, mtp_gather_radial_kernel<V2Shape<D>::R, 3, 1>, mtp_gather_radial_kernel<V2Shape<D>::R, 3, 2>}, \
    mtp_moments_v2<D>,                                                                                                  \
    {mtp_forces_v2<D, v2_ab_for(V2Shape<D>::KF), false>, mtp_forces_v2<D, v2_ab_for(V2Shape<D>::KF), true>}}
 const V2Entry kV2[] = {V2_ENTRY(0), V2_ENTRY(1), V2_ENTRY(2), V2_ENTRY(3), V2_ENTRY(4), V2_ENTRY(5),
@@ -533,17 +535,26 @@ void upload_potential(mtp_handle *h)
     const V2Entry &E = kV2[h->v2_entry];
     const int nrad = d.S * d.S * d.R * d.B;
     h->v2_smem_g = (size_t) ((nrad + 1) & ~1) * 8 + (size_t) 8 * V2_RING * 4 * 8;    // coefficients + one ring per warp
-    bool ok = h->v2_smem_g <= max_dynamic_smem((const void *) E.radial, smem_max);
+    // resident CTAs per SM the gather kernel is compiled for: the gather is bound by the latency of its L2 gathers, so
+    // resident warps count more than registers (the radial phase spills a few values at 48 registers)
+    int gv = 0;
+    if (const char *e = getenv("MTP_B200_GR_VARIANT")) gv = std::max(0, std::min(2, atoi(e)));
+    h->v2_radial = E.radial_v[gv];
+    bool ok = h->v2_smem_g <= max_dynamic_smem((const void *) h->v2_radial, smem_max);
     if (ok) {
-      CUDA_CHECK(cudaFuncSetAttribute((const void *) E.radial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->v2_smem_g));
+      CUDA_CHECK(cudaFuncSetAttribute((const void *) h->v2_radial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->v2_smem_g));
       if (!getenv("MTP_B200_NO_CARVEOUT")) {
-        CUDA_CHECK(cudaFuncSetAttribute((const void *) E.radial, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        // the gather lives on its L1 hit rate (see the kernel): it asks for the smallest shared-memory carve-out that holds
+        // its rings, unlike the other kernels of the pipeline, which all ask for the maximum
+        int carve = 25;
+        if (const char *e = getenv("MTP_B200_GR_CARVEOUT")) carve = atoi(e);
+        CUDA_CHECK(cudaFuncSetAttribute((const void *) h->v2_radial, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         CUDA_CHECK(cudaFuncSetAttribute((const void *) E.moments, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         for (int gq = 0; gq < 2; gq++)
           CUDA_CHECK(cudaFuncSetAttribute((const void *) E.forces[gq], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       }
       int per_sm = 0;
-      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.radial, 256, h->v2_smem_g));
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) h->v2_radial, 256, h->v2_smem_g));
       h->v2_grid_r = std::max(1, per_sm) * h->sm_count;
       h->v2_grid_g = h->v2_grid_r;
       h->v2_smem_m = (size_t) 2 * V2_NT * (3 + E.R) * 33 * 8;
@@ -927,7 +938,7 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
       {
         ProfSpan sp(h, MTP_PROF_GATHER, ls);
         const int gr = std::max(1, std::min(h->v2_grid_r, (n + 7) / 8));
-        E.radial<<<gr, 256, h->v2_smem_g, ls>>>(d, s, pb);
+        h->v2_radial<<<gr, 256, h->v2_smem_g, ls>>>(d, s, pb);
       }
       {
         ProfSpan sp(h, MTP_PROF_MOMENTS, ls);

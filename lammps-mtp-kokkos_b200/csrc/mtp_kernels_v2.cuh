@@ -159,8 +159,8 @@ __device__ __forceinline__ void radial_unrolled(const DevPotential &pot, const d
 // The displacement never travels through global memory, every lane of the radial phase is busy, and the FP64 work of
 // one warp runs under the gather latency of the others.
 constexpr int V2_RING = 64;
-template <int R>
-__global__ void __launch_bounds__(256, 3)
+template <int R, int MINB, int V2_GB>
+__global__ void __launch_bounds__(256, MINB)
 mtp_gather_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
 {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -173,9 +173,51 @@ mtp_gather_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
     s_ct[(ri * pot.R + mu) * SS + pt] = pot.radial[t];
   }
   __syncthreads();
-  for (int ii = blockIdx.x * W + warp; ii < a.inum; ii += gridDim.x * W) {
+  // The chain ilist -> {position, numneigh, row offset} -> neighbor ids -> neighbor records is four dependent memory
+  // latencies per centre.  It is software-pipelined: the id of the centre after next and the header of the next centre
+  // are requested before the current centre is processed, and the ids / records of up to V2_GB batches of 32 listed
+  // neighbors are requested back to back, so that a centre costs about two exposed latencies instead of eight.
+  struct Hdr {
+    int i, jnum, itype;
+    long long row0;
+    double x0, x1, x2;
+  };
+  // every warp walks a CONTIGUOUS run of the list: consecutive centres share most of their neighbors (the list is in
+  // spatial order after LAMMPS's atom sort), so the gathered records of a run stay in L1 (the kernel asks for a large
+  // L1 carve-out) and only ~10 % of the gathers go to L2
+  const int nwarps = gridDim.x * W, gw = blockIdx.x * W + warp;
+  const int per = (a.inum + nwarps - 1) / nwarps;
+  const int ii_begin = min(a.inum, gw * per), ii_end = min(a.inum, ii_begin + per);
+  const int stride = 1;
+  auto load_id = [&](int ii) { return ii < ii_end ? (a.ilist ? a.ilist[a.first_ii + ii] : a.first_ii + ii) : 0; };
+  auto load_hdr = [&](int i, Hdr &h) {
+    h.i = i;
+    ld_atomrec(a.xt + i, h.x0, h.x1, h.x2, h.itype);
+    h.jnum = a.numneigh[i];
+    h.row0 = a.neigh_offsets ? a.neigh_offsets[i] : (long long) i * a.stride_i;
+  };
+  int ii = ii_begin;
+  Hdr nxt;
+  nxt.i = nxt.jnum = nxt.itype = 0;
+  nxt.row0 = 0;
+  nxt.x0 = nxt.x1 = nxt.x2 = 0.0;
+  if (ii < ii_end) load_hdr(load_id(ii), nxt);
+  int id_after = load_id(ii + stride);
+  for (; ii < ii_end; ii += stride) {
     V1Atom at;
-    v1_load_atom(pot, a, ii, lane, at);
+    at.i = nxt.i;
+    at.itype = nxt.itype;
+    at.jnum = nxt.jnum;
+    at.row0 = nxt.row0;
+    at.xi0 = nxt.x0;
+    at.xi1 = nxt.x1;
+    at.xi2 = nxt.x2;
+    if (at.itype < 0 || at.itype >= pot.S) {    // pair_mtp.cpp:91-93
+      if (lane == 0) atomicOr(a.status, 1);
+      at.itype = 0;
+    }
+    if (ii + stride < ii_end) load_hdr(id_after, nxt);
+    id_after = load_id(ii + 2 * stride);
     const long long slot0 = (long long) ii * pb.ncap;
     int head = 0, count = 0, done = 0;
     // lane = entry `head + lane` of the ring -> record `done + lane` of this centre
@@ -186,8 +228,10 @@ mtp_gather_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
         const double r0 = ring[e], r1 = ring[V2_RING + e], r2 = ring[2 * V2_RING + e];
         const int2 jj = reinterpret_cast<const int2 *>(ring + 3 * V2_RING)[e];
         const int jt = jj.y;
-        const double dist = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2)));
-        const double invd = 1.0 / dist;
+        // one reciprocal square root gives both d and 1/d (the cutoff mask above used rsq itself, bit-exactly)
+        const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2));
+        const double invd = rsqrt(rsq);
+        const double dist = rsq * invd;
         double F[R], Fd[R];
         const double *ct = s_ct + (at.itype * pot.S + jt);
         if (pot.B == 8) radial_unrolled<R, 8>(pot, ct, SS, dist, F, Fd);
@@ -238,38 +282,48 @@ mtp_gather_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
       count -= n;
       done += n;
     };
-    for (int base = 0; base < at.jnum; base += 32) {
-      const int jj = base + lane;
-      bool within = false;
-      int j = 0, jt = 0;
-      double r0 = 0, r1 = 0, r2 = 0;
-      if (jj < at.jnum) {
-        const long long pos = at.row0 + (long long) jj * a.stride_jj;
-        j = a.neighbors[pos] & a.neighmask;
-        double nx, ny, nz;
-        ld_atomrec(a.xt + j, nx, ny, nz, jt);
-        r0 = nx - at.xi0;
-        r1 = ny - at.xi1;
-        r2 = nz - at.xi2;
-        // separately rounded, left to right, exactly pair_mtp.cpp:121-123 (no FMA contraction)
-        const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2));
-        within = !(rsq > pot.cutsq);
-        if (jt < 0 || jt >= pot.S) {    // pair_mtp.cpp:116-118
-          atomicOr(a.status, 1);
-          within = false;
+    for (int base0 = 0; base0 < at.jnum; base0 += 32 * V2_GB) {
+      int jv[V2_GB], jtv[V2_GB];
+      double nx[V2_GB], ny[V2_GB], nz[V2_GB];
+#pragma unroll
+      for (int b = 0; b < V2_GB; b++) {
+        const int jj = base0 + 32 * b + lane;
+        jv[b] = jj < at.jnum ? (a.neighbors[at.row0 + (long long) jj * a.stride_jj] & a.neighmask) : at.i;
+      }
+#pragma unroll
+      for (int b = 0; b < V2_GB; b++)
+        if (base0 + 32 * b < at.jnum) ld_atomrec(a.xt + jv[b], nx[b], ny[b], nz[b], jtv[b]);    // warp-uniform condition
+#pragma unroll
+      for (int b = 0; b < V2_GB; b++) {
+        if (base0 + 32 * b >= at.jnum) break;
+        const int jj = base0 + 32 * b + lane;
+        bool within = false;
+        const int j = jv[b], jt = jtv[b];
+        double r0 = 0, r1 = 0, r2 = 0;
+        if (jj < at.jnum) {
+          r0 = nx[b] - at.xi0;
+          r1 = ny[b] - at.xi1;
+          r2 = nz[b] - at.xi2;
+          // separately rounded, left to right, exactly pair_mtp.cpp:121-123 (no FMA contraction)
+          const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2));
+          within = !(rsq > pot.cutsq);
+          if (jt < 0 || jt >= pot.S) {    // pair_mtp.cpp:116-118
+            atomicOr(a.status, 1);
+            within = false;
+          }
+          if (a.within) a.within[at.row0 + (long long) jj * a.stride_jj] = within ? 1 : 0;
         }
-        if (a.within) a.within[pos] = within ? 1 : 0;
+        const unsigned bal = __ballot_sync(FULL, within);
+        if (within) {
+          const int e = (head + count + __popc(bal & ((1u << lane) - 1u))) & (V2_RING - 1);
+          ring[e] = r0;
+          ring[V2_RING + e] = r1;
+          ring[2 * V2_RING + e] = r2;
+          reinterpret_cast<int2 *>(ring + 3 * V2_RING)[e] = make_int2(j, jt);
+        }
+        count += __popc(bal);
+        if (count >= 32) flush(32);
       }
-      const unsigned bal = __ballot_sync(FULL, within);
-      if (within) {
-        const int e = (head + count + __popc(bal & ((1u << lane) - 1u))) & (V2_RING - 1);
-        ring[e] = r0;
-        ring[V2_RING + e] = r1;
-        ring[2 * V2_RING + e] = r2;
-        reinterpret_cast<int2 *>(ring + 3 * V2_RING)[e] = make_int2(j, jt);
-      }
-      count += __popc(bal);
-      if (count >= 32) flush(32);
     }
     if (count > 0) flush(count);
     if (lane == 0) pb.pcnt[ii] = done;
