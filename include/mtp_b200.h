@@ -24,11 +24,13 @@
 #ifndef MTP_B200_H
 #define MTP_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define MTP_B200_ABI_VERSION 4 /* 4: + mtp_codegen_source, mtp_codegen_prebuild, mtp_program_kernel_note */
+#define MTP_B200_ABI_VERSION 4 /* 4: + mtp_codegen_source, mtp_codegen_prebuild, mtp_program_kernel_note, mtp_fetch_grades, mtp_select_grades_host, mtp_cfg_grade, mtp_alloc_pinned; mtp_compute_args.f_overwrite */
 
 #define MTP_OK 0
 #define MTP_ERR_ARG (-1)      /* bad argument */
@@ -191,6 +193,23 @@ int mtp_neigh_build(mtp_handle *h, int nlocal, int nall, const double *x, double
  * Blocks until the count is known. */
 int mtp_select_grades(mtp_handle *h, const double *grades, int n, double threshold, int *indices_out, int *count_out,
                       void *stream);
+
+/* Host-buffer flavour of the same (plain LAMMPS): the neighbourhood grades of the last grade step of mtp_compute_host()
+ * stay resident on the device (they are copied to the host only when args->grades is given).
+ *   mtp_fetch_grades        copies the first n of them to the host -- what extract_peratom("extrapolation") hands to
+ *                           `fix pair` and what the .cfg writer needs when a configuration is selected
+ *                           (pair_mtp_extrapolation.cpp:641-652, 418-425);
+ *   mtp_select_grades_host  ids (ascending) and grades of the atoms i < n with grade >= threshold: only those cross PCIe.
+ *                           *count_out = number selected; at most cap of them are written. */
+int mtp_fetch_grades(mtp_handle *h, double *grades_host, int n);
+int mtp_select_grades_host(mtp_handle *h, int n, double threshold, int *ids_out, double *grades_out, int cap, int *count_out);
+/* Configuration-mode grade of a candidate vector that was summed over ranks on the host (MPI_Allreduce,
+ * pair_mtp_extrapolation.cpp:366-376): max_i |Ainv[i,:] . b| / natoms_total, evaluated on the device against the
+ * resident inverse active set. */
+int mtp_cfg_grade(mtp_handle *h, const double *candidate_host, long long natoms_total, double *grade_out);
+/* page-locked host memory for buffers the device writes directly (ev_out of mtp_compute in the LAMMPS-KOKKOS flavour) */
+void *mtp_alloc_pinned(size_t bytes);
+void mtp_free_pinned(void *p);
 
 /* ---- velocity-Verlet half steps on the device (the steps either side of the path) ---- */
 /* Upstream FixNVE::initial_integrate / final_integrate, which the reference's example deck runs around the pair style

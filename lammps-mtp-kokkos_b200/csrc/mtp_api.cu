@@ -203,9 +203,10 @@ struct mtp_handle {
   // host-buffer path
   DevBuf<double> h_f0;
   cudaEvent_t ev_f0 = nullptr;
-  size_t h_nid = 0, h_ntype = 0;
+  size_t h_nid = 0, h_ntype = 0, h_grades_n = 0;
   DevBuf<double> h_x, h_f, h_eatom, h_vatom, h_grades, h_ev, h_cfgc;
-  DevBuf<int> h_type, h_ilist, h_numneigh, h_neigh;
+  DevBuf<int> h_type, h_ilist, h_numneigh, h_neigh, sel_ids;
+  DevBuf<double> sel_val;
   DevBuf<long long> h_offsets;
   DevBuf<unsigned char> h_within;
   long long h_list_len = 0;
@@ -268,6 +269,14 @@ size_t max_dynamic_smem(const void *fn, size_t optin)
   cudaFuncAttributes fa;
   CUDA_CHECK(cudaFuncGetAttributes(&fa, fn));
   return optin > fa.sharedSizeBytes ? optin - fa.sharedSizeBytes : 0;
+}
+
+// Kernel attributes are per-device state shared by every handle of the process: the dynamic shared-memory limit of a
+// kernel is therefore always raised to the device's opt-in maximum (never to what one potential needs -- a second
+// handle with a smaller table would lower it under the first); the per-potential sizes are launch arguments only.
+void allow_max_dynamic_smem(const void *fn, size_t optin)
+{
+  CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) max_dynamic_smem(fn, optin)));
 }
 
 // ---- instantiations of the register-resident kernel: (max tensor rank, padded radial function count) ----
@@ -542,7 +551,7 @@ void upload_potential(mtp_handle *h)
     h->v2_radial = E.radial_v[gv];
     bool ok = h->v2_smem_g <= max_dynamic_smem((const void *) h->v2_radial, smem_max);
     if (ok) {
-      CUDA_CHECK(cudaFuncSetAttribute((const void *) h->v2_radial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->v2_smem_g));
+      allow_max_dynamic_smem((const void *) h->v2_radial, smem_max);
       if (!getenv("MTP_B200_NO_CARVEOUT")) {
         // the gather lives on its L1 hit rate (see the kernel): it asks for the smallest shared-memory carve-out that holds
         // its rings, unlike the other kernels of the pipeline, which all ask for the maximum
@@ -560,7 +569,7 @@ void upload_potential(mtp_handle *h)
       h->v2_smem_m = (size_t) 2 * V2_NT * (3 + E.R) * 33 * 8;
       ok = h->v2_smem_m <= max_dynamic_smem((const void *) E.moments, smem_max);
       if (ok) {
-        CUDA_CHECK(cudaFuncSetAttribute((const void *) E.moments, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->v2_smem_m));
+        allow_max_dynamic_smem((const void *) E.moments, smem_max);
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.moments, 32 * E.NP, h->v2_smem_m));
         h->v2_grid_m = std::max(1, per_sm) * h->sm_count;
       }
@@ -571,7 +580,7 @@ void upload_potential(mtp_handle *h)
         const void *fk = (const void *) E.forces[gq];
         ok = ok && h->v2_smem_f <= max_dynamic_smem(fk, smem_max);
         if (!ok) break;
-        CUDA_CHECK(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->v2_smem_f));
+        allow_max_dynamic_smem(fk, smem_max);
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk, 256, h->v2_smem_f));
         h->v2_grid_fg[gq] = std::max(1, per_sm) * h->sm_count;
       }
@@ -592,7 +601,7 @@ void upload_potential(mtp_handle *h)
       h->pl_smem_m = L.radial_bytes + W * L.warp_bytes_moments;
       ok = ok && h->pl_smem_m <= max_dynamic_smem((const void *) E.moments, smem_max);
       if (ok) {
-        CUDA_CHECK(cudaFuncSetAttribute((const void *) E.moments, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->pl_smem_m));
+        allow_max_dynamic_smem((const void *) E.moments, smem_max);
         int per_sm = 0;
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.moments, W * 32, h->pl_smem_m));
         h->pl_grid_m = std::max(1, per_sm) * h->sm_count;
@@ -604,7 +613,7 @@ void upload_potential(mtp_handle *h)
       h->pl_smem_f[gflag] = L.radial_bytes + W * L.warp_bytes_forces;
       ok = ok && h->pl_smem_f[gflag] <= max_dynamic_smem((const void *) E.forces[gflag], smem_max);
       if (!ok) break;
-      CUDA_CHECK(cudaFuncSetAttribute((const void *) E.forces[gflag], cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->pl_smem_f[gflag]));
+      allow_max_dynamic_smem((const void *) E.forces[gflag], smem_max);
       int per_sm = 0;
       CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) E.forces[gflag], W * 32, h->pl_smem_f[gflag]));
       h->pl_grid_f[gflag] = std::max(1, per_sm) * h->sm_count;
@@ -621,10 +630,10 @@ void upload_potential(mtp_handle *h)
     while (w > 1 && L.cta_bytes + (size_t) w * L.warp_bytes > gen_max) w--;
     const size_t bytes = L.cta_bytes + (size_t) w * L.warp_bytes;
     if (bytes > gen_max) {
-      if (h->v1_entry >= 0) continue;
+      if (h->v1_entry >= 0 || h->v2_entry >= 0) continue;    // the pipelines serve this potential
       throw std::runtime_error("potential too large for on-chip per-atom state (alpha_moments_count)");
     }
-    CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes));
+    allow_max_dynamic_smem(fn, smem_max);
     int per_sm = 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, w * 32, bytes));
     if (per_sm < 1) per_sm = 1;
@@ -633,6 +642,12 @@ void upload_potential(mtp_handle *h)
     h->grid_cap[gflag] = per_sm * h->sm_count;
   }
 
+  if (p.has_selection_state) {    // grade kernels (per device, like everything above)
+    allow_max_dynamic_smem((const void *) grade_dmma_reg_kernel<64>, smem_max);
+    allow_max_dynamic_smem((const void *) mtp_cand_radial_kernel<2>, smem_max);
+    allow_max_dynamic_smem((const void *) mtp_cand_radial_kernel<4>, smem_max);
+    allow_max_dynamic_smem((const void *) mtp_cand_radial_kernel<8>, smem_max);
+  }
   // generated contraction-program kernel for the two-kernel pipelines (NVRTC, cached cubins)
   h->p4[0].unload();
   h->p4[1].unload();
@@ -1027,12 +1042,6 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
         if (h->qpad <= 256 && !getenv("MTP_B200_GRADE_SMEM")) {    // A operand of 8 rows fits one warp's registers
           gb = (n + GRT_WARPS * 8 - 1) / (GRT_WARPS * 8);
           h->d_blockmax.ensure((size_t) gb);
-          static bool attr_set = false;
-          if (!attr_set) {
-            CUDA_CHECK(cudaFuncSetAttribute((const void *) grade_dmma_reg_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int) (2 * GRT_COLS * (256 + 4) * 8)));
-            attr_set = true;
-          }
           grade_dmma_reg_kernel<64><<<std::min(gb, h->sm_count), GRT_WARPS * 32, smem_g, st>>>(
               h->d_cand.p, n, h->qpad, h->d_ainv.p, a.ilist, first, a.grades ? a.grades : nullptr, h->d_blockmax.p);
         } else {
@@ -1556,8 +1565,16 @@ int mtp_compute_host(mtp_handle *h, const mtp_compute_args *a, int list_changed)
       h->h_vatom.upload(a->vatom, 6 * nall, st);
       d.vatom = h->h_vatom.p;
     }
-    if (a->want_grade && a->grades) {
-      h->h_grades.upload(a->grades, nall, st);
+    if (a->want_grade && h->pot.has_selection_state && !h->pot.configuration_mode) {
+      // neighbourhood grades stay resident on the device (mtp_fetch_grades / mtp_select_grades_host read them later);
+      // they cross PCIe only when the caller hands in an array
+      const bool fresh = h->h_grades.cap < nall || h->h_grades_n != nall;
+      if (a->grades) h->h_grades.upload(a->grades, nall, st);
+      else {
+        h->h_grades.ensure(nall);
+        if (fresh) CUDA_CHECK(cudaMemsetAsync(h->h_grades.p, 0, sizeof(double) * nall, st));
+      }
+      h->h_grades_n = nall;
       d.grades = h->h_grades.p;
     }
     if (a->want_grade && a->cfg_candidate && h->pot.has_selection_state) {
@@ -1582,7 +1599,7 @@ int mtp_compute_host(mtp_handle *h, const mtp_compute_args *a, int list_changed)
     CUDA_CHECK(cudaMemcpyAsync(a->ev_out, d.ev_out, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
     if (d.eatom) CUDA_CHECK(cudaMemcpyAsync(a->eatom, d.eatom, sizeof(double) * nall, cudaMemcpyDeviceToHost, st));
     if (d.vatom) CUDA_CHECK(cudaMemcpyAsync(a->vatom, d.vatom, sizeof(double) * 6 * nall, cudaMemcpyDeviceToHost, st));
-    if (d.grades) CUDA_CHECK(cudaMemcpyAsync(a->grades, d.grades, sizeof(double) * nall, cudaMemcpyDeviceToHost, st));
+    if (d.grades && a->grades) CUDA_CHECK(cudaMemcpyAsync(a->grades, d.grades, sizeof(double) * nall, cudaMemcpyDeviceToHost, st));
     if (d.cfg_candidate)
       CUDA_CHECK(cudaMemcpyAsync(a->cfg_candidate, d.cfg_candidate, sizeof(double) * h->pot.coeff_count,
                                  cudaMemcpyDeviceToHost, st));
@@ -1712,6 +1729,78 @@ int mtp_select_grades(mtp_handle *h, const double *grades, int n, double thresho
     CUDA_CHECK(cudaMemcpyAsync(count_out, h->nb_max.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
   });
+}
+
+int mtp_fetch_grades(mtp_handle *h, double *grades_host, int n)
+{
+  if (!h || (n > 0 && !grades_host)) return fail(MTP_ERR_ARG, "null argument");
+  if ((size_t) n > h->h_grades_n) return fail(MTP_ERR_MODE, "no neighbourhood grades of that size are resident (run a grade step through mtp_compute_host first)");
+  if (n <= 0) return MTP_OK;
+  return guarded([&] {
+    set_device(h);
+    CUDA_CHECK(cudaMemcpy(grades_host, h->h_grades.p, sizeof(double) * (size_t) n, cudaMemcpyDeviceToHost));
+  });
+}
+
+int mtp_select_grades_host(mtp_handle *h, int n, double threshold, int *ids_out, double *grades_out, int cap, int *count_out)
+{
+  if (!h || !count_out) return fail(MTP_ERR_ARG, "null argument");
+  *count_out = 0;
+  if (n < 0 || cap < 0 || (cap > 0 && (!ids_out || !grades_out))) return fail(MTP_ERR_ARG, "bad selection arguments");
+  if ((size_t) n > h->h_grades_n) return fail(MTP_ERR_MODE, "no neighbourhood grades of that size are resident (run a grade step through mtp_compute_host first)");
+  if (n == 0) return MTP_OK;
+  int count = 0;
+  int rc = guarded([&] {
+    set_device(h);
+    if (!h->hstream) CUDA_CHECK(cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+    h->sel_ids.ensure((size_t) n);
+  });
+  if (rc != MTP_OK) return rc;
+  rc = mtp_select_grades(h, h->h_grades.p, n, threshold, h->sel_ids.p, &count, h->hstream);
+  if (rc != MTP_OK) return rc;
+  *count_out = count;
+  const int m = std::min(count, cap);
+  if (m == 0) return MTP_OK;
+  return guarded([&] {
+    h->sel_val.ensure((size_t) m);
+    gather_by_index_kernel<<<(m + 255) / 256, 256, 0, h->hstream>>>(h->h_grades.p, h->sel_ids.p, m, h->sel_val.p);
+    g_launches++;
+    CUDA_CHECK(cudaMemcpyAsync(ids_out, h->sel_ids.p, sizeof(int) * (size_t) m, cudaMemcpyDeviceToHost, h->hstream));
+    CUDA_CHECK(cudaMemcpyAsync(grades_out, h->sel_val.p, sizeof(double) * (size_t) m, cudaMemcpyDeviceToHost, h->hstream));
+    CUDA_CHECK(cudaStreamSynchronize(h->hstream));
+  });
+}
+
+int mtp_cfg_grade(mtp_handle *h, const double *candidate_host, long long natoms_total, double *grade_out)
+{
+  if (!h || !candidate_host || !grade_out) return fail(MTP_ERR_ARG, "null argument");
+  if (!h->pot.has_selection_state) return fail(MTP_ERR_MODE, "no selection state loaded");
+  return guarded([&] {
+    set_device(h);
+    const int Q = h->pot.coeff_count;
+    h->d_cfg.ensure((size_t) h->qpad);
+    h->h_ev.ensure(8);
+    CUDA_CHECK(cudaMemcpy(h->d_cfg.p, candidate_host, sizeof(double) * Q, cudaMemcpyHostToDevice));
+    cfg_grade_kernel<<<1, 256>>>(h->d_ainv.p, h->qpad, Q, h->d_cfg.p, natoms_total > 0 ? 1.0 / (double) natoms_total : 0.0,
+                                 h->h_ev.p + 7);
+    g_launches++;
+    CUDA_CHECK(cudaMemcpy(grade_out, h->h_ev.p + 7, sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
+void *mtp_alloc_pinned(size_t bytes)
+{
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    fail(MTP_ERR_CUDA, "cudaMallocHost failed");
+    return nullptr;
+  }
+  return p;
+}
+
+void mtp_free_pinned(void *p)
+{
+  if (p) cudaFreeHost(p);
 }
 
 int mtp_nve_initial_integrate(int nlocal, double *x, double *v, const double *f, const int *type, const double *mass,

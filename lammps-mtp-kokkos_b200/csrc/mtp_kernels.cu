@@ -722,6 +722,13 @@ __global__ void cfg_grade_kernel(const double *ainv_pad, int ld, int q, const do
   }
 }
 
+// out[k] = v[idx[k]]  (selected grades -> a dense array for the host)
+__global__ void gather_by_index_kernel(const double *__restrict__ v, const int *__restrict__ idx, int n, double *__restrict__ out)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = v[idx[k]];
+}
+
 // ---- halo helpers ---------------------------------------------------------------------------------
 __global__ void halo_pack_x_kernel(const double *__restrict__ x, const int *__restrict__ sendlist, int n, double sx,
                                    double sy, double sz, double *__restrict__ out)

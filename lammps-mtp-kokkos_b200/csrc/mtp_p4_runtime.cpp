@@ -160,7 +160,7 @@ void P4Module::load(const std::vector<char> &cubin, int device, int sm_count)
   P4_CUDA(cudaSetDevice(device));
   P4_CUDA(cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
   P4_CUDA(cudaLibraryGetKernel(&kernel, lib, "mtp_program_p4"));
-  P4_CUDA(cudaFuncSetAttribute((const void *) kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) info.smem_bytes));
+  P4_CUDA(cudaFuncSetAttribute((const void *) kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) info.smem_bytes));    // module-private kernel
   P4_CUDA(cudaFuncSetAttribute((const void *) kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
   P4_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) kernel, info.threads, info.smem_bytes));

@@ -25,6 +25,12 @@
 #include "neigh_list.h"
 #include "neighbor.h"
 #include "utils.h"
+#ifdef LMP_KOKKOS
+#include "atom_kokkos.h"
+#include "atom_masks.h"
+#include "memory_kokkos.h"
+#include "neigh_list_kokkos.h"
+#endif
 
 #include "mtp_b200.h"
 
@@ -32,6 +38,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
 
 using namespace LAMMPS_NS;
 
@@ -45,8 +54,14 @@ PairMTPB200::PairMTPB200(LAMMPS *lmp, int variant_, bool extrapolation_) :
   restartinfo = 0;
   one_coeff = 1;
   manybody_flag = 1;
-  // pair_mtp_kokkos.cpp:37-45 minus the Kokkos bookkeeping
   respa_enable = 0;
+#ifdef LMP_KOKKOS
+  // pair_mtp_kokkos.cpp:37-45: the style reads and writes atom data on the device only
+  kokkosable = 1;
+  execution_space = Device;
+  datamask_read = EMPTY_MASK;
+  datamask_modify = EMPTY_MASK;
+#endif
   if (extrapolation) {    // pair_mtp_extrapolation.cpp:42-44
     nextra = 1;
     pvector = new double[nextra];
@@ -64,14 +79,32 @@ PairMTPB200::~PairMTPB200()
     memory->destroy(setflag);
     memory->destroy(cutsq);
   }
+#ifdef LMP_KOKKOS
+  MemoryKokkos mk;
+  mk.destroy_kokkos(k_eatom, eatom);
+  mk.destroy_kokkos(k_vatom, vatom_rows_kk);
+  k_grades.release();
+  mtp_free_pinned(ev_pinned);
+  vatom = nullptr;
+#endif
   delete[] pvector;
   pvector = nullptr;
 }
 
-void PairMTPB200::fatal(const char *file, int line, int rc)
+// The library reports, LAMMPS aborts (the reference's fatal-error convention, pair_mtp.cpp:92,288,306,315,327).
+// A failure of one force evaluation (the species bound on this rank's atoms, a CUDA error on this rank's GPU) is this
+// rank's alone -- error->one, like the reference's per-atom check (pair_mtp.cpp:91-93,116-118); error->all would wait
+// for ranks that never get here.
+void PairMTPB200::fatal_one(const char *file, int line, int rc)
 {
-  // the library reports, LAMMPS aborts: the reference's fatal-error convention (pair_mtp.cpp:92,288,306,315,327)
+  error->one(file, line, "{} (mtp_b200 error {})", mtp_last_error(), rc);
+  throw std::runtime_error("unreachable");
+}
+
+void PairMTPB200::fatal_all(const char *file, int line, int rc)
+{
   error->all(file, line, "{} (mtp_b200 error {})", mtp_last_error(), rc);
+  throw std::runtime_error("unreachable");
 }
 
 /* ----------------------------------------------------------------------
@@ -108,7 +141,7 @@ void PairMTPB200::settings(int narg, char **arg)
   handle = mtp_create_from_file(arg[0], extrapolation ? 1 : 0, -1);
   if (!handle) error->all(FLERR, "{}", mtp_last_error());
   int rc = mtp_set_chunksize(handle, chunksize);
-  if (rc) fatal(FLERR, rc);
+  if (rc) fatal_all(FLERR, rc);
 
   mtp_info info;
   mtp_get_info(handle, &info);
@@ -187,17 +220,44 @@ double PairMTPB200::init_one(int i, int j)
 void PairMTPB200::compute(int eflag, int vflag)
 {
   const bool want_grade = extrapolation && (extrapolation_flag || mlip3_style);    // pair_mtp_extrapolation.cpp:71
-  if (extrapolation && want_grade) max_grade = 0;
+#ifdef LMP_KOKKOS
+  ev_init(eflag, vflag, 0);    // per-atom arrays are DualViews of this class (pair_mtp_kokkos.cpp:212-224)
+#else
   ev_init(eflag, vflag);
+#endif
 
-  const int nlocal = atom->nlocal, nall = atom->nlocal + atom->nghost;
-  const int inum = list->inum;
-  if (want_grade && !configuration_mode && nbh_count < std::max(inum, nall)) {    // :91-94, indexed by atom id
-    memory->grow(nbh_extrapolation_grades, std::max(inum, nall), "nbh_extrapolation_grades");
-    nbh_count = std::max(inum, nall);
+  double ev[8] = {0, 0, 0, 0, 0, 0, 0, 0};    // E, virial xx yy zz xy xz yz, max grade of this rank
+  if (atom->nlocal + atom->nghost > 0 && list->inum > 0) {
+#ifdef LMP_KOKKOS
+    compute_device_views(eflag, vflag, want_grade, ev);
+#else
+    compute_host_buffers(eflag, vflag, want_grade, ev);
+#endif
   }
+  if (eflag_global) eng_vdwl += ev[0];
+  if (vflag)
+    for (int k = 0; k < 6; k++) virial[k] += ev[1 + k];    // pair_mtp.cpp:257-266: -sym(F (x) r), never fdotr
 
-  // flatten the paged host list on re-neighboring steps only
+  if (want_grade) {
+    max_grade = ev[7];
+    host_grades_stale = true;
+    grade_rows = atom->nlocal + atom->nghost;
+    reduce_max_grade();
+    if (mlip3_style) act_on_thresholds();
+  }
+}
+
+/* ----------------------------------------------------------------------
+   plain LAMMPS: atom data and the paged neighbor list live on the host
+------------------------------------------------------------------------- */
+
+void PairMTPB200::compute_host_buffers(int /*eflag*/, int vflag, bool want_grade, double *ev)
+{
+  const int nall = atom->nlocal + atom->nghost;
+  const int inum = list->inum;
+
+  // The list only changes on re-neighboring steps: it is flattened (one block copy per run of consecutive pages) and
+  // uploaded then, and stays resident on the device in between.
   const bool list_changed = neighbor->ago == 0 || flat_offsets.empty();
   if (list_changed) {
     flat_offsets.assign((size_t) nall + 1, 0);
@@ -205,157 +265,259 @@ void PairMTPB200::compute(int eflag, int vflag)
     for (int ii = 0; ii < inum; ii++) total += list->numneigh[list->ilist[ii]];
     flat_neigh.resize((size_t) std::max<long long>(total, 1));
     long long at = 0;
-    for (int ii = 0; ii < inum; ii++) {
-      const int i = list->ilist[ii];
-      flat_offsets[i] = at;
-      std::memcpy(flat_neigh.data() + at, list->firstneigh[i], sizeof(int) * (size_t) list->numneigh[i]);
-      at += list->numneigh[i];
+    int ii = 0;
+    while (ii < inum) {
+      // rows that follow each other in a page of LAMMPS's neighbor pool are copied as one block
+      const int *src = list->firstneigh[list->ilist[ii]];
+      long long run = 0;
+      int jj = ii;
+      while (jj < inum && list->firstneigh[list->ilist[jj]] == src + run) {
+        flat_offsets[list->ilist[jj]] = at + run;
+        run += list->numneigh[list->ilist[jj]];
+        jj++;
+      }
+      if (run) std::memcpy(flat_neigh.data() + at, src, sizeof(int) * (size_t) run);
+      at += run;
+      ii = jj;
     }
   }
 
-  double ev[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   mtp_compute_args a;
   std::memset(&a, 0, sizeof(a));
   a.variant = variant;
   a.inum = inum;
   a.nall = nall;
-  a.x = nall ? &atom->x[0][0] : nullptr;
+  a.x = &atom->x[0][0];
   a.type = atom->type;
   a.ilist = list->ilist;
   a.numneigh = list->numneigh;
   a.neighbors = flat_neigh.data();
   a.neigh_offsets = flat_offsets.data();
-  a.stride_i = 0;
   a.stride_jj = 1;
   a.neighmask = NEIGHMASK;
   a.eflag = (eflag_global ? 1 : 0) | (eflag_atom ? 2 : 0);
   a.vflag = vflag ? ((vflag_atom ? 4 : 0) | 1) : 0;    // the CPU style tallies the pairwise virial whenever vflag != 0
   a.want_grade = want_grade ? 1 : 0;
   a.natoms_total = (long long) atom->natoms;
-  a.f = nall ? &atom->f[0][0] : nullptr;
+  a.f = &atom->f[0][0];
+  // LAMMPS clears f before Pair::compute; a lone pair style is the first to add to it, so nothing needs uploading
+  a.f_overwrite = (force->pair == this) ? 1 : 0;
   a.eatom = eflag_atom ? eatom : nullptr;
   a.vatom = vflag_atom ? &vatom[0][0] : nullptr;
   a.ev_out = ev;
-  a.grades = (want_grade && !configuration_mode) ? nbh_extrapolation_grades : nullptr;
+  a.grades = nullptr;    // neighbourhood grades stay on the device until somebody asks (host_grades_current)
   a.cfg_candidate = (want_grade && configuration_mode) ? cfg_candidate.data() : nullptr;
-  if (nall > 0 && inum > 0) {
-    const int rc = mtp_compute_host(handle, &a, list_changed ? 1 : 0);
-    if (rc) fatal(FLERR, rc);
-  }
+  const int rc = mtp_compute_host(handle, &a, list_changed ? 1 : 0);
+  if (rc) fatal_one(FLERR, rc);
+}
 
-  if (eflag_global) eng_vdwl += ev[0];
-  if (vflag)
-    for (int k = 0; k < 6; k++) virial[k] += ev[1 + k];    // pair_mtp.cpp:257-266: -sym(F (x) r), never fdotr
+#ifdef LMP_KOKKOS
+/* ----------------------------------------------------------------------
+   LAMMPS-KOKKOS: device views of atom data and of the neighbor list go straight to the CUDA layer
+   (what pair_mtp_kokkos.cpp:231-240 hands its functors)
+------------------------------------------------------------------------- */
 
-  if (want_grade) {
-    max_grade = ev[7];
-    compile_grades();
-    if (mlip3_style) evaluate_grades();
+void PairMTPB200::compute_device_views(int /*eflag*/, int vflag, bool want_grade, double *ev)
+{
+  AtomKokkos *atomKK = (AtomKokkos *) atom;
+  MemoryKokkos memoryKK;
+  const int nall = atom->nlocal + atom->nghost;
+
+  // reallocate per-atom arrays if necessary (pair_mtp_kokkos.cpp:215-224)
+  if (eflag_atom) {
+    memoryKK.destroy_kokkos(k_eatom, eatom);
+    memoryKK.create_kokkos(k_eatom, eatom, maxeatom, "pair:eatom");
   }
-  (void) nlocal;
+  if (vflag_atom) {
+    memoryKK.destroy_kokkos(k_vatom, vatom_rows_kk);
+    memoryKK.create_kokkos(k_vatom, vatom_rows_kk, maxvatom, 6, "pair:vatom");
+    vatom = vatom_rows_kk;
+  }
+  if (want_grade && !configuration_mode && k_grades.d_view.extent(0) < nall) {
+    memory->grow(nbh_extrapolation_grades, nall, "nbh_extrapolation_grades");
+    nbh_count = nall;
+    k_grades.allocate(nbh_extrapolation_grades, nall);
+  }
+  if (!ev_pinned) ev_pinned = (double *) mtp_alloc_pinned(8 * sizeof(double));
+  if (!ev_pinned) fatal_one(FLERR, MTP_ERR_CUDA);
+
+  atomKK->sync((ExecutionSpace) execution_space, X_MASK | F_MASK | TYPE_MASK);
+  auto x = atomKK->k_x.view<LMPDeviceType>();
+  auto f = atomKK->k_f.view<LMPDeviceType>();
+  auto type = atomKK->k_type.view<LMPDeviceType>();
+  auto *k_list = static_cast<NeighListKokkos<LMPDeviceType> *>(list);
+
+  mtp_compute_args a;
+  std::memset(&a, 0, sizeof(a));
+  a.variant = variant;
+  a.inum = list->inum;
+  a.nall = nall;
+  a.x = x.data();
+  a.type = type.data();
+  a.ilist = k_list->d_ilist.data();
+  a.numneigh = k_list->d_numneigh.data();
+  a.neighbors = k_list->d_neighbors.data();         // d_neighbors(i, jj), either layout
+  a.stride_i = k_list->d_neighbors.stride(0);
+  a.stride_jj = k_list->d_neighbors.stride(1);
+  a.max_numneigh = (int) k_list->d_neighbors.extent(1);
+  a.neighmask = NEIGHMASK;
+  a.eflag = (eflag_global ? 1 : 0) | (eflag_atom ? 2 : 0);
+  a.vflag = vflag ? ((vflag_atom ? 4 : 0) | 1) : 0;
+  a.want_grade = want_grade ? 1 : 0;
+  a.natoms_total = (long long) atom->natoms;
+  a.f = f.data();
+  a.eatom = eflag_atom ? k_eatom.view<LMPDeviceType>().data() : nullptr;
+  a.vatom = vflag_atom ? k_vatom.view<LMPDeviceType>().data() : nullptr;
+  a.ev_out = ev_pinned;
+  a.grades = (want_grade && !configuration_mode) ? k_grades.view<LMPDeviceType>().data() : nullptr;
+  DAT::tdual_efloat_1d k_cand;
+  if (want_grade && configuration_mode) {
+    k_cand.allocate(cfg_candidate.data(), coeff_count);
+    a.cfg_candidate = k_cand.view<LMPDeviceType>().data();
+  }
+  int rc = mtp_compute(handle, &a);
+  if (!rc) rc = mtp_synchronize(handle);
+  if (rc) {
+    k_cand.release();
+    fatal_one(FLERR, rc);
+  }
+  for (int k = 0; k < 8; k++) ev[k] = ev_pinned[k];
+  atomKK->modified((ExecutionSpace) execution_space, F_MASK);
+
+  // per-atom results back to the host side of their DualViews (pair_mtp_kokkos.cpp:379-390)
+  if (eflag_atom) {
+    k_eatom.modify<LMPDeviceType>();
+    k_eatom.sync<LMPHostType>();
+  }
+  if (vflag_atom) {
+    k_vatom.modify<LMPDeviceType>();
+    k_vatom.sync<LMPHostType>();
+  }
+  if (a.grades) k_grades.modify<LMPDeviceType>();    // synced on demand (host_grades_current)
+  if (a.cfg_candidate) {
+    k_cand.modify<LMPDeviceType>();
+    k_cand.sync<LMPHostType>();
+    k_cand.release();
+  }
+}
+#endif
+
+/* ----------------------------------------------------------------------
+   The neighbourhood grades of a grade step stay on the device; the host array that extract_peratom() and the
+   .cfg writer expose (indexed by atom id, pair_mtp_extrapolation.cpp:335,641-652) is refreshed the first time it
+   is asked for after the step.  Only the 8-double record crosses PCIe on a step nobody looks at the array.
+------------------------------------------------------------------------- */
+
+void PairMTPB200::host_grades_current()
+{
+  if (!host_grades_stale || configuration_mode) return;
+#ifdef LMP_KOKKOS
+  k_grades.sync<LMPHostType>();
+#else
+  if (nbh_count < grade_rows) {    // pair_mtp_extrapolation.cpp:91-94
+    memory->grow(nbh_extrapolation_grades, grade_rows, "nbh_extrapolation_grades");
+    nbh_count = grade_rows;
+  }
+  const int rc = mtp_fetch_grades(handle, nbh_extrapolation_grades, grade_rows);
+  if (rc) fatal_one(FLERR, rc);
+#endif
+  host_grades_stale = false;
 }
 
 /* ----------------------------------------------------------------------
-   collective reduction (pair_mtp_extrapolation.cpp:363-382).  In configuration mode the candidate vector
-   is summed over ranks and the grade is re-evaluated from the sum.
+   Grade of the whole system from the per-rank results (what pair_mtp_extrapolation.cpp:363-382 computes).
+   Neighbourhood mode: the largest per-atom grade of any rank.  Configuration mode: the candidate vectors of the
+   ranks add up to the configuration's, whose grade max|Ainv . b| / natoms the device evaluates against the
+   resident inverse active set (one rank: mtp_compute already did, with natoms_total).
+   pvector[0] is written on rank 0 only, because `compute pair` SUMs it over ranks.
 ------------------------------------------------------------------------- */
 
-void PairMTPB200::compile_grades()
+void PairMTPB200::reduce_max_grade()
 {
-  if (configuration_mode) {
-    if (comm->nprocs > 1) {
+  if (comm->nprocs > 1) {
+    if (configuration_mode) {
       MPI_Allreduce(MPI_IN_PLACE, cfg_candidate.data(), coeff_count, MPI_DOUBLE, MPI_SUM, world);
-      // max_i |Ainv[i,:] . b| / natoms on the summed vector
-      std::vector<double> ainv((size_t) coeff_count * coeff_count);
-      mtp_get_tables(handle, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ainv.data());
-      double g = 0.0;
-      for (int i = 0; i < coeff_count; i++) {
-        double s = 0.0;
-        for (int j = 0; j < coeff_count; j++) s += ainv[(size_t) i * coeff_count + j] * cfg_candidate[j];
-        g = std::max(g, std::fabs(s));
-      }
-      max_grade = atom->natoms > 0 ? g / (double) atom->natoms : 0.0;
+      const int rc = mtp_cfg_grade(handle, cfg_candidate.data(), (long long) atom->natoms, &max_grade);
+      if (rc) fatal_one(FLERR, rc);
+    } else {
+      double mine = max_grade;
+      MPI_Allreduce(&mine, &max_grade, 1, MPI_DOUBLE, MPI_MAX, world);
     }
-    // single rank: the library already normalised by natoms_total
-  } else {
-    MPI_Allreduce(MPI_IN_PLACE, &max_grade, 1, MPI_DOUBLE, MPI_MAX, world);
   }
-  if (comm->me == 0) pvector[0] = max_grade;    // Expose the max grade (rank 0 only: compute pair SUMs pvector)
-}
-
-void PairMTPB200::evaluate_grades()
-{
-  if (max_grade >= select_threshold) write_config();
-  if (max_grade >= break_threshold && comm->me == 0) {
-    std::fflush(preselected_file);    // Ensure the writing buffers are flushed before breaking.
-    std::fclose(preselected_file);
-    preselected_file = nullptr;
-    error->one(FLERR, "Exceeded Break Threshold: {:.5f}. Terminating simulation.\n", max_grade);
-  }
+  if (comm->me == 0) pvector[0] = max_grade;
 }
 
 /* ----------------------------------------------------------------------
-   MLIP-3 preselected-configuration block (pair_mtp_extrapolation.cpp:401-479), same text byte for byte
+   MLIP-3 style thresholds (pair_mtp_extrapolation.cpp:387-397): a configuration whose grade reaches the selection
+   threshold is appended to the preselected file; at the break threshold the run stops with the file closed.
 ------------------------------------------------------------------------- */
 
-void PairMTPB200::write_config()
+void PairMTPB200::act_on_thresholds()
 {
-  write_buffer.clear();
+  if (max_grade >= select_threshold) append_selected_configuration();
+  if (max_grade < break_threshold || comm->me != 0) return;
+  if (preselected_file) {
+    std::fclose(preselected_file);    // fclose flushes: everything selected so far is on disk before the abort
+    preselected_file = nullptr;
+  }
+  error->one(FLERR, "Exceeded Break Threshold: {:.5f}. Terminating simulation.\n", max_grade);
+}
+
+/* ----------------------------------------------------------------------
+   One BEGIN_CFG ... END_CFG block of the MLIP-3 preselected-configuration format, byte for byte what
+   pair_mtp_extrapolation.cpp:401-479 writes (tests compare with the reference writer's own output): header from
+   the domain, one line per listed atom in rank order -- id = running 1-based index over ranks, 0-based type, raw
+   coordinates, and in neighbourhood mode the atom's grade; like the reference the rows are indexed by ii itself,
+   SURVEY.md App. B9 -- then the grade of the configuration.  Rank 0 writes; the other ranks' lines reach it
+   through one gather of sizes and one gather of text.
+------------------------------------------------------------------------- */
+
+void PairMTPB200::append_selected_configuration()
+{
   const int inum = list->inum;
-  int *type = atom->type;
-  double **x = atom->x;
-  int index_offset = 0;
-  MPI_Scan(&inum, &index_offset, 1, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
-  index_offset -= inum;
+  if (!configuration_mode) host_grades_current();
 
-  char line[256];
+  // running atom index over ranks: inclusive prefix sum minus my own count
+  int before_me = 0;
+  MPI_Scan(&inum, &before_me, 1, MPI_INT, MPI_SUM, world);
+  before_me -= inum;
+
+  std::string mine;
+  mine.reserve((size_t) inum * 64);
+  char row[256];
   for (int ii = 0; ii < inum; ii++) {
-    const int i = ii;    // (sic) the reference indexes by ii, SURVEY.md App. B9
-    const int itype = type[i] - 1;
-    const int global_i = i + index_offset + 1;
-    int n;
-    if (!configuration_mode)
-      n = snprintf(line, sizeof(line), "%d\t%d\t%.6f\t%.6f\t%.6f\t%.5f\n", global_i, itype, x[i][0], x[i][1], x[i][2],
-                   nbh_extrapolation_grades[i]);
-    else
-      n = snprintf(line, sizeof(line), "%d\t%d\t%.6f\t%.6f\t%.6f\n", global_i, itype, x[i][0], x[i][1], x[i][2]);
-    write_buffer.append(line, (size_t) n);
+    const double *xi = atom->x[ii];
+    int n = snprintf(row, sizeof(row), "%d\t%d\t%.6f\t%.6f\t%.6f", before_me + ii + 1, atom->type[ii] - 1, xi[0], xi[1], xi[2]);
+    if (!configuration_mode) n += snprintf(row + n, sizeof(row) - n, "\t%.5f", nbh_extrapolation_grades[ii]);
+    row[n++] = '\n';
+    mine.append(row, (size_t) n);
   }
 
-  bigint char_buffer_size = (bigint) write_buffer.size();
-  bigint max_char_buffer_size = char_buffer_size;
-  MPI_Reduce(&char_buffer_size, &max_char_buffer_size, 1, MPI_LMP_BIGINT, MPI_MAX, 0, world);
-
+  // rank-ordered concatenation on rank 0
+  const int nprocs = comm->nprocs;
+  int my_len = (int) mine.size();
+  std::vector<int> lens((size_t) nprocs, 0), at((size_t) nprocs, 0);
+  MPI_Gather(&my_len, 1, MPI_INT, lens.data(), 1, MPI_INT, 0, world);
+  std::string all;
   if (comm->me == 0) {
-    std::fprintf(preselected_file, "BEGIN_CFG\n");
-    std::fprintf(preselected_file, "Size\n");
-    std::fprintf(preselected_file, "%ld\n", (long) atom->natoms);
-    std::fprintf(preselected_file, "Supercell\n");
-    std::fprintf(preselected_file, "%.6f %.6f %.6f\n", domain->xprd, 0.0, 0.0);
-    std::fprintf(preselected_file, "%.6f %.6f %.6f\n", domain->xy, domain->yprd, 0.0);
-    std::fprintf(preselected_file, "%.6f %.6f %.6f\n", domain->xz, domain->yz, domain->zprd);
-    if (!configuration_mode)
-      std::fprintf(preselected_file,
-                   "AtomData:  id type       cartes_x      cartes_y      cartes_z       nbh_grades\n");
-    else
-      std::fprintf(preselected_file, "AtomData:  id type       cartes_x      cartes_y      cartes_z\n");
-    std::fwrite(write_buffer.data(), 1, (size_t) char_buffer_size, preselected_file);
-  }
-
-  if (comm->me != 0) {
-    MPI_Send(write_buffer.data(), (int) char_buffer_size, MPI_CHAR, 0, 0, world);
-  } else {
-    std::vector<char> recv((size_t) std::max<bigint>(max_char_buffer_size, 1));
-    for (int p = 1; p < comm->nprocs; p++) {
-      MPI_Status status;
-      int n_chars = 0;
-      MPI_Recv(recv.data(), (int) max_char_buffer_size, MPI_CHAR, p, 0, world, &status);
-      MPI_Get_count(&status, MPI_CHAR, &n_chars);
-      std::fwrite(recv.data(), 1, (size_t) n_chars, preselected_file);
+    long long total = 0;
+    for (int p = 0; p < nprocs; p++) {
+      at[p] = (int) total;
+      total += lens[p];
     }
-    std::fprintf(preselected_file, "Feature   MV_grade\t%.6f\n", max_grade);
-    std::fprintf(preselected_file, "END_CFG\n\n");
+    all.resize((size_t) total);
   }
+  MPI_Gatherv(mine.data(), my_len, MPI_CHAR, all.empty() ? nullptr : &all[0], lens.data(), at.data(), MPI_CHAR, 0, world);
+  if (comm->me != 0) return;
+
+  FILE *out = preselected_file;
+  std::fprintf(out, "BEGIN_CFG\nSize\n%ld\nSupercell\n", (long) atom->natoms);
+  std::fprintf(out, "%.6f %.6f %.6f\n", domain->xprd, 0.0, 0.0);
+  std::fprintf(out, "%.6f %.6f %.6f\n", domain->xy, domain->yprd, 0.0);
+  std::fprintf(out, "%.6f %.6f %.6f\n", domain->xz, domain->yz, domain->zprd);
+  std::fprintf(out, "AtomData:  id type       cartes_x      cartes_y      cartes_z%s\n", configuration_mode ? "" : "       nbh_grades");
+  std::fwrite(all.data(), 1, all.size(), out);
+  std::fprintf(out, "Feature   MV_grade\t%.6f\nEND_CFG\n\n", max_grade);
 }
 
 /* ----------------------------------------------------------------------
@@ -375,6 +537,7 @@ void *PairMTPB200::extract_peratom(const char *str, int &ncol)
     if (configuration_mode)
       error->one(FLERR, "Please use the MLIP-3 style extrapolation for configuration mode MTPs!");
     ncol = 0;
+    host_grades_current();
     return (void *) nbh_extrapolation_grades;
   }
   return nullptr;

@@ -26,6 +26,9 @@ PairStyle(mtp/extrapolation/small/kk/device,PairMTPB200ExtrapolationSmall);
 #define LMP_PAIR_MTP_B200_H
 
 #include "pair.h"
+#ifdef LMP_KOKKOS
+#include "kokkos_type.h"
+#endif
 
 #include <string>
 #include <vector>
@@ -47,10 +50,17 @@ class PairMTPB200 : public Pair {
   void *extract_peratom(const char *, int &) override;
 
  protected:
-  void compile_grades();     // pair_mtp_extrapolation.cpp:363-382
-  void evaluate_grades();    // :387-396
-  void write_config();       // :401-479
-  void fatal(const char *file, int line, int rc);
+  // grade bookkeeping after a grade step (semantics of pair_mtp_extrapolation.cpp:363-397)
+  void reduce_max_grade();            // across ranks: MAX (neighbourhood) or grade of the SUMMED candidate (configuration)
+  void act_on_thresholds();           // select_threshold -> append the configuration, break_threshold -> abort
+  void append_selected_configuration();   // MLIP-3 .cfg block (:401-479), rank-ordered text gathered on rank 0
+  void host_grades_current();         // fetches the device-resident neighbourhood grades once per grade step
+  void compute_host_buffers(int eflag, int vflag, bool want_grade, double *ev);
+#ifdef LMP_KOKKOS
+  void compute_device_views(int eflag, int vflag, bool want_grade, double *ev);
+#endif
+  [[noreturn]] void fatal_one(const char *file, int line, int rc);    // this rank only (a device or species error)
+  [[noreturn]] void fatal_all(const char *file, int line, int rc);    // every rank fails alike (settings, file parsing)
 
   mtp_handle *handle = nullptr;
   int variant;               // MTP_VARIANT_LARGE / MTP_VARIANT_SMALL
@@ -66,15 +76,22 @@ class PairMTPB200 : public Pair {
   bool mlip3_style = false;
   double select_threshold = 0.0, break_threshold = 0.0, max_grade = 0.0;
   int nbh_count = 0;
-  double *nbh_extrapolation_grades = nullptr;
+  double *nbh_extrapolation_grades = nullptr;    // host copy, by atom id; filled lazily (host_grades_current)
+  bool host_grades_stale = true;
+  int grade_rows = 0;                            // rows the last grade step covered
   std::vector<double> cfg_candidate;
   FILE *preselected_file = nullptr;
-  std::string write_buffer;
 
   // host-list staging for a non-KOKKOS LAMMPS (list->firstneigh is paged): flattened on re-neighboring
   std::vector<int> flat_neigh;
   std::vector<long long> flat_offsets;
-  std::vector<double> fbuf;
+#ifdef LMP_KOKKOS
+  // LAMMPS-KOKKOS flavour: per-atom outputs are DualViews like the reference's (pair_mtp_kokkos.h:128-133)
+  DAT::tdual_efloat_1d k_eatom, k_grades;
+  DAT::tdual_virial_array k_vatom;
+  double **vatom_rows_kk = nullptr;
+  double *ev_pinned = nullptr;                   // [8] written by the device, read after mtp_synchronize
+#endif
 };
 
 class PairMTPB200Large : public PairMTPB200 {

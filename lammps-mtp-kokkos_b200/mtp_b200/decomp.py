@@ -348,6 +348,16 @@ class DirectHalo:
                 dist.all_reduce(ev[7:8], op=dist.ReduceOp.MAX)
 
 
+def allreduce_cfg_grade(candidate: torch.Tensor, inverse_active_set: torch.Tensor, natoms_total: int) -> torch.Tensor:
+    """Configuration-mode grade over ranks (pair_mtp_extrapolation.cpp:366-376, ReduceCoeffDers + compile_grades of the
+    KOKKOS styles): the per-rank candidate vectors [Q] are SUMMED (one all-reduce of Q doubles, in place), and the grade
+    max_i |Ainv[i, :] . b| / natoms is evaluated from the sum on the device.  A MAX over per-rank grades -- what
+    ``allreduce_ev`` does with ev[7] -- is only right in neighbourhood mode."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(candidate, op=dist.ReduceOp.SUM)
+    return (inverse_active_set @ candidate).abs().max() / float(natoms_total)
+
+
 def split_interior(x_own: np.ndarray, sublo, subhi, rghost: float):
     """Owned atoms whose whole neighbor list (radius rghost = cutoff + skin) lies inside the brick cannot have a ghost
     neighbor: their forces need no halo.  Returns (interior ids, boundary ids), both ascending int32."""

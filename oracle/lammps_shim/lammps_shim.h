@@ -63,6 +63,17 @@ static inline int MPI_Scan(const void *s, void *r, int n, MPI_Datatype t, MPI_Op
 static inline int MPI_Send(const void *, int, MPI_Datatype, int, int, MPI_Comm) { return 0; }
 static inline int MPI_Recv(void *, int, MPI_Datatype, int, int, MPI_Comm, MPI_Status *) { return 0; }
 static inline int MPI_Get_count(const MPI_Status *, MPI_Datatype, int *c) { *c = 0; return 0; }
+static inline int MPI_Gather(const void *s, int n, MPI_Datatype t, void *r, int, MPI_Datatype, int, MPI_Comm)
+{
+  memcpy(r, s, n * shim_mpi_size(t));
+  return 0;
+}
+static inline int MPI_Gatherv(const void *s, int n, MPI_Datatype t, void *r, const int *, const int *displs, MPI_Datatype, int,
+                              MPI_Comm)
+{
+  memcpy((char *) r + (displs ? displs[0] : 0) * shim_mpi_size(t), s, n * shim_mpi_size(t));
+  return 0;
+}
 
 namespace LAMMPS_NS {
 
@@ -208,6 +219,7 @@ class Force {
  public:
   int newton_pair = 1;
   int newton = 1;
+  class Pair *pair = nullptr;    // the top-level pair style (this style itself unless pair_style hybrid wraps it)
 };
 
 class Domain {
@@ -325,6 +337,8 @@ class Pair : protected Pointers {
   int vflag_either = 0, vflag_global = 0, vflag_atom = 0, cvflag_atom = 0, vflag_fdotr = 0;
   int maxeatom = 0, maxvatom = 0;
   int copymode = 0, kokkosable = 0;
+  int execution_space = 0;
+  unsigned int datamask_read = 0, datamask_modify = 0;
   int allocated = 0;
   NeighList *list = nullptr;
   char *suffix = nullptr;

@@ -28,7 +28,7 @@ def main():
     grid = decomp.brick_grid(world)
     dev = torch.device("cpu")
     cells = (7, 7, 7) if kind == "overlap" else (5, 5, 5)
-    pot = almtp.random_potential(10, 2)
+    pot = almtp.random_potential(10, 2, with_active_set=(kind == "cfg"), configuration_mode=(kind == "cfg"))
     sysm, halo = decomp.make_rank_system(2, cells, grid, rank, dev, direct=direct)
     nlocal = sysm.nlocal
     # move the owned atoms after setup (same displacement field in every brick keeps the global reference simple)
@@ -39,6 +39,15 @@ def main():
     halo.forward(x)
     assert not torch.equal(stale_ghosts, x[nlocal:])
     orc = OracleMTP(pot)
+    cfg_grade = None
+    if kind == "cfg":
+        # configuration mode: per-rank candidate vectors summed over ranks, grade from the sum
+        natoms = nlocal * world
+        rr = orc.compute(x.numpy(), sysm.type, sysm.ilist, sysm.numneigh, sysm.neigh, sysm.offsets, eflag=1, vflag=0,
+                         grade=True, natoms_total=natoms)
+        cand = torch.from_numpy(rr.candidate.copy())
+        ainv = torch.from_numpy(np.ascontiguousarray(pot.inverse_active_set))
+        cfg_grade = float(decomp.allreduce_cfg_grade(cand, ainv, natoms))
     if kind == "overlap":
         # the split-phase exchange with the interior / boundary partition (the oracle stands in for the kernels)
         x[nlocal:] = stale_ghosts
@@ -80,11 +89,12 @@ def main():
         gx = np.concatenate([g[0] for g in gathered])
         gt = np.concatenate([g[1] for g in gathered])
         gs = harness.make_system(np.mod(gx, gbox), gt, gbox, 5.0, 2.0)
-        ref = orc.compute(gs.x, gs.type, gs.ilist, gs.numneigh, gs.neigh, gs.offsets, eflag=3, vflag=5)
+        ref = orc.compute(gs.x, gs.type, gs.ilist, gs.numneigh, gs.neigh, gs.offsets, eflag=3, vflag=5, grade=(kind == "cfg"))
         fref = gs.reverse_comm(ref.f)
         np.savez(out, f=np.concatenate([g[2] for g in gathered]), fref=fref, ev=ev.numpy(), evref=ref.ev,
                  eatom=np.concatenate([g[3] for g in gathered]), eatomref=ref.eatom[: gs.nlocal],
-                 ghosts=np.array([sysm.nall - nlocal]), halo_bytes=np.array([halo.bytes_per_step]))
+                 ghosts=np.array([sysm.nall - nlocal]), halo_bytes=np.array([halo.bytes_per_step]),
+                 cfg=np.array([cfg_grade if cfg_grade is not None else 0.0, ref.ev[7]]))
     dist.barrier()
     dist.destroy_process_group()
 

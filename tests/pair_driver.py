@@ -8,6 +8,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "lammps-mtp-kokkos_b200", "lammps", "libpair_mtp_b200_shim.so")
+SO_KK = os.path.join(ROOT, "lammps-mtp-kokkos_b200", "lammps", "libpair_mtp_b200_kk_shim.so")    # LMP_KOKKOS flavour
 
 _dp, _ip, _lp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_long)
 
@@ -16,6 +17,7 @@ def build():
     sys.path.insert(0, ROOT)
     import __graft_entry__ as g
     g.build_cuda()
+    g.build_lammps_plugin(kokkos=True)
     return g.build_lammps_plugin()
 
 
@@ -24,10 +26,13 @@ class LammpsError(RuntimeError):
 
 
 class PairB200:
-    def __init__(self, style, *args, species=1, newton=1):
-        if not os.path.exists(SO):
+    def __init__(self, style, *args, species=1, newton=1, kokkos=False, lone=False):
+        """kokkos: the LMP_KOKKOS flavour of the style (device views through tests/shim/kokkos_stub);
+        lone: the style is force->pair itself (no pair_style hybrid above it)."""
+        if not os.path.exists(SO) or not os.path.exists(SO_KK):
             build()
-        self.lib = C.CDLL(SO)
+        self.lib = C.CDLL(SO_KK if kokkos else SO)
+        assert bool(self.lib.b200drv_is_kokkos()) == kokkos
         self.lib.b200drv_create.restype = C.c_void_p
         self.lib.b200drv_log.restype = C.c_char_p
         err = C.create_string_buffer(2048)
@@ -35,6 +40,7 @@ class PairB200:
         self.h = self.lib.b200drv_create(style.encode(), C.c_int(len(args)), argv, C.c_int(species), err, C.c_int(2048))
         if not self.h:
             raise LammpsError(err.value.decode())
+        self.lib.b200drv_set_lone_pair(C.c_void_p(self.h), C.c_int(1 if lone else 0))
 
     @property
     def log(self):

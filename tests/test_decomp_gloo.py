@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("kind", ["staged", "direct", "overlap"])
+@pytest.mark.parametrize("kind", ["staged", "direct", "overlap", "cfg"])
 @pytest.mark.parametrize("world", [2, 4])
 def test_decomposed_equals_global(tmp_path, built, world, kind):
     out = str(tmp_path / "res.npz")
@@ -36,6 +36,8 @@ def test_decomposed_equals_global(tmp_path, built, world, kind):
     assert np.abs(z["ev"][1:7] - z["evref"][1:7]).max() <= 1e-11 * np.abs(z["evref"][1:7]).max()
     assert np.abs(z["eatom"] - z["eatomref"]).max() <= 1e-12 * np.abs(z["eatomref"]).max()
     assert z["ghosts"][0] > 0 and z["halo_bytes"][0] > 0
+    if kind == "cfg":      # grade of the summed candidate == grade of the undecomposed configuration
+        assert z["cfg"][1] > 0 and abs(z["cfg"][0] - z["cfg"][1]) <= 1e-11 * z["cfg"][1]
 
 
 def test_single_rank_direct_halo(built):

@@ -1,0 +1,245 @@
+"""GPU tests added in round 2: paths the round-1 suite never reached (VERDICT.md "What's weak" #1)."""
+import os
+
+import numpy as np
+import pytest
+
+import util
+from util import TOL_AUX, TOL_E_REL, TOL_F_MAXABSREL, maxabsrel
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp(gpu, ref, ilist=None, grades=False):
+    assert abs(gpu.energy - ref.energy) <= TOL_E_REL * abs(ref.energy)
+    assert maxabsrel(gpu.f, ref.f) <= TOL_F_MAXABSREL
+    assert maxabsrel(gpu.virial, ref.virial) <= TOL_AUX
+    if ilist is not None:
+        assert maxabsrel(gpu.eatom[ilist], ref.eatom[ilist]) <= TOL_AUX
+    if grades:
+        assert maxabsrel(gpu.grades[ilist], ref.grades[ilist]) <= TOL_AUX
+
+
+@pytest.mark.parametrize("env,family", [({"MTP_B200_FORCE_GENERIC": "1"}, 0), ({"MTP_B200_NO_V2": "1"}, 1)])
+@pytest.mark.parametrize("level,species,grade", [(8, 2, True), (12, 1, False)])
+def test_other_kernel_families_match_the_oracle(tmp_path, built, monkeypatch, env, family, level, species, grade):
+    """The generic fused site kernel (family 0) and the DMMA-moment pipeline (family 1) serve potentials whose basic
+    moments are not a standard set; forced here on standard potentials so that the oracle comparison covers them."""
+    from mtp_b200.api import MTPB200
+    from oracle_py import OracleMTP
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    path, pot = util.write_potential(tmp_path, level, species, active_set=grade)
+    sysm = util.small_system("bcc", 3.165, (6, 6, 6), species, seed=3)
+    ref = OracleMTP(pot).compute(sysm.x, sysm.type, sysm.ilist, sysm.numneigh, sysm.neigh, sysm.offsets, grade=grade)
+    mtp = MTPB200(path, selection_state=grade)
+    gpu = mtp.compute_system(sysm, grade=grade)
+    assert mtp.last_kernel_path()["family"] == family
+    _cmp(gpu, ref, sysm.ilist, grade)
+    assert maxabsrel(gpu.vatom, ref.vatom) <= TOL_AUX
+    mtp.close()
+
+
+def _permuted(tmp_path, level, species, truncate=False):
+    """The same potential with its basic moments renumbered at random and the products of every dependency wave
+    shuffled, as a file from another generator may order them; truncate: drop the last basic moment nobody multiplies
+    (the set is then no standard MLIP set any more)."""
+    from mtp_b200 import almtp, mtp_basis
+    path, pot = util.write_potential(tmp_path, level, species)
+    rng = np.random.default_rng(11)
+    K = pot.K
+    perm = rng.permutation(K)
+    basic = np.asarray(pot.alpha_index_basic).reshape(K, 4)
+    new_basic = np.zeros_like(basic)
+    new_basic[perm] = basic
+    ren = np.arange(pot.alpha_moments_count)
+    ren[:K] = perm
+    times = np.asarray(pot.alpha_index_times).reshape(-1, 4).copy()
+    times[:, 0], times[:, 1], times[:, 3] = ren[times[:, 0]], ren[times[:, 1]], ren[times[:, 3]]
+    out, at = [], 0
+    for n in mtp_basis.prepare_waves(pot.alpha_index_times, K):
+        out.append(times[at:at + n][rng.permutation(n)])
+        at += n
+    pot.alpha_index_basic = new_basic.astype(np.int32)
+    pot.alpha_index_times = np.concatenate(out).astype(np.int32)
+    pot.alpha_moment_mapping = np.array([int(ren[m]) for m in pot.alpha_moment_mapping], dtype=np.int32)
+    path2 = os.path.join(str(tmp_path), "permuted.almtp")
+    almtp.write_almtp(path2, pot)
+    return path2, almtp.read_almtp(path2)
+
+
+@pytest.mark.parametrize("level,species", [(12, 2), (16, 1)])
+def test_permuted_tables_match_the_oracle(tmp_path, built, level, species):
+    from mtp_b200.api import MTPB200
+    from oracle_py import OracleMTP
+    path, pot = _permuted(tmp_path, level, species)
+    sysm = util.small_system("fcc", 4.05, (5, 5, 5), species, seed=9)
+    ref = OracleMTP(pot).compute(sysm.x, sysm.type, sysm.ilist, sysm.numneigh, sysm.neigh, sysm.offsets)
+    mtp = MTPB200(path)
+    gpu = mtp.compute_system(sysm)
+    used = mtp.last_kernel_path()
+    assert used["family"] == 2 and mtp.program_kernel_note() == ""      # standard set in another order: same kernels
+    _cmp(gpu, ref, sysm.ilist)
+    mtp.close()
+
+
+def test_two_live_handles_evaluated_alternately(tmp_path, built):
+    """Kernel attributes are per-device state shared by all handles: a second, smaller potential must not
+    lower the shared-memory limit under the first."""
+    from mtp_b200.api import MTPB200
+    from oracle_py import OracleMTP
+    pa, pota = util.write_potential(tmp_path, 16, 2, active_set=True, name="a.almtp")
+    pb, potb = util.write_potential(tmp_path, 16, 1, name="b.almtp")
+    pc, potc = util.write_potential(tmp_path, 10, 1, name="c.almtp")
+    sa = util.small_system("bcc", 3.165, (6, 6, 6), 2, seed=3)
+    sb = util.small_system("bcc", 3.165, (6, 6, 6), 1, seed=3)
+    ra = OracleMTP(pota).compute(sa.x, sa.type, sa.ilist, sa.numneigh, sa.neigh, sa.offsets, grade=True)
+    rb = OracleMTP(potb).compute(sb.x, sb.type, sb.ilist, sb.numneigh, sb.neigh, sb.offsets)
+    rc = OracleMTP(potc).compute(sb.x, sb.type, sb.ilist, sb.numneigh, sb.neigh, sb.offsets)
+    ma = MTPB200(pa, selection_state=True)
+    mb = MTPB200(pb)
+    mc = MTPB200(pc)
+    for _ in range(2):
+        _cmp(ma.compute_system(sa, grade=True), ra, sa.ilist, True)
+        _cmp(mb.compute_system(sb), rb, sb.ilist)
+        _cmp(mc.compute_system(sb), rc, sb.ilist)
+    for m in (ma, mb, mc):
+        m.close()
+
+
+def test_resident_list_between_reneighboring_steps(tmp_path, built):
+    """The host path LAMMPS takes on every step that does not re-neighbor (list_changed = 0): the list, the types and
+    the bookkeeping of the previous upload are reused; several super-chunks so that the sliced, overlapped list upload
+    runs; a grade step toggled in between two list rebuilds."""
+    from mtp_b200.api import MTPB200
+    from oracle_py import OracleMTP
+    path, pot = util.write_potential(tmp_path, 10, 2, active_set=True)
+    sysm = util.small_system("bcc", 3.165, (10, 10, 10), 2, seed=5)
+    orc = OracleMTP(pot)
+    mtp = MTPB200(path, selection_state=True)
+    mtp.set_chunksize(300)           # 2000 atoms -> 7 super-chunks
+    mtp.set_lanes(3)
+    rng = np.random.default_rng(2)
+    x = sysm.x.copy()
+    args = (sysm.type, sysm.ilist, sysm.numneigh, sysm.neigh, sysm.offsets)
+    for step in range(6):
+        if step:
+            x = x + rng.uniform(-0.02, 0.02, size=x.shape)       # atoms move, the list stays (inside the skin)
+        grade = step in (2, 5)
+        ref = orc.compute(x, *args, grade=grade)
+        gpu = mtp.compute_host(x, *args, grade=grade, list_changed=(step in (0, 4)), f_overwrite=bool(step % 2))
+        _cmp(gpu, ref, sysm.ilist, grade)
+        if grade:
+            assert abs(gpu.max_grade - ref.max_grade) <= TOL_AUX * ref.max_grade
+    # a stale list must matter: same call with a DIFFERENT list but list_changed = 0 still answers for the old one
+    other = util.small_system("bcc", 3.165, (10, 10, 10), 2, seed=5, skin=1.0)
+    stale = mtp.compute_host(x, sysm.type, other.ilist, other.numneigh, other.neigh, other.offsets, list_changed=False)
+    _cmp(stale, orc.compute(x, *args), sysm.ilist)      # (inside the cutoff both lists hold the same pairs)
+    mtp.close()
+
+
+def test_grades_stay_on_the_device_until_asked(tmp_path, built):
+    """Host-buffer flavour: a grade step returns only the 8-double record; mtp_fetch_grades / mtp_select_grades_host
+    bring back all grades or only those above a threshold."""
+    import ctypes as C
+    from mtp_b200.api import MTPB200, MTPComputeArgs, _check
+    from oracle_py import OracleMTP
+    path, pot = util.write_potential(tmp_path, 8, 2, active_set=True)
+    sysm = util.small_system("bcc", 3.165, (6, 6, 6), 2, seed=11)
+    ref = OracleMTP(pot).compute(sysm.x, sysm.type, sysm.ilist, sysm.numneigh, sysm.neigh, sysm.offsets, grade=True)
+    mtp = MTPB200(path, selection_state=True)
+    lib = mtp.lib
+    lib.mtp_fetch_grades.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.mtp_select_grades_host.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    f = np.zeros((sysm.nall, 3))
+    ev = np.zeros(8)
+    a = MTPComputeArgs()
+    a.inum, a.nall = sysm.nlocal, sysm.nall
+    a.x, a.type, a.ilist = sysm.x.ctypes.data, sysm.type.ctypes.data, sysm.ilist.ctypes.data
+    a.numneigh, a.neighbors, a.neigh_offsets = sysm.numneigh.ctypes.data, sysm.neigh.ctypes.data, sysm.offsets.ctypes.data
+    a.stride_jj, a.eflag, a.vflag, a.want_grade = 1, 1, 0, 1
+    a.f, a.ev_out = f.ctypes.data, ev.ctypes.data          # no grades array: they stay on the device
+    _check(lib, lib.mtp_compute_host(mtp.h, C.byref(a), 1))
+    assert abs(ev[7] - ref.max_grade) <= TOL_AUX * ref.max_grade
+    g = np.zeros(sysm.nall)
+    _check(lib, lib.mtp_fetch_grades(mtp.h, g.ctypes.data, sysm.nall))
+    assert maxabsrel(g[: sysm.nlocal], ref.grades[: sysm.nlocal]) <= TOL_AUX
+    thr = float(np.quantile(g[: sysm.nlocal], 0.9))
+    ids, vals, cnt = np.zeros(sysm.nlocal, np.int32), np.zeros(sysm.nlocal), C.c_int(0)
+    _check(lib, lib.mtp_select_grades_host(mtp.h, sysm.nlocal, thr, ids.ctypes.data, vals.ctypes.data, sysm.nlocal, C.byref(cnt)))
+    want = np.nonzero(g[: sysm.nlocal] >= thr)[0]
+    assert cnt.value == len(want) and np.array_equal(ids[: cnt.value], want) and np.array_equal(vals[: cnt.value], g[want])
+    with pytest.raises(Exception, match="resident"):
+        _check(lib, lib.mtp_fetch_grades(mtp.h, g.ctypes.data, sysm.nall + 5))
+    mtp.close()
+
+
+def test_cfg_grade_of_a_summed_candidate(tmp_path, built):
+    """Configuration mode over ranks: the candidate vectors add up and the grade is re-evaluated on the device
+    (mtp_cfg_grade) -- two halves of one system here stand for two ranks."""
+    import ctypes as C
+    from mtp_b200.api import MTPB200, _check
+    from oracle_py import OracleMTP
+    path, pot = util.write_potential(tmp_path, 10, 2, active_set=True, cfg_mode=True)
+    sysm = util.small_system("bcc", 3.165, (6, 6, 6), 2, seed=4)
+    ref = OracleMTP(pot).compute(sysm.x, sysm.type, sysm.ilist, sysm.numneigh, sysm.neigh, sysm.offsets, grade=True,
+                                 natoms_total=sysm.nlocal)
+    mtp = MTPB200(path, selection_state=True)
+    half = sysm.nlocal // 2
+    cand = np.zeros(mtp.info.coeff_count)
+    for il in (sysm.ilist[:half], sysm.ilist[half:]):
+        r = mtp.compute_host(sysm.x, sysm.type, il, sysm.numneigh, sysm.neigh, sysm.offsets, grade=True, natoms_total=sysm.nlocal)
+        cand += r.candidate
+    lib = mtp.lib
+    lib.mtp_cfg_grade.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(C.c_double)]
+    g = C.c_double(0.0)
+    _check(lib, lib.mtp_cfg_grade(mtp.h, cand.ctypes.data, sysm.nlocal, C.byref(g)))
+    assert abs(g.value - ref.max_grade) <= TOL_AUX * ref.max_grade
+    mtp.close()
+
+
+def test_config3_full_size_both_variants(tmp_path, built):
+    """BASELINE.json config 3 at its full size (2,000-atom diamond Si, level 20) against the oracle: the latency variant
+    (mtp/small/kk: generated program kernel in its 8-atoms-per-CTA shape) and the throughput variant."""
+    from mtp_b200 import api, harness
+    from mtp_b200.api import MTPB200
+    from oracle_py import OracleMTP
+    cfg = harness.CONFIGS[3]
+    path, pot = util.write_potential(tmp_path, cfg["level"], cfg["species"])
+    sysm = harness.make_config(3)
+    assert sysm.nlocal == 2000
+    ref = OracleMTP(pot).compute(sysm.x, sysm.type, sysm.ilist, sysm.numneigh, sysm.neigh, sysm.offsets)
+    mtp = MTPB200(path)
+    for variant in (api.VARIANT_SMALL, api.VARIANT_LARGE):
+        gpu = mtp.compute_system(sysm, variant=variant)
+        _cmp(gpu, ref, sysm.ilist)
+        used = mtp.last_kernel_path()
+        assert used["program_generated"] and used["program_atoms_per_cta"] == 8, used      # 2,000 atoms: latency shape
+    mtp.close()
+
+
+def test_config4_full_size_grades(tmp_path, built):
+    """BASELINE.json config 4 at its full size (256,000-atom Al-Cu, level 16, neighbourhood grades): size-independent
+    properties on the whole system, the oracle on a slab of centre atoms."""
+    from mtp_b200 import harness
+    from mtp_b200.api import MTPB200
+    from oracle_py import OracleMTP
+    cfg = harness.CONFIGS[4]
+    path, pot = util.write_potential(tmp_path, cfg["level"], cfg["species"], active_set=True)
+    sysm = harness.make_config(4)
+    assert sysm.nlocal == 256000
+    mtp = MTPB200(path, selection_state=True)
+    mtp.set_chunksize(32768)
+    res = mtp.compute_system(sysm, eflag=3, vflag=1, grade=True)
+    f = sysm.reverse_comm(res.f)
+    assert np.abs(f.sum(axis=0)).max() <= 1e-9 * np.abs(f).max() * np.sqrt(sysm.nlocal)
+    assert abs(res.eatom[: sysm.nlocal].sum() - res.energy) <= 1e-12 * abs(res.energy)
+    assert res.max_grade == res.grades[: sysm.nlocal].max()
+    # the same step without grades: energies and forces do not depend on the grade path
+    plain = mtp.compute_system(sysm, eflag=1, vflag=1)
+    assert abs(plain.energy - res.energy) <= TOL_E_REL * abs(res.energy) and maxabsrel(plain.f, res.f) <= TOL_F_MAXABSREL
+    slab = np.arange(120000, 121500, dtype=np.int32)
+    ref = OracleMTP(pot).compute(sysm.x, sysm.type, slab, sysm.numneigh, sysm.neigh, sysm.offsets, eflag=3, vflag=0, grade=True)
+    assert maxabsrel(res.grades[slab], ref.grades[slab]) <= TOL_AUX
+    assert maxabsrel(res.eatom[slab], ref.eatom[slab]) <= TOL_AUX
+    mtp.close()

@@ -55,11 +55,14 @@ def test_missing_file_and_no_gpu_are_fatal(plugin, tmp_path):
 
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
+@pytest.mark.parametrize("kokkos", [False, True], ids=["host-buffers", "kokkos-views"])
 @pytest.mark.parametrize("style", ["mtp/kk", "mtp/small/kk"])
 @pytest.mark.parametrize("name", ["L10_S1_fcc", "L16_S2_bcc", "L12_S3_cluster"])
-def test_inference_styles_match_reference_cpu_style(plugin, tmp_path, style, name):
+def test_inference_styles_match_reference_cpu_style(plugin, tmp_path, style, name, kokkos):
+    """Both build flavours of the style: host buffers (plain LAMMPS, mtp_compute_host) and device views (LMP_KOKKOS,
+    mtp_compute on AtomKokkos / NeighListKokkos views, the 2-D neighbor view in LayoutLeft)."""
     g = golden_util.Golden(name, tmp_path)
-    pair = PairB200(style, g.path, "chunksize", "32768", species=g.pot.species_count)
+    pair = PairB200(style, g.path, "chunksize", "32768", species=g.pot.species_count, kokkos=kokkos)
     assert "species" in pair.log
     r = pair.compute(g.x, g.type, g.nlocal, g.ilist, g.numneigh, g.neigh, g.offsets, eflag=3, vflag=5)
     assert abs(r.energy - g.energy) <= TOL_E_REL * abs(g.energy)
@@ -71,6 +74,12 @@ def test_inference_styles_match_reference_cpu_style(plugin, tmp_path, style, nam
     r2 = pair.compute(g.x, g.type, g.nlocal, g.ilist, g.numneigh, g.neigh, g.offsets, eflag=1, vflag=1, ago=1, f_init=r.f)
     assert maxabsrel(r2.f, 2 * g.f) <= TOL_F_MAXABSREL
     pair.close()
+    if not kokkos:
+        # the style alone (force->pair): LAMMPS cleared f, so the result is stored, whatever the array held
+        lone = PairB200(style, g.path, "chunksize", "32768", species=g.pot.species_count, lone=True)
+        r3 = lone.compute(g.x, g.type, g.nlocal, g.ilist, g.numneigh, g.neigh, g.offsets, eflag=1, vflag=1, f_init=r.f)
+        assert maxabsrel(r3.f, g.f) <= TOL_F_MAXABSREL
+        lone.close()
 
 
 @pytest.mark.gpu
@@ -92,11 +101,16 @@ def _parse_cfg(text):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kokkos", [False, True], ids=["host-buffers", "kokkos-views"])
 @pytest.mark.parametrize("style", ["mtp/extrapolation/kk", "mtp/extrapolation/small/kk"])
 @pytest.mark.parametrize("name", ["L10_S2_nbh", "L10_S2_cfg"])
-def test_extrapolation_styles(plugin, tmp_path, style, name):
+def test_extrapolation_styles(plugin, tmp_path, style, name, kokkos):
     g = golden_util.Golden(name, tmp_path)
     S = g.pot.species_count
+    PairB200_ = PairB200
+
+    def PairB200(*a, **k):      # noqa: N802  (every style of this test in the flavour under test)
+        return PairB200_(*a, kokkos=kokkos, **k)
     # LAMMPS-style: grades only when fix pair raises extrapolation_flag
     pair = PairB200(style, g.path, "chunksize", "100", species=S)
     assert ("Configuration" if g.mode == "cfg" else "Neighborhood") in pair.log
