@@ -264,6 +264,7 @@ int mtp_codegen_source(const char *path, int latency_shape, char *buf, long long
 int mtp_codegen_prebuild(const char *path, int latency_shape, int *compiled_out);
 /* empty when the generated kernel serves this handle, else the reason it does not (the interpreting kernels run) */
 const char *mtp_program_kernel_note(const mtp_handle *h);
+const char *mtp_program_kernel_note_small(const mtp_handle *h);    /* same for the latency shape (mtp/small/kk) */
 
 /* Which kernels the last mtp_compute() of this handle launched (tests assert that the intended path ran):
  * bits 0-3 kernel family (0 generic fused site kernel, 1 DMMA-moment pipeline, 2 register-resident pair kernels),

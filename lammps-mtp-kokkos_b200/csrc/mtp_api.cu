@@ -192,6 +192,7 @@ struct mtp_handle {
   std::vector<short> slot_of_k;   // basic moment -> row of mb / gb
   int p4_nslots = 0;
   std::string p4_note;            // why the generated kernel is not in use (empty when it is)
+  std::string p4_note_small;      // same for the latency shape
   int p3_na = 0;                  // atoms per CTA of the 4-atoms-per-lane program kernel, 0 = not usable for this potential
   size_t prog_max = 0;
   int pl_na[2] = {0, 0};          // atoms per CTA of the program kernel: throughput shape, latency shape
@@ -652,6 +653,7 @@ void upload_potential(mtp_handle *h)
   h->p4[0].unload();
   h->p4[1].unload();
   h->p4_note.clear();
+  h->p4_note_small.clear();
   if ((h->v2_entry >= 0 || h->v1_entry >= 0) && !getenv("MTP_B200_NO_P4")) {
     if (h->v2_entry < 0) {
       std::vector<short> none;
@@ -669,6 +671,8 @@ void upload_potential(mtp_handle *h)
       } catch (const std::exception &e) {
         h->p4[shape].unload();
         if (shape == 0) h->p4_note = e.what();
+        else
+          h->p4_note_small = e.what();
         if (getenv("MTP_B200_P4_REQUIRE")) throw;
       }
     }
@@ -891,7 +895,9 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, p3 ? P3_THREADS : PROG_THREADS, smem_p));
     grid_p_cap = std::max(1, per_sm) * h->sm_count;
     // the generated kernel of this potential, when it was built: latency shape for small systems if there is one
-    p4m = (small && h->p4[1].loaded()) ? &h->p4[1] : (h->p4[0].loaded() ? &h->p4[0] : nullptr);
+    // (a system that cannot give every SM a 32-atom chunk is a small system whatever the style is called)
+    const bool small_p4 = a.variant == MTP_VARIANT_SMALL || nfirst < 32 * h->sm_count;
+    p4m = (small_p4 && h->p4[1].loaded()) ? &h->p4[1] : (h->p4[0].loaded() ? &h->p4[0] : nullptr);
     if (p4m) {
       p3 = nullptr;
       na = p4m->choice.prm.na;
@@ -1136,6 +1142,7 @@ int mtp_program_check(const char *path, int atoms_per_cta, double *max_rel_err_o
 int mtp_last_kernel_path(const mtp_handle *h) { return h ? h->last_path : -1; }
 
 const char *mtp_program_kernel_note(const mtp_handle *h) { return h ? h->p4_note.c_str() : ""; }
+const char *mtp_program_kernel_note_small(const mtp_handle *h) { return h ? h->p4_note_small.c_str() : ""; }
 
 namespace {
 // host-only: the generator inputs mtp_create would use for the potential at `path`

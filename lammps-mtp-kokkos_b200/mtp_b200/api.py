@@ -93,6 +93,8 @@ def load_library():
     lib.mtp_last_kernel_path.argtypes = [C.c_void_p]
     lib.mtp_program_kernel_note.argtypes = [C.c_void_p]
     lib.mtp_program_kernel_note.restype = C.c_char_p
+    lib.mtp_program_kernel_note_small.argtypes = [C.c_void_p]
+    lib.mtp_program_kernel_note_small.restype = C.c_char_p
     lib.mtp_codegen_source.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_longlong, _llp, _llp]
     lib.mtp_codegen_prebuild.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int)]
     lib.mtp_nve_initial_integrate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
@@ -299,9 +301,10 @@ class MTPB200:
         return {"family": v & 15, "program_v3": bool(v & 16), "program_generated": bool(v & 32),
                 "program_atoms_per_cta": (v >> 8) & 255}
 
-    def program_kernel_note(self) -> str:
+    def program_kernel_note(self, latency_shape: bool = False) -> str:
         """Empty when the generated contraction-program kernel serves this handle, else why it does not."""
-        return self.lib.mtp_program_kernel_note(self.h).decode()
+        fn = self.lib.mtp_program_kernel_note_small if latency_shape else self.lib.mtp_program_kernel_note
+        return fn(self.h).decode()
 
     def synchronize(self):
         _check(self.lib, self.lib.mtp_synchronize(self.h))

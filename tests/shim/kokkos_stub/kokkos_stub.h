@@ -63,7 +63,10 @@ template <class T> struct KKDualView {
     d_view.ext[1] = n1;
     d_view.str[0] = n1 > 0 ? n1 : 1;
     d_view.str[1] = 1;
-    if (d_view.span()) kk_check(cudaMalloc((void **) &d_view.ptr, sizeof(T) * (size_t) d_view.span()), "cudaMalloc");
+    if (d_view.span()) {    // Kokkos views are zero-initialised
+      kk_check(cudaMalloc((void **) &d_view.ptr, sizeof(T) * (size_t) d_view.span()), "cudaMalloc");
+      kk_check(cudaMemset(d_view.ptr, 0, sizeof(T) * (size_t) d_view.span()), "cudaMemset");
+    }
   }
   void release()
   {

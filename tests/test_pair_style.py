@@ -107,10 +107,9 @@ def _parse_cfg(text):
 def test_extrapolation_styles(plugin, tmp_path, style, name, kokkos):
     g = golden_util.Golden(name, tmp_path)
     S = g.pot.species_count
-    PairB200_ = PairB200
-
-    def PairB200(*a, **k):      # noqa: N802  (every style of this test in the flavour under test)
-        return PairB200_(*a, kokkos=kokkos, **k)
+    from functools import partial
+    import pair_driver
+    PairB200 = partial(pair_driver.PairB200, kokkos=kokkos)      # noqa: N806  (every style of this test in one flavour)
     # LAMMPS-style: grades only when fix pair raises extrapolation_flag
     pair = PairB200(style, g.path, "chunksize", "100", species=S)
     assert ("Configuration" if g.mode == "cfg" else "Neighborhood") in pair.log
