@@ -38,23 +38,29 @@ P4Choice p4_choose(const Potential &p, size_t smem_optin, bool latency_shape)
   // per row (32 per CTA); potentials whose tables do not fit that (levels >= 20) keep the interpreting kernels, whose
   // loop stays in the instruction cache.  The latency shape (mtp/small/kk: few atoms, every SM must get a chunk) takes
   // 8 atoms per CTA and 8 warps: the chunk's critical path is what counts there.
-  P4Params prm;
-  prm.na = latency_shape ? 8 : 32;
-  prm.warps = latency_shape ? 8 : 4;
-  size_t b = p4_smem_bytes(p, prm);
-  if (b == 0) return ch;    // structure not supported
-  if (b <= two_ctas) {      // two CTAs per SM: their instruction streams overlap
-    ch.prm = prm;
-    ch.min_blocks = 2;
-    ch.ok = true;
-    return ch;
-  }
-  prm.warps = 8;
-  b = p4_smem_bytes(p, prm);
-  if (b <= smem_optin) {
-    ch.prm = prm;
-    ch.min_blocks = 1;
-    ch.ok = true;
+  // Latency shape: a chunk streams the whole program through one SM whatever its width, so the widest chunk that fits
+  // (16 atoms, else 8) halves the number of chunks per SM; 8 warps shorten the chunk's critical path.
+  const int nas[2] = {latency_shape ? 16 : 32, latency_shape ? 8 : 32};
+  for (int t = 0; t < (latency_shape ? 2 : 1); t++) {
+    P4Params prm;
+    prm.na = nas[t];
+    prm.warps = latency_shape ? 8 : 4;
+    size_t b = p4_smem_bytes(p, prm);
+    if (b == 0) return ch;    // structure not supported
+    if (b <= two_ctas) {      // two CTAs per SM: their instruction streams overlap
+      ch.prm = prm;
+      ch.min_blocks = 2;
+      ch.ok = true;
+      return ch;
+    }
+    prm.warps = 8;
+    b = p4_smem_bytes(p, prm);
+    if (b <= smem_optin) {
+      ch.prm = prm;
+      ch.min_blocks = 1;
+      ch.ok = true;
+      return ch;
+    }
   }
   return ch;
 }

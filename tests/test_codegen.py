@@ -63,13 +63,13 @@ def test_throughput_shape_is_refused_when_a_warp_of_atoms_does_not_fit(tmp_path)
     path, _ = util.write_potential(tmp_path, 20, 1)
     with pytest.raises(api.MTPError, match="outside the generator's range"):
         api.codegen_source(path, False)
-    assert api.codegen_source(path, True)[1]["atoms_per_cta"] == 8
+    assert api.codegen_source(path, True)[1]["atoms_per_cta"] == 16
 
 
 def test_latency_shape_and_two_atoms_per_lane(tmp_path):
     path, pot = util.write_potential(tmp_path, 12, 2)
     info = _host_check(tmp_path, path, pot, True)
-    assert info["atoms_per_cta"] == 8
+    assert info["atoms_per_cta"] == 16
     info = _host_check(tmp_path, path, pot, False, env={"MTP_B200_P4": "64,8,24,8,1"})
     assert info["atoms_per_cta"] == 64 and info["warps"] == 8
     info = _host_check(tmp_path, path, pot, False, env={"MTP_B200_P4": "16,3,6,2,1"})    # tiny cache, odd warp count

@@ -200,7 +200,7 @@ def test_cfg_grade_of_a_summed_candidate(tmp_path, built):
 
 def test_config3_full_size_both_variants(tmp_path, built):
     """BASELINE.json config 3 at its full size (2,000-atom diamond Si, level 20) against the oracle: the latency variant
-    (mtp/small/kk: generated program kernel in its 8-atoms-per-CTA shape) and the throughput variant."""
+    (mtp/small/kk: generated program kernel in its 16-atoms-per-CTA shape) and the throughput variant."""
     from mtp_b200 import api, harness
     from mtp_b200.api import MTPB200
     from oracle_py import OracleMTP
@@ -214,7 +214,7 @@ def test_config3_full_size_both_variants(tmp_path, built):
         gpu = mtp.compute_system(sysm, variant=variant)
         _cmp(gpu, ref, sysm.ilist)
         used = mtp.last_kernel_path()
-        assert used["program_generated"] and used["program_atoms_per_cta"] == 8, (used, mtp.program_kernel_note(True))
+        assert used["program_generated"] and used["program_atoms_per_cta"] == 16, (used, mtp.program_kernel_note(True))
     mtp.close()
 
 
