@@ -240,9 +240,9 @@ def main():
                     help="ghost exchange: one 26-direction stage (default) or LAMMPS's three dimension-by-dimension stages")
     ap.add_argument("--md-steps", type=int, default=50,
                     help="informational device-resident NVE run of this many steps after the bench (N = 1 only; 0 = off)")
-    ap.add_argument("--overlap", action="store_true",
-                    help="N > 1: hide the halo exchange behind the interior atoms (decomp.OverlappedStep: three partial "
-                         "evaluations per step; measured slower than the plain sequence at config 2, see DESIGN.md)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N > 1: do not hide the halo exchange behind the interior atoms (decomp.OverlappedStep + "
+                         "mtp_compute_phased); default is to overlap")
     ap.add_argument("--lanes", type=int, default=3, help="internal streams the super-chunks are dealt to (mtp_set_lanes)")
     ap.add_argument("--chunksize", type=int, default=131072,
                     help="pair_style ... chunksize N: README.md:44 of the reference asks the user to tune it (\"sufficient "
@@ -358,7 +358,7 @@ def main():
 
     lst = {"nn": t_nn, "neigh": t_neigh, "mx": max_nn}
     overlap = None
-    if world > 1 and args.halo == "direct" and args.overlap:
+    if world > 1 and args.halo == "direct" and not args.no_overlap:
         overlap = decomp.OverlappedStep(halo, sysm.x[:nlocal], halo.sublo, halo.subhi, halo.rghost, dev)
         if not overlap.enabled:
             overlap = None
@@ -369,6 +369,11 @@ def main():
                            grades=t_grades if grade_step else None,
                            stride_i=int(lst["neigh"].shape[1]) if devlist_mode else 0, stride_jj=1)
 
+    def compute_phased(il, counts, waits, dones, evbuf):
+        mtp.compute_device_phased(counts, waits, dones, t_x, t_type, il, lst["nn"], lst["neigh"], t_off, t_f, evbuf, eflag=1,
+                                  vflag=1, variant=variant, stream=stream, max_numneigh=lst["mx"],
+                                  stride_i=int(lst["neigh"].shape[1]) if devlist_mode else 0, stride_jj=1)
+
     def step_device(rebuild=False):
         # what LAMMPS does around Pair::compute every step: forward comm of x, zero f, compute, reverse comm of f,
         # and the energy/virial all-reduce (rebuild: a re-neighboring step, list built on the device after the halo).
@@ -376,7 +381,7 @@ def main():
         grade_step = bool(args.grade_every) and step_no[0] % args.grade_every == 0
         step_no[0] += 1
         if overlap is not None and not rebuild and not grade_step:
-            overlap.run(t_x, t_f, t_ev, compute_part, t_ilist)
+            overlap.run(t_x, t_f, t_ev, compute_part, t_ilist, compute_phased=compute_phased)
             return
         halo.forward(t_x)
         if rebuild:

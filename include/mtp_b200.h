@@ -153,6 +153,16 @@ int mtp_set_lanes(mtp_handle *h, int lanes);
 /* ---- the hot path ---------------------------------------------------------------------------- */
 /* Asynchronous on args->stream; results are valid after the stream is synchronised. */
 int mtp_compute(mtp_handle *h, const mtp_compute_args *device_args);
+/* The same evaluation with the listed centres cut into `nphase` consecutive runs of ilist (phase_inum[p] centres each,
+ * adding up to args->inum).  The kernels of phase p start only after wait_events[p] (a cudaEvent_t, or NULL) has
+ * completed, and done_events[p] (cudaEvent_t or NULL) is recorded when all work of phases 0..p is complete.  This is
+ * how a multi-GPU caller hides the ghost halo (LAMMPS Comm::forward_comm / reverse_comm around pair_mtp.cpp:72-280)
+ * behind the pair style: list the interior centres -- those without a ghost in their neighbor list -- first and last,
+ * the boundary centres in between with wait = "ghost positions arrived"; when the boundary phase is done the ghost
+ * forces can travel back while the remaining interior centres are evaluated.  One energy / virial record, one set of
+ * lanes: unlike separate calls per run, the phases share the library's internal streams. */
+int mtp_compute_phased(mtp_handle *h, const mtp_compute_args *device_args, int nphase, const int *phase_inum,
+                       void *const *wait_events, void *const *done_events);
 /* Waits for the device and reports deferred errors (species bound check, pair_mtp.cpp:91-93). */
 int mtp_synchronize(mtp_handle *h);
 /* Same evaluation with HOST buffers: copies x (every call) and, when list_changed != 0 -- LAMMPS re-neighboring

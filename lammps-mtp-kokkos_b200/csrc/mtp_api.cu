@@ -243,6 +243,8 @@ struct mtp_handle {
   static constexpr int kMaxLanes = 4;
   Lane lanes[kMaxLanes];
   cudaEvent_t ev_fork = nullptr;
+  cudaStream_t phase_stream = nullptr;
+  std::vector<cudaEvent_t> phase_events;
   int nlanes = 2;
   V2GatherFn v2_radial = nullptr;
   int v2_grid_g = 0, v2_grid_r = 0, v2_grid_m = 0, v2_grid_f = 0, v2_grid_fg[2] = {0, 0}, v2_ab = 0;
@@ -758,8 +760,17 @@ int plan_chunk(const mtp_handle *h, int inum, bool grade)
 
 // chunk_ready (optional): one event per super-chunk that must have completed before the chunk's kernels may read
 // the neighbor list (the host path uploads the list slice by slice while earlier chunks compute)
+// phases (optional): the centres are cut into consecutive runs of the list ("phases", mtp_compute_phased); super-chunks
+// never straddle a phase, the kernels of a phase wait for its event, and an event is recorded when a phase is complete
+struct PhaseSpec {
+  int nphase = 0;
+  const int *inum = nullptr;
+  void *const *wait_events = nullptr;
+  void *const *done_events = nullptr;
+};
+
 void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
-                 const std::vector<cudaEvent_t> *chunk_ready = nullptr)
+                 const std::vector<cudaEvent_t> *chunk_ready = nullptr, const PhaseSpec *phases = nullptr)
 {
   const DevPotential &d = h->dpot;
   const bool grade = a.want_grade != 0;
@@ -824,7 +835,29 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
   }
   const int ld = (chunk + 63) / 64 * 64;
   if (grade) h->d_cand.ensure((size_t) chunk * h->qpad);
-  const int nsuper = a.inum > 0 ? (a.inum + chunk - 1) / chunk : 1;
+  // super-chunks: {first centre, count, phase}
+  struct Chunk {
+    int first, n, phase;
+  };
+  std::vector<Chunk> chunks;
+  if (phases && phases->nphase > 0) {
+    int at = 0;
+    for (int p = 0; p < phases->nphase; p++) {
+      const int np = phases->inum[p];
+      // a phase is cut into equal super-chunks no larger than `chunk`
+      const int parts = np > 0 ? (np + chunk - 1) / chunk : 0;
+      for (int q = 0; q < parts; q++) {
+        const int b = (int) ((long long) np * q / parts), e = (int) ((long long) np * (q + 1) / parts);
+        chunks.push_back({at + b, e - b, p});
+      }
+      at += np;
+    }
+    if (at != a.inum) throw std::invalid_argument("the phases do not add up to inum");
+  } else
+    for (int first = 0; first < std::max(a.inum, 1); first += chunk)
+      chunks.push_back({first, std::max(0, std::min(chunk, a.inum - first)), 0});
+  if (chunks.empty()) chunks.push_back({0, 0, 0});
+  const int nsuper = (int) chunks.size();
   const int nlanes = (use_v2 && !grade) ? std::max(1, std::min(h->nlanes, nsuper)) : 1;    // grade scratch is not per lane
   if (use_v2) {
     const V2Entry &E = kV2[h->v2_entry];
@@ -937,9 +970,35 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
     CUDA_CHECK(cudaLaunchKernel((const void *) p4m->kernel, dim3(grid), dim3(p4m->info.threads), kargs, p4m->info.smem_bytes, ls));
   };
 
+  // a phase is complete when every lane has drained the chunks dealt to it so far
+  auto phase_done = [&](int p) {
+    if (!phases || !phases->done_events || !phases->done_events[p]) return;
+    cudaEvent_t done = (cudaEvent_t) phases->done_events[p];
+    if (nlanes > 1) {
+      if (!h->phase_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&h->phase_stream, cudaStreamNonBlocking));
+      for (int l = 0; l < nlanes; l++) {
+        if (h->phase_events.size() <= (size_t) l) {
+          cudaEvent_t e;
+          CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+          h->phase_events.push_back(e);
+        }
+        CUDA_CHECK(cudaEventRecord(h->phase_events[l], h->lanes[l].stream));
+        CUDA_CHECK(cudaStreamWaitEvent(h->phase_stream, h->phase_events[l], 0));
+      }
+      CUDA_CHECK(cudaEventRecord(done, h->phase_stream));
+    } else
+      CUDA_CHECK(cudaEventRecord(done, st));
+  };
+
   for (int sc = 0; sc < nsuper; sc++) {
-    const int first = sc * chunk;
-    const int n = std::max(0, std::min(chunk, a.inum - first));
+    const int first = chunks[sc].first;
+    const int n = chunks[sc].n;
+    if (sc > 0 && chunks[sc].phase != chunks[sc - 1].phase)
+      for (int p = chunks[sc - 1].phase; p < chunks[sc].phase; p++) phase_done(p);
+    if (phases && phases->wait_events && phases->wait_events[chunks[sc].phase]) {
+      cudaStream_t ws = (use_v2 && nlanes > 1) ? h->lanes[sc % nlanes].stream : st;
+      CUDA_CHECK(cudaStreamWaitEvent(ws, (cudaEvent_t) phases->wait_events[chunks[sc].phase], 0));
+    }
     s.inum = n;
     s.first_ii = first;
     s.cand_rows = grade ? h->d_cand.p : nullptr;
@@ -1061,6 +1120,8 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
       }
     }
   }
+  if (phases)
+    for (int p = chunks.back().phase; p < phases->nphase; p++) phase_done(p);
   if (nlanes > 1)    // join
     for (int l = 0; l < nlanes; l++) {
       CUDA_CHECK(cudaEventRecord(h->lanes[l].done, h->lanes[l].stream));
@@ -1320,6 +1381,8 @@ void mtp_destroy(mtp_handle *h)
     if (L.done) cudaEventDestroy(L.done);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->phase_stream) cudaStreamDestroy(h->phase_stream);
+  for (cudaEvent_t e : h->phase_events) cudaEventDestroy(e);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->ev_f0) cudaEventDestroy(h->ev_f0);
   for (cudaEvent_t e : h->copy_events) cudaEventDestroy(e);
@@ -1421,6 +1484,24 @@ int mtp_compute(mtp_handle *h, const mtp_compute_args *a)
   return guarded([&] {
     set_device(h);
     launch_site(h, *a, (cudaStream_t) a->stream);
+  });
+}
+
+int mtp_compute_phased(mtp_handle *h, const mtp_compute_args *a, int nphase, const int *phase_inum, void *const *wait_events,
+                       void *const *done_events)
+{
+  if (!h || !a || nphase < 1 || !phase_inum) return fail(MTP_ERR_ARG, "null argument");
+  if (!a->x || !a->type || !a->numneigh || !a->neighbors || !a->f || !a->ev_out)
+    return fail(MTP_ERR_ARG, "x, type, numneigh, neighbors, f and ev_out are required");
+  if (a->variant != MTP_VARIANT_LARGE && a->variant != MTP_VARIANT_SMALL) return fail(MTP_ERR_ARG, "unknown variant");
+  return guarded([&] {
+    set_device(h);
+    PhaseSpec ph;
+    ph.nphase = nphase;
+    ph.inum = phase_inum;
+    ph.wait_events = wait_events;
+    ph.done_events = done_events;
+    launch_site(h, *a, (cudaStream_t) a->stream, nullptr, &ph);
   });
 }
 

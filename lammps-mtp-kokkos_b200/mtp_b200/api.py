@@ -248,6 +248,28 @@ class MTPB200:
         a.max_numneigh = int(max_numneigh)
         _check(self.lib, self.lib.mtp_compute(self.h, C.byref(a)))
 
+    def compute_device_phased(self, phase_inum, wait_events, done_events, x, type_, ilist, numneigh, neigh, offsets, f, ev_out, *,
+                              stride_i=0, stride_jj=1, eflag=1, vflag=1, variant=VARIANT_LARGE, stream=None, max_numneigh=0):
+        """mtp_compute_phased: ilist is cut into consecutive phases of phase_inum[p] centres; phase p starts after the
+        torch.cuda.Event wait_events[p] (or None) and done_events[p] (or None) is recorded when it is complete."""
+        a = MTPComputeArgs()
+        a.variant, a.nall, a.inum = variant, x.shape[0], ilist.shape[0]
+        a.x, a.type, a.ilist = x.data_ptr(), type_.data_ptr(), ilist.data_ptr()
+        a.numneigh, a.neighbors = numneigh.data_ptr(), neigh.data_ptr()
+        a.neigh_offsets = None if offsets is None else offsets.data_ptr()
+        a.stride_i, a.stride_jj, a.neighmask = stride_i, stride_jj, 0x1FFFFFFF
+        a.eflag, a.vflag = eflag, vflag
+        a.f, a.ev_out = f.data_ptr(), ev_out.data_ptr()
+        a.stream = stream
+        a.max_numneigh = int(max_numneigh)
+        n = len(phase_inum)
+        cnt = (C.c_int * n)(*[int(v) for v in phase_inum])
+        wv = (C.c_void_p * n)(*[None if e is None else e.cuda_event for e in wait_events])
+        dv = (C.c_void_p * n)(*[None if e is None else e.cuda_event for e in done_events])
+        self.lib.mtp_compute_phased.argtypes = [C.c_void_p, C.POINTER(MTPComputeArgs), C.c_int, C.POINTER(C.c_int),
+                                                C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        _check(self.lib, self.lib.mtp_compute_phased(self.h, C.byref(a), n, cnt, wv, dv))
+
     ERR_CAPACITY = -7
 
     def neigh_build(self, x, nlocal: int, cutneigh: float, width: int | None = None, stream=None):

@@ -371,32 +371,55 @@ class OverlappedStep:
     """One force evaluation of a rank with the halo exchange hidden behind the interior atoms:
 
         forward halo posted  ||  pair style on the first half of the interior atoms
-        pair style on the boundary atoms (needs the ghosts)
+        pair style on the boundary atoms (waits for the ghosts)
         reverse halo posted  ||  pair style on the second half of the interior atoms
-        ghost forces added, one 7-double all-reduce
+        ghost forces added (atomic adds, concurrent with the interior forces), one 7-double all-reduce
 
-    ``compute(ilist, ev)`` is the caller's closure around ``MTPB200.compute_device`` for a list of centre atoms; the
-    three partial energy / virial records are summed before the all-reduce.  With one rank (no remote peers) the plain
-    sequence forward / compute / reverse is used."""
+    GPU: ONE ``mtp_compute_phased`` call -- the three runs of the list share the library's lanes, the boundary phase waits
+    for a CUDA event recorded behind the NCCL receives, and the reverse exchange starts on a side stream from the event
+    the library records when the boundary phase is complete.  CPU (gloo tests; ``compute`` = closure around the checker):
+    three partial evaluations in the same order.  With one rank the plain sequence forward / compute / reverse is used."""
 
     def __init__(self, halo, x_own, sublo, subhi, rghost, device, min_part=16384):
         self.halo = halo
+        self.device = device
         interior, boundary = split_interior(x_own, sublo, subhi, rghost)
         self.enabled = isinstance(halo, DirectHalo) and halo.world > 1 and len(interior) >= 2 * min_part and len(boundary) > 0
         half = len(interior) // 2
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)  # noqa: E731
         self.parts = [t(interior[:half]), t(boundary), t(interior[half:])] if self.enabled else []
         self.counts = (int(half), int(len(boundary)), int(len(interior) - half))
+        self.ilist = torch.cat(self.parts) if self.enabled else None
         self.evs = [torch.zeros(8, dtype=torch.float64, device=device) for _ in range(3)]
+        if self.enabled and device.type == "cuda":
+            self.side = [torch.cuda.Stream(device=device) for _ in range(2)]
+            self.ev_halo = torch.cuda.Event()
+            self.ev_boundary = torch.cuda.Event()
+            self.ev_reverse = torch.cuda.Event()
 
-    def run(self, x, f, ev, compute, all_ilist, grade=False):
+    def run(self, x, f, ev, compute, all_ilist, grade=False, compute_phased=None):
         h = self.halo
         if not self.enabled:
             h.forward(x)
             f.zero_()
             compute(all_ilist, ev)
             h.reverse(f)
-            h.allreduce_ev(ev, grade) if isinstance(h, DirectHalo) else h.allreduce_ev(ev)
+            h.allreduce_ev(ev, grade)
+            return
+        if compute_phased is not None and self.device.type == "cuda":
+            main = torch.cuda.current_stream()
+            works = h.forward_begin(x)
+            with torch.cuda.stream(self.side[0]):       # the event completes when the ghost positions have landed
+                h.forward_end(works)
+                self.ev_halo.record()
+            f.zero_()
+            compute_phased(self.ilist, self.counts, [None, self.ev_halo, None], [None, self.ev_boundary, None], ev)
+            self.side[1].wait_event(self.ev_boundary)
+            with torch.cuda.stream(self.side[1]):       # ghost forces travel back under the second interior phase
+                h.reverse_end(f, h.reverse_begin(f))
+                self.ev_reverse.record()
+            main.wait_event(self.ev_reverse)
+            h.allreduce_ev(ev, grade)
             return
         works = h.forward_begin(x)
         f.zero_()

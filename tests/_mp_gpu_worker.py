@@ -49,8 +49,15 @@ def main():
         def part(il, evbuf):
             mtp.compute_device(x, t_type, il, t_nn, t_ne, t_off, f, evbuf, eatom=eatom, eflag=3, vflag=1,
                                stream=torch.cuda.current_stream().cuda_stream)
+        def phased(il, counts, waits, dones, evbuf):
+            mtp.compute_device_phased(counts, waits, dones, x, t_type, il, t_nn, t_ne, t_off, f, evbuf, eflag=1, vflag=1,
+                                      stream=torch.cuda.current_stream().cuda_stream)
         f.fill_(7.0)      # run() zeroes f itself
-        ov.run(x, f, ev, part, t_il)
+        ov.run(x, f, ev, part, t_il, compute_phased=phased if world > 1 else None)
+        if world > 1:      # per-atom energies are not part of the phased call: one plain evaluation for them
+            f2, ev2 = torch.zeros_like(f), torch.zeros_like(ev)
+            mtp.compute_device(x, t_type, t_il, t_nn, t_ne, t_off, f2, ev2, eatom=eatom, eflag=3, vflag=1,
+                               stream=torch.cuda.current_stream().cuda_stream)
     else:
         halo.forward(x)
         mtp.compute_device(x, t_type, t_il, t_nn, t_ne, t_off, f, ev, eatom=eatom, eflag=3, vflag=1,
