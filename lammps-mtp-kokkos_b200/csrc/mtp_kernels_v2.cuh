@@ -34,6 +34,9 @@ struct PairBuf {
   int ncap;           // slots per centre (>= max numneigh)
 };
 
+#ifndef MTP_V2_ACC
+#define MTP_V2_ACC 0       // > 0: force the accumulator budget of the moment kernel (experiments); 0 = per-level choice
+#endif
 template <int D0> struct V2Shape {
   static constexpr int R = D0 / 2 + 1 + (D0 & 1);
   __host__ __device__ static constexpr int dmu(int mu) { return D0 - 2 * mu > 0 ? D0 - 2 * mu : 0; }
@@ -55,7 +58,11 @@ template <int D0> struct V2Shape {
     for (int c = 0; c <= D0 - a - b; c++) s += rcnt(a + b + c);
     return s;
   }
-  static constexpr int BUDGET = (KF + ((KF + 47) / 48) - 1) / ((KF + 47) / 48) + 2;
+  // basic-moment accumulators a thread keeps in registers (one pass): fewer and therefore more passes (warps) per CTA
+  // up to level 18 -- the kernel is latency bound and wants resident warps -- 48 above, where the passes are many anyway
+  static constexpr int ACC = MTP_V2_ACC > 0 ? MTP_V2_ACC : (D0 <= 7 ? 32 : 48);
+  static constexpr int NPASS0 = (KF + ACC - 1) / ACC;    // passes if the columns packed perfectly
+  static constexpr int BUDGET = (KF + NPASS0 - 1) / NPASS0 + 2;
   // pass of column (a, b); with (a, b) = (D0 + 1, 0) returns the number of passes
   __host__ __device__ static constexpr int pass_of(int qa, int qb)
   {
@@ -487,8 +494,14 @@ template <int D0> struct V2PassDispatch<D0, V2Shape<D0>::NP> {
   __device__ __forceinline__ static void run(int, const SiteArgs &, const PairBuf &, double *, int, double *) {}
 };
 
+// resident CTAs the kernel is compiled for: shared memory allows three; with many passes (warps) per CTA two are enough
+// to keep ~16 warps on an SM, and the register cap stays above what a pass of MTP_V2_ACC accumulators needs
+template <int D0> struct V2MomentsBounds {
+  static constexpr int NP = V2Shape<D0>::NP;
+  static constexpr int MINB = NP <= 5 ? 3 : (NP <= 8 ? 2 : 1);
+};
 template <int D0>
-__global__ void __launch_bounds__(32 * V2Shape<D0>::NP, (288 / (32 * V2Shape<D0>::NP)) > 0 ? (288 / (32 * V2Shape<D0>::NP)) : 1)
+__global__ void __launch_bounds__(32 * V2Shape<D0>::NP, V2MomentsBounds<D0>::MINB)
 mtp_moments_v2(SiteArgs a, PairBuf pb, double *__restrict__ mb, int ld)
 {
   extern __shared__ __align__(16) unsigned char smem[];    // two tiles of V2_NT x NF x 33 doubles
