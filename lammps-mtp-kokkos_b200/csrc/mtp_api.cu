@@ -331,9 +331,9 @@ bool build_v1_tables(mtp_handle *h, int e)
 typedef void (*V2GatherKernel)(DevPotential, SiteArgs, PairBuf);
 typedef void (*V2MomentsKernel)(SiteArgs, PairBuf, double *, int);
 typedef void (*V2ForcesKernel)(SiteArgs, PairBuf, const double *, int, double *);
-// atoms per CTA of the force kernel: two buffers of canonical adjoints (2 x KF x AB x 8 B) stay below ~110 KB so that
+// atoms per CTA of the force kernel: three buffers of canonical adjoints (3 x KF x AB x 8 B) stay below ~110 KB so that
 // two CTAs fit an SM; fixed per D0 at compile time so that only one variant per shape is instantiated
-constexpr int v2_ab_for(int kf) { return 2 * kf * 64 * 8 <= 110 * 1024 ? 64 : 2 * kf * 32 * 8 <= 110 * 1024 ? 32 : 2 * kf * 16 * 8 <= 110 * 1024 ? 16 : 8; }
+constexpr int v2_ab_for(int kf) { return 3 * kf * 64 * 8 <= 110 * 1024 ? 64 : 3 * kf * 32 * 8 <= 110 * 1024 ? 32 : 3 * kf * 16 * 8 <= 110 * 1024 ? 16 : 8; }
 struct V2Entry {
   int d0, R, KF, NP, AB;
   V2GatherKernel radial_v[3];    // {resident CTAs per SM, batches of 32 neighbors in flight}: {2, 3}, {3, 1}, {3, 2}
@@ -578,7 +578,7 @@ void upload_potential(mtp_handle *h)
       }
       // forces: atoms per CTA fixed per shape (v2_ab_for)
       h->v2_ab = E.AB;
-      h->v2_smem_f = (size_t) 2 * E.KF * E.AB * 8 + (size_t) 2 * (E.AB + 1) * 4;
+      h->v2_smem_f = (size_t) V2_FNB * E.KF * E.AB * 8 + (size_t) V2_FNB * (E.AB + 1) * 4;
       for (int gq = 0; gq < 2 && ok; gq++) {
         const void *fk = (const void *) E.forces[gq];
         ok = ok && h->v2_smem_f <= max_dynamic_smem(fk, smem_max);

@@ -611,6 +611,11 @@ __device__ __forceinline__ void v2_pair_force(const double *__restrict__ gr /* g
   for (int mu = 0; mu < R; mu++) pm[mu] = PM[mu];
 }
 
+// The pairs of a CTA's atom blocks form ONE stream: lane l of iteration t takes pair 256 t + l of the stream, whatever
+// block it belongs to, so no lane idles at the end of a block (a block of 32 atoms x 26 pairs fills 3.25 iterations of
+// 256 lanes).  Three blocks of adjoints are resident: the current one, the next one (an iteration may straddle the two)
+// and the one after, in flight (cp.async).
+constexpr int V2_FNB = 3;
 template <int D0, int AB, bool GRADE>
 __global__ void __launch_bounds__(256, 2)
 mtp_forces_v2(SiteArgs a, PairBuf pb, const double *__restrict__ gb, int ld, double *__restrict__ partials)
@@ -618,11 +623,11 @@ mtp_forces_v2(SiteArgs a, PairBuf pb, const double *__restrict__ gb, int ld, dou
   using Sh = V2Shape<D0>;
   constexpr int R = Sh::R, KF = Sh::KF, GSZ = KF * AB;
   extern __shared__ __align__(16) unsigned char smem[];
-  double *gbuf = reinterpret_cast<double *>(smem);                      // [2][KF][AB] adjoints, rows = canonical slots
-  int *prebuf = reinterpret_cast<int *>(gbuf + 2 * (size_t) GSZ);       // [2][AB + 1] exclusive prefix of pcnt
+  double *gbuf = reinterpret_cast<double *>(smem);                            // [3][KF][AB] adjoints, rows = canonical slots
+  int *prebuf = reinterpret_cast<int *>(gbuf + V2_FNB * (size_t) GSZ);        // [3][AB + 1] exclusive prefix of pcnt
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double vloc[6] = {0, 0, 0, 0, 0, 0};
-  const int nblk = (a.inum + AB - 1) / AB;
+  const int nblk = (a.inum + AB - 1) / AB, G = gridDim.x;
 
   // asynchronous fill of one block's adjoints (straight 16-byte copies of the rows of gb) + pair-count prefix
   auto prefetch = [&](int buf, int blk) {
@@ -654,59 +659,106 @@ mtp_forces_v2(SiteArgs a, PairBuf pb, const double *__restrict__ gb, int ld, dou
     }
   };
 
-  int blk = blockIdx.x, buf = 0;
-  if (blk < nblk) prefetch(0, blk);
-  for (; blk < nblk; blk += gridDim.x, buf ^= 1) {
+  int b_cur = blockIdx.x, buf_cur = 0, buf_nxt = 1, buf_nn = 2;
+  if (b_cur < nblk) {
+    prefetch(buf_cur, b_cur);
+    if (b_cur + G < nblk) prefetch(buf_nxt, b_cur + G);
     cp_async_wait<0>();
-    __syncthreads();    // this block's adjoints + prefix are in place; the other buffer is free
-    if (blk + gridDim.x < nblk) prefetch(buf ^ 1, blk + gridDim.x);
-    const double *g = gbuf + (size_t) buf * GSZ;
-    const int *pre = prebuf + buf * (AB + 1);
-    const int ii0 = blk * AB;
-    const int total = pre[AB];
-    // pair records are requested one iteration ahead of their use
+    __syncthreads();
+    if (b_cur + 2 * G < nblk) prefetch(buf_nn, b_cur + 2 * G);
+
+    // a pair record, located in the stream: state 0 = past the end of everything this CTA owns, 1 = live,
+    // 2 = beyond the two resident blocks (located again once the blocks have moved on)
     struct Rec {
       double ux, uy, uz, d, f[R], fd[R];
-      int j, al;
-      bool live;
+      size_t s;
+      int j, al, which, state;
     };
-    auto load_rec = [&](int p, Rec &r) {
-      r.live = p < total;
+    auto load_rec = [&](int q, Rec &r) {
+      const int *pre_c = prebuf + buf_cur * (AB + 1), *pre_n = prebuf + buf_nxt * (AB + 1);
+      const int tot_c = pre_c[AB];
+      const bool has_n = b_cur + G < nblk;
+      const int tot_n = has_n ? pre_n[AB] : 0;
       r.al = 0;
       r.j = 0;
-      if (r.live) {    // largest al with pre[al] <= p
-        int lo = 0, hi = AB;
-#pragma unroll
-        for (int it = 0; (1 << it) < AB; it++) {
-          const int mid = (lo + hi) >> 1;
-          if (pre[mid] <= p) lo = mid;
-          else
-            hi = mid;
+      r.which = 0;
+      r.s = 0;
+      const int *pre = pre_c;
+      int p = q;
+      if (q >= tot_c) {
+        p = q - tot_c;
+        pre = pre_n;
+        r.which = 1;
+        if (!has_n) {
+          r.state = 0;
+          return;
         }
-        r.al = lo;
-        const size_t s = (size_t) (ii0 + lo) * pb.ncap + (p - pre[lo]);
-        r.ux = pb.fld[s];
-        r.uy = pb.fld[pb.cap + s];
-        r.uz = pb.fld[2 * pb.cap + s];
-        r.d = pb.fld[3 * pb.cap + s];
-#pragma unroll
-        for (int mu = 0; mu < R; mu++) {
-          r.f[mu] = pb.fld[(4 + mu) * pb.cap + s];
-          r.fd[mu] = pb.fld[(4 + R + mu) * pb.cap + s];
+        if (p >= tot_n) {
+          r.state = (b_cur + 2 * G < nblk) ? 2 : 0;
+          return;
         }
-        r.j = pb.pj[s];
       }
+      r.state = 1;
+      int lo = 0, hi = AB;    // largest al with pre[al] <= p
+#pragma unroll
+      for (int it = 0; (1 << it) < AB; it++) {
+        const int mid = (lo + hi) >> 1;
+        if (pre[mid] <= p) lo = mid;
+        else
+          hi = mid;
+      }
+      r.al = lo;
+      const int ii0 = (r.which ? b_cur + G : b_cur) * AB;
+      const size_t s = (size_t) (ii0 + lo) * pb.ncap + (p - pre[lo]);
+      r.s = s;
+      r.ux = pb.fld[s];
+      r.uy = pb.fld[pb.cap + s];
+      r.uz = pb.fld[2 * pb.cap + s];
+      r.d = pb.fld[3 * pb.cap + s];
+#pragma unroll
+      for (int mu = 0; mu < R; mu++) {
+        r.f[mu] = pb.fld[(4 + mu) * pb.cap + s];
+        r.fd[mu] = pb.fld[(4 + R + mu) * pb.cap + s];
+      }
+      r.j = pb.pj[s];
     };
+
+    int base = 0;
     Rec cur;
     load_rec(threadIdx.x, cur);
-    for (int p0 = 0; p0 < total; p0 += 256) {
+    while (true) {
+      const int tot_c = prebuf[buf_cur * (AB + 1) + AB];
+      if (base >= tot_c) {    // the current block is finished: the next becomes current, the one in flight next
+        if (b_cur + G >= nblk) break;
+        __syncthreads();      // everyone is done with the current buffer
+        base -= tot_c;
+        const int t = buf_cur;
+        buf_cur = buf_nxt;
+        buf_nxt = buf_nn;
+        buf_nn = t;
+        b_cur += G;
+        cp_async_wait<0>();
+        __syncthreads();      // the new next block has landed
+        if (b_cur + 2 * G < nblk) prefetch(buf_nn, b_cur + 2 * G);
+        if (cur.state == 1) cur.which = 0;    // (a located record of the old next block)
+        else if (cur.state == 2)
+          load_rec(base + threadIdx.x, cur);
+        continue;
+      }
+      // an iteration serves the pairs [base, base + adv): all 256 lanes unless the two resident blocks end earlier
+      // (tiny blocks) while another block is still to come -- those pairs are taken up after the blocks have moved on
+      const int resident = tot_c - base + ((b_cur + G < nblk) ? prebuf[buf_nxt * (AB + 1) + AB] : 0);
+      const int adv = (b_cur + 2 * G < nblk) ? min(256, resident) : 256;
+      // pair records are requested one iteration ahead of their use
       Rec nxt;
-      load_rec(p0 + 256 + threadIdx.x, nxt);
-      const bool live = cur.live;
-      const int al = cur.al;
+      load_rec(base + adv + threadIdx.x, nxt);
+      const bool live = cur.state == 1 && (int) threadIdx.x < adv;
+      const int al = cur.al, which = cur.which;
       double Fx = 0, Fy = 0, Fz = 0;
-      const int i = a.ilist ? a.ilist[a.first_ii + ii0 + al] : a.first_ii + ii0 + al;
+      const int ii_l = (which ? b_cur + G : b_cur) * AB + al;
+      const int i = a.ilist ? a.ilist[a.first_ii + ii_l] : a.first_ii + ii_l;
       if (live) {
+        const double *g = gbuf + (size_t) (which ? buf_nxt : buf_cur) * GSZ;
         const double ux = cur.ux, uy = cur.uy, uz = cur.uz, d = cur.d;
         const double invd = 1.0 / d;
         double fvi[R], fder[R];
@@ -718,9 +770,8 @@ mtp_forces_v2(SiteArgs a, PairBuf pb, const double *__restrict__ gb, int ld, dou
         double pm[R];
         v2_pair_force<D0, AB, GRADE>(g + al, ux, uy, uz, fvi, fder, Fx, Fy, Fz, pm);
         if (GRADE) {    // P_mu(u_n) replaces f_mu in the pair record (consumed by mtp_cand_radial_kernel)
-          const size_t sp = (size_t) (ii0 + al) * pb.ncap + (p0 + threadIdx.x - pre[al]);
 #pragma unroll
-          for (int mu = 0; mu < R; mu++) pb.fld[(4 + mu) * pb.cap + sp] = pm[mu];
+          for (int mu = 0; mu < R; mu++) pb.fld[(4 + mu) * pb.cap + cur.s] = pm[mu];
         }
         const int j = cur.j;
         atomicAdd(&a.f[3 * (size_t) j], -Fx);
@@ -746,8 +797,8 @@ mtp_forces_v2(SiteArgs a, PairBuf pb, const double *__restrict__ gb, int ld, dou
           }
         }
       }
-      // centre atom: segmented sum over the lanes that share it (lanes are sorted by atom)
-      const int key = live ? al : -1 - lane;
+      // centre atom: segmented sum over the lanes that share it (lanes are sorted by block, then atom)
+      const int key = live ? which * AB + al : -1 - lane;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int ko = __shfl_down_sync(FULL, key, o);
@@ -765,6 +816,7 @@ mtp_forces_v2(SiteArgs a, PairBuf pb, const double *__restrict__ gb, int ld, dou
         atomicAdd(&a.f[3 * (size_t) i + 2], Fz);
       }
       cur = nxt;
+      base += adv;
     }
   }
 
