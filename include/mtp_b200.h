@@ -268,8 +268,9 @@ int mtp_program_check(const char *path, int atoms_per_cta, double *max_rel_err_o
  * $MTP_B200_KCACHE or <library directory>/kcache).  The two entry points below run the generator without a device:
  * mtp_codegen_source returns the emitted CUDA source (tests compile it for the host and run it against the sequential
  * program), mtp_codegen_prebuild compiles it and stores the cubin in the cache (build step).
- * info_out[12] = atoms per CTA, warps, CTAs per SM, shared-memory rows, stages, shared-memory bytes, term steps per
- * atom, row loads per chunk, row stores per chunk, critical-path term steps, rows of mb/gb, structure hash. */
+ * info_out[13] = atoms per CTA, warps, CTAs per SM, shared-memory rows, stages, shared-memory bytes, term steps per
+ * atom, row loads per chunk, row stores per chunk, critical-path term steps, rows of mb/gb, structure hash, rounds
+ * (> 1: a program whose rows exceed a CTA's shared memory is evaluated in rounds of basis functions that reuse them). */
 int mtp_codegen_source(const char *path, int latency_shape, char *buf, long long cap, long long *needed, long long *info_out);
 int mtp_codegen_prebuild(const char *path, int latency_shape, int *compiled_out);
 /* empty when the generated kernel serves this handle, else the reason it does not (the interpreting kernels run) */

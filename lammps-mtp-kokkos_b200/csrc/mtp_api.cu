@@ -1235,8 +1235,8 @@ int mtp_codegen_source(const char *path, int latency_shape, char *buf, long long
     *needed = (long long) src.size() + 1;
     if (buf && cap >= *needed) memcpy(buf, src.c_str(), src.size() + 1);
     if (info_out) {
-      const long long v[12] = {ch.prm.na, ch.prm.warps, ch.min_blocks, info.rows, info.stages, (long long) info.smem_bytes, info.terms,
-                               info.loads, info.stores, info.crit_terms, nslots, (long long) info.hash};
+      const long long v[13] = {ch.prm.na, ch.prm.warps, ch.min_blocks, info.rows, info.stages, (long long) info.smem_bytes, info.terms,
+                               info.loads, info.stores, info.crit_terms, nslots, (long long) info.hash, info.rounds};
       memcpy(info_out, v, sizeof(v));
     }
   });

@@ -33,9 +33,13 @@ struct Analysis {
   std::vector<int> fstage, rstage;          // stage of the forward / reverse task of node n, or -1
   int m_rows = 0, g_rows = 0, nstages = 0;
   long long terms = 0;
+  bool first_round = true;                  // every basic moment gets its adjoint written (later rounds: only the touched)
 };
 
-bool analyse(const Potential &p, Analysis &an, std::string &why)
+// active (optional, [A]): the basis functions this round evaluates; the program is then restricted to their ancestors,
+// and the other basis functions that are ancestors themselves count as plain intermediates (adjoint seed 0)
+bool analyse(const Potential &p, Analysis &an, std::string &why, const std::vector<char> *active = nullptr,
+             bool first_round = true)
 {
   an.K = p.alpha_index_basic_count;
   an.M = p.alpha_moment_count;
@@ -47,19 +51,31 @@ bool analyse(const Potential &p, Analysis &an, std::string &why)
   an.scalar.assign(M, -1);
   an.operand.assign(M, 0);
   an.target.assign(M, 0);
+  an.first_round = first_round;
   const int *tm = p.alpha_index_times.data();
-  for (int e = 0; e < T; e++) {
-    const int a0 = tm[4 * e], a1 = tm[4 * e + 1], c = tm[4 * e + 2], t = tm[4 * e + 3];
-    if (t < K) {
+  for (int e = 0; e < T; e++)
+    if (tm[4 * e + 3] < K) {
       why = "a basic moment is the target of a product";
       return false;
     }
+  // nodes this round needs: ancestors of its basis functions (the file is topologically ordered: one backward sweep)
+  std::vector<char> needed(M, active ? 0 : 1);
+  if (active) {
+    for (int s = 0; s < an.A; s++)
+      if ((*active)[s]) needed[p.alpha_moment_mapping[s]] = 1;
+    for (int e = T - 1; e >= 0; e--)
+      if (needed[tm[4 * e + 3]]) needed[tm[4 * e]] = needed[tm[4 * e + 1]] = 1;
+  }
+  for (int e = 0; e < T; e++) {
+    const int a0 = tm[4 * e], a1 = tm[4 * e + 1], c = tm[4 * e + 2], t = tm[4 * e + 3];
+    if (!needed[t]) continue;
     an.in[t].push_back({a0, a1, c});
     an.operand[a0] = an.operand[a1] = 1;
     an.target[t] = 1;
   }
   for (int s = 0; s < an.A; s++) {
     const int n = p.alpha_moment_mapping[s];
+    if (active && !(*active)[s]) continue;
     if (an.scalar[n] >= 0) {
       why = "alpha_moment_mapping lists a moment twice";
       return false;
@@ -339,7 +355,8 @@ void emit_reverse_block(const Analysis &an, const std::vector<int> &nodes, const
   for (size_t i = 0; i < nodes.size(); i++) {
     const int n = nodes[i];
     if (!have[i]) E.line("  " + acc[i] + " = ZERO;\n");
-    if (n < an.K) E.line("  GBST(" + std::to_string(slot_of_k ? (int) slot_of_k[n] : n) + ", " + acc[i] + ");\n");
+    if (n < an.K)
+      E.line(std::string(an.first_round ? "  GBST(" : "  GBACC(") + std::to_string(slot_of_k ? (int) slot_of_k[n] : n) + ", " + acc[i] + ");\n");
     else
       E.line("  ST(" + std::to_string(an.grow[n]) + ", " + acc[i] + ");\n");
     if (!E.record) stores++;
@@ -356,7 +373,7 @@ unsigned long long fnv(unsigned long long h, const void *data, size_t n)
   return h;
 }
 
-const char *kGeneratorVersion = "p4-r2-04";
+const char *kGeneratorVersion = "p4-r2-07";
 
 // ---- fixed text: device prelude and kernel skeleton ------------------------------------------------------
 const char *kDevicePrelude = R"P4(
@@ -422,6 +439,7 @@ template <int OFF> P4_FN void p4_sts(unsigned a, double v) { asm volatile("st.sh
 #define SPLAT(u) (u)
 #define ZERO 0.0
 #define GBST(slot, v) do { if (flags & 1) __stcg(gb + (long long) (slot) * ld, (v)); } while (0)
+#define GBACC(slot, v) do { if (flags & 1) { double *q_ = gb + (long long) (slot) * ld; __stcg(q_, __ldcg(q_) + (v)); } } while (0)
 #define ESC(s, v) do { e = fma(LIN(s), (v), e); if ((flags & 5) == 5) cand[s] = (v); } while (0)
 #else
 template <int OFF> P4_FN T_ p4_lds2(unsigned a)
@@ -453,6 +471,8 @@ P4_FN T_ p4_splat(double u) { T_ r; r.x = u; r.y = u; return r; }
 #define ZERO p4_splat(0.0)
 #define GBST(slot, v) do { const T_ v_ = (v); double *q_ = gb + (long long) (slot) * ld; \
     if (flags & 2) __stcg(reinterpret_cast<double2 *>(q_), make_double2(v_.x, v_.y)); else if (flags & 1) __stcg(q_, v_.x); } while (0)
+#define GBACC(slot, v) do { const T_ v_ = (v); double *q_ = gb + (long long) (slot) * ld; \\
+    if (flags & 1) __stcg(q_, __ldcg(q_) + v_.x); if (flags & 2) __stcg(q_ + 1, __ldcg(q_ + 1) + v_.y); } while (0)
 #define ESC(s, v) do { const T_ v_ = (v); e = p4_fmau(LIN(s), v_, e); \
     if (flags & 4) { if (flags & 1) cand[s] = v_.x; if (flags & 2) cand[cand_ld + (s)] = v_.y; } } while (0)
 #endif
@@ -548,13 +568,14 @@ struct Plan {
   std::vector<std::vector<std::vector<Task>>> work;    // [stage][warp] -> tasks in order
 };
 
-bool make_plan(const Potential &p, const P4Params &prm, Plan &pl, std::string &why)
+bool make_plan(const Potential &p, const P4Params &prm, Plan &pl, std::string &why, const std::vector<char> *active = nullptr,
+               bool first_round = true)
 {
   if (!(prm.na == 8 || prm.na == 16 || prm.na == 32 || prm.na == 64) || prm.warps < 1 || prm.warps > 32 || prm.warps * 32 < prm.na) {
     why = "bad generator parameters";
     return false;
   }
-  if (!analyse(p, pl.an, why)) return false;
+  if (!analyse(p, pl.an, why, active, first_round)) return false;
   const Analysis &an = pl.an;
   pl.work.assign(an.nstages, std::vector<std::vector<Task>>(prm.warps));
   for (int st = 0; st < an.nstages; st++) {
@@ -566,7 +587,7 @@ bool make_plan(const Potential &p, const P4Params &prm, Plan &pl, std::string &w
       if (an.target[n] && an.fstage[n] == st && (an.operand[n] || an.scalar[n] >= 0))
         tasks.push_back({0, n, (int) an.in[n].size() + 2});
     for (int n = 0; n < an.M; n++)
-      if ((n < an.K || an.operand[n]) && an.rstage[n] == st) {
+      if ((n < an.K ? (an.first_round || !an.out[n].empty() || an.scalar[n] >= 0) : an.operand[n]) && an.rstage[n] == st) {
         int c = 2;
         for (const RevPair &rp : an.out[n]) c += (int) rp.terms.size() + 1;
         tasks.push_back({1, n, c});
@@ -584,40 +605,160 @@ bool make_plan(const Potential &p, const P4Params &prm, Plan &pl, std::string &w
   return true;
 }
 
-size_t smem_of(const Analysis &an, const P4Params &prm)
+size_t smem_of_rows(int rows, int A, const P4Params &prm)
 {
-  return ((size_t) (an.m_rows + an.g_rows) * prm.na + (size_t) ((an.A + 1) & ~1) + (size_t) prm.warps * prm.na) * 8;
+  return ((size_t) rows * prm.na + (size_t) ((A + 1) & ~1) + (size_t) prm.warps * prm.na) * 8;
+}
+
+// Rounds.  When the rows of the whole program (moments of every operand node + adjoints of the non-basic ones) do not
+// fit the shared memory of a CTA, the basis functions are dealt to several ROUNDS: a round evaluates the ancestors of
+// its basis functions only -- forward, energy, reverse -- in rows that the next round reuses, and adds its share of the
+// basic-moment adjoints to gb (the reverse pass is linear in the seeds, so the shares add up).  Intermediates that two
+// rounds need are computed twice; the basis functions are taken in file order, which keeps related contractions together.
+bool make_rounds(const Potential &p, const P4Params &prm, std::vector<std::vector<char>> &rounds, std::string &why)
+{
+  Analysis all;
+  if (!analyse(p, all, why)) return false;
+  rounds.clear();
+  if (prm.smem_budget == 0 || smem_of_rows(all.m_rows + all.g_rows, all.A, prm) <= prm.smem_budget) return true;    // one round
+  const int K = all.K, M = all.M, T = all.T, A = all.A;
+  const long long fixed = (long long) smem_of_rows(0, A, prm);
+  const long long row_budget = ((long long) prm.smem_budget - fixed) / ((long long) prm.na * 8);
+  const int *tm = p.alpha_index_times.data();
+  // proper non-basic ancestors of every basis function (bit sets): exactly the nodes that need a moment row and an
+  // adjoint row in the round that evaluates it
+  const int W64 = (M + 63) / 64;
+  std::vector<std::vector<int>> in_ops(M);
+  for (int e = 0; e < T; e++) {
+    in_ops[tm[4 * e + 3]].push_back(tm[4 * e]);
+    in_ops[tm[4 * e + 3]].push_back(tm[4 * e + 1]);
+  }
+  std::vector<std::vector<unsigned long long>> anc(M);    // ancestors of node n, n itself excluded (memoised, file order)
+  std::vector<int> order;
+  {
+    std::vector<char> seen(M, 0);
+    for (int e = 0; e < T; e++)
+      if (!seen[tm[4 * e + 3]]) {
+        seen[tm[4 * e + 3]] = 1;
+        order.push_back(tm[4 * e + 3]);
+      }
+  }
+  for (int n = 0; n < M; n++) anc[n].assign(W64, 0ULL);
+  for (int t : order)    // a target's factors were completed before its first product (topological file order)
+    for (int o : in_ops[t]) {
+      if (o >= K) anc[t][o >> 6] |= 1ULL << (o & 63);
+      for (int w = 0; w < W64; w++) anc[t][w] |= anc[o][w];
+    }
+  auto popcount = [&](const std::vector<unsigned long long> &v) {
+    long long c = 0;
+    for (unsigned long long x : v) c += __builtin_popcountll(x);
+    return c;
+  };
+  std::vector<char> assigned(A, 0);
+  int left = A;
+  while (left > 0) {
+    // seed: the unassigned basis function with the most ancestors; then always the one that adds the fewest rows
+    std::vector<unsigned long long> cur(W64, 0ULL);
+    std::vector<char> act(A, 0);
+    int in_cur = 0;
+    while (true) {
+      int best = -1;
+      long long best_add = 0, best_size = -1;
+      for (int sc = 0; sc < A; sc++) {
+        if (assigned[sc]) continue;
+        const std::vector<unsigned long long> &as = anc[p.alpha_moment_mapping[sc]];
+        long long add = 0, size = 0;
+        for (int w = 0; w < W64; w++) {
+          add += __builtin_popcountll(as[w] & ~cur[w]);
+          size += __builtin_popcountll(as[w]);
+        }
+        const bool better = in_cur == 0 ? size > best_size : (best < 0 || add < best_add || (add == best_add && size > best_size));
+        if (better) {
+          best = sc;
+          best_add = add;
+          best_size = size;
+        }
+      }
+      if (best < 0) break;
+      if (K + 2 * (popcount(cur) + best_add) > row_budget) {
+        if (in_cur == 0) {
+          why = "one basis function alone needs more shared-memory rows than a CTA has";
+          return false;
+        }
+        break;
+      }
+      const std::vector<unsigned long long> &as = anc[p.alpha_moment_mapping[best]];
+      for (int w = 0; w < W64; w++) cur[w] |= as[w];
+      act[best] = 1;
+      assigned[best] = 1;
+      in_cur++;
+      left--;
+    }
+    rounds.push_back(act);
+  }
+  if ((int) rounds.size() > 64) {
+    why = "the program would need more than 64 rounds";
+    return false;
+  }
+  return true;
 }
 
 }    // namespace
 
 size_t p4_smem_bytes(const Potential &p, const P4Params &prm)
 {
-  Analysis an;
+  std::vector<std::vector<char>> rounds;
   std::string why;
-  if (!analyse(p, an, why)) return 0;
-  return smem_of(an, prm);
+  if (!make_rounds(p, prm, rounds, why)) return 0;
+  int rows = 0, A = 0;
+  if (rounds.empty()) {
+    Analysis an;
+    if (!analyse(p, an, why)) return 0;
+    rows = an.m_rows + an.g_rows;
+    A = an.A;
+  } else
+    for (size_t r = 0; r < rounds.size(); r++) {
+      Analysis an;
+      if (!analyse(p, an, why, &rounds[r], r == 0)) return 0;
+      rows = std::max(rows, an.m_rows + an.g_rows);
+      A = an.A;
+    }
+  return smem_of_rows(rows, A, prm);
 }
 
 bool p4_generate(const Potential &p, const P4Params &prm, const short *slot_of_k, int nslots, std::string &src, P4Info &info,
                  std::string &why)
 {
-  Plan pl;
-  if (!make_plan(p, prm, pl, why)) return false;
-  const Analysis &an = pl.an;
-  const int K = an.K, rows = an.m_rows + an.g_rows;
+  std::vector<std::vector<char>> rounds;
+  if (!make_rounds(p, prm, rounds, why)) return false;
+  const int nrounds = std::max<int>(1, (int) rounds.size());
+  std::vector<Plan> plans((size_t) nrounds);
+  for (int r = 0; r < nrounds; r++)
+    if (!make_plan(p, prm, plans[r], why, rounds.empty() ? nullptr : &rounds[r], r == 0)) return false;
+  const Analysis &an0 = plans[0].an;
+  const int K = an0.K;
+  int rows = 0, nstages = 0, m_rows = 0;
+  long long terms = 0;
+  for (const Plan &pl : plans) {
+    rows = std::max(rows, pl.an.m_rows + pl.an.g_rows);
+    m_rows = std::max(m_rows, pl.an.m_rows);
+    nstages += pl.an.nstages;
+    terms += pl.an.terms;
+  }
   info = P4Info();
   info.rows = rows;
-  info.m_rows = an.m_rows;
-  info.g_rows = an.g_rows;
-  info.stages = an.nstages;
-  info.smem_bytes = smem_of(an, prm);
-  info.terms = an.terms;
+  info.m_rows = m_rows;
+  info.g_rows = rows - m_rows;
+  info.stages = nstages;
+  info.rounds = nrounds;
+  info.smem_bytes = smem_of_rows(rows, an0.A, prm);
+  info.terms = terms;
   info.threads = prm.warps * 32;
 
   unsigned long long h = 1469598103934665603ULL;
   h = fnv(h, kGeneratorVersion, strlen(kGeneratorVersion));
-  const int hdr[10] = {K, an.M, an.T, an.A, prm.na, prm.warps, prm.cache, prm.acc_max, nslots, prm.fn_cost};
+  const long long hdr[11] = {K, an0.M, an0.T, an0.A, prm.na, prm.warps, prm.cache, prm.acc_max, nslots, prm.fn_cost,
+                             (long long) prm.smem_budget};
   h = fnv(h, hdr, sizeof(hdr));
   h = fnv(h, p.alpha_index_times.data(), p.alpha_index_times.size() * sizeof(int));
   h = fnv(h, p.alpha_moment_mapping.data(), p.alpha_moment_mapping.size() * sizeof(int));
@@ -626,13 +767,13 @@ bool p4_generate(const Potential &p, const P4Params &prm, const short *slot_of_k
 
   const int apl = prm.na == 64 ? 2 : 1;
   src.clear();
-  src.reserve((size_t) 64 * 1024 + (size_t) an.terms * 96);
-  char buf[512];
+  src.reserve((size_t) 64 * 1024 + (size_t) terms * 96);
+  char buf[640];
   snprintf(buf, sizeof(buf),
-           "// generated by mtp_codegen (%s): contraction program of one potential structure, K=%d M=%d T=%d A=%d\n"
+           "// generated by mtp_codegen (%s): contraction program of one potential structure, K=%d M=%d T=%d A=%d, %d round(s)\n"
            "#define P4_NA %d\n#define P4_APL %d\n#define P4_W %d\n#define P4_ROWS %d\n#define P4_MROWS %d\n#define P4_K %d\n"
            "#define P4_A %d\n#define P4_M %d\n#define P4_NSTAGE %d\n#define P4_NSLOTS %d\n#ifndef P4_MINB\n#define P4_MINB 1\n#endif\n",
-           kGeneratorVersion, K, an.M, an.T, an.A, prm.na, apl, prm.warps, rows, an.m_rows, K, an.A, an.M, an.nstages, nslots);
+           kGeneratorVersion, K, an0.M, an0.T, an0.A, nrounds, prm.na, apl, prm.warps, rows, m_rows, K, an0.A, an0.M, nstages, nslots);
   src += buf;
   src += kDevicePrelude;
   // tables
@@ -654,76 +795,80 @@ bool p4_generate(const Potential &p, const P4Params &prm, const short *slot_of_k
   src += "#define P4_NZERO " + std::to_string(zero.size()) + "\nP4_TABLE short p4_zero_slot[P4_NZERO + 1] = {";
   for (int s : zero) src += std::to_string(s) + ",";
   src += "0};\n";
-  // m-row of every node (host harness: lets the checker read back every stored moment); -1 = not stored
+  // m-row of every node in the LAST round (host harness: lets the checker read back the stored moments); -1 = not stored
   src += "#ifdef P4_HOST\nstatic const int p4_mrow[P4_M] = {";
-  for (int n = 0; n < an.M; n++) src += std::to_string(an.mrow[n]) + (n + 1 < an.M ? "," : "");
+  for (int n = 0; n < an0.M; n++) src += std::to_string(plans.back().an.mrow[n]) + (n + 1 < an0.M ? "," : "");
   src += "};\n#endif\n";
 
-  // stage functions
-  std::vector<std::pair<int, int>> present;
-  for (int st = 0; st < an.nstages; st++) {
-    long long crit = 0;
-    for (int w = 0; w < prm.warps; w++) {
-      const std::vector<Task> &tasks = pl.work[st][w];
-      if (tasks.empty()) continue;
-      long long wt = 0;
-      for (const Task &t : tasks) wt += t.cost;
-      crit = std::max(crit, wt);
-      // a warp's share of a stage is emitted as a sequence of separately compiled (noinline) functions of bounded
-      // size: ptxas allocates registers per function, and its compile time is superlinear in the function length
-      size_t i = 0;
-      int part = 0;
-      while (i < tasks.size()) {
-        size_t j = i;
-        long long c = 0;
-        while (j < tasks.size() && (j == i || c + tasks[j].cost <= prm.fn_cost)) c += tasks[j++].cost;
-        Emitter E;
-        E.capacity = std::max(4, prm.cache);
-        E.uniform_base = rows;
-        std::string body;
-        E.out = &body;
-        for (int pass = 0; pass < 2; pass++) {
-          int ntmp = 0;
-          long long st_count = 0;
-          if (pass == 1) E.begin_emit();
-          size_t q = i;
-          while (q < j) {
-            const Task &t = tasks[q];
-            if (t.kind == 2) {
-              const std::string m = E.use(an.mrow[t.node]);
-              E.line("  ESC(" + std::to_string(an.scalar[t.node]) + ", " + m + ");\n");
-              q++;
-            } else if (t.kind == 0) {
-              emit_forward(an, t.node, E, ntmp, st_count);
-              q++;
-            } else {
-              std::vector<int> blk;
-              while (q < j && tasks[q].kind == 1 && (int) blk.size() < std::max(1, prm.acc_max)) blk.push_back(tasks[q++].node);
-              emit_reverse_block(an, blk, slot_of_k, E, ntmp, st_count);
+  // stage functions, round after round; the kernel walks the stages of all rounds in order
+  std::vector<std::pair<int, std::string>> present;    // (global stage * W + warp, function name)
+  int stage0 = 0;
+  for (int r = 0; r < nrounds; r++) {
+    const Plan &pl = plans[r];
+    const Analysis &an = pl.an;
+    const int rrows = an.m_rows + an.g_rows;
+    for (int st = 0; st < an.nstages; st++) {
+      long long crit = 0;
+      for (int w = 0; w < prm.warps; w++) {
+        const std::vector<Task> &tasks = pl.work[st][w];
+        if (tasks.empty()) continue;
+        long long wt = 0;
+        for (const Task &t : tasks) wt += t.cost;
+        crit = std::max(crit, wt);
+        // a warp's share of a stage is emitted as a sequence of separately compiled (noinline) functions of bounded
+        // size: ptxas allocates registers per function, and its compile time is superlinear in the function length
+        size_t i = 0;
+        int part = 0;
+        while (i < tasks.size()) {
+          size_t j = i;
+          long long c = 0;
+          while (j < tasks.size() && (j == i || c + tasks[j].cost <= prm.fn_cost)) c += tasks[j++].cost;
+          Emitter E;
+          E.capacity = std::max(4, prm.cache);
+          E.uniform_base = rrows;
+          std::string body;
+          E.out = &body;
+          for (int pass = 0; pass < 2; pass++) {
+            int ntmp = 0;
+            long long st_count = 0;
+            if (pass == 1) E.begin_emit();
+            size_t q = i;
+            while (q < j) {
+              const Task &t = tasks[q];
+              if (t.kind == 2) {
+                const std::string m = E.use(an.mrow[t.node]);
+                E.line("  ESC(" + std::to_string(an.scalar[t.node]) + ", " + m + ");\n");
+                q++;
+              } else if (t.kind == 0) {
+                emit_forward(an, t.node, E, ntmp, st_count);
+                q++;
+              } else {
+                std::vector<int> blk;
+                while (q < j && tasks[q].kind == 1 && (int) blk.size() < std::max(1, prm.acc_max)) blk.push_back(tasks[q++].node);
+                emit_reverse_block(an, blk, slot_of_k, E, ntmp, st_count);
+              }
             }
+            if (pass == 1) info.stores += st_count;
           }
-          if (pass == 1) info.stores += st_count;
+          info.loads += E.loads;
+          snprintf(buf, sizeof(buf), "p4_r%d_s%d_w%d_%d", r, st, w, part);
+          src += std::string("P4_STAGE_FN P4_RET ") + buf + "(P4_PARAMS)\n{\n";
+          src += body;
+          src += "  P4_RETURN;\n}\n";
+          present.push_back({(stage0 + st) * prm.warps + w, buf});
+          part++;
+          i = j;
         }
-        info.loads += E.loads;
-        snprintf(buf, sizeof(buf), "P4_STAGE_FN P4_RET p4_s%d_w%d_%d(P4_PARAMS)\n{\n", st, w, part);
-        src += buf;
-        src += body;
-        src += "  P4_RETURN;\n}\n";
-        present.push_back({st * prm.warps + w, part});
-        part++;
-        i = j;
       }
+      info.crit_terms += crit;
     }
-    info.crit_terms += crit;
+    stage0 += an.nstages;
   }
   src += "P4_FN void p4_run_stage(int stage, int warp, P4Ctx &x)\n{\n  switch (stage * P4_W + warp) {\n";
   for (size_t q = 0; q < present.size();) {
     const int key = present[q].first;
     src += "    case " + std::to_string(key) + ":\n";
-    for (; q < present.size() && present[q].first == key; q++) {
-      snprintf(buf, sizeof(buf), "      P4_CALL(p4_s%d_w%d_%d);\n", key / prm.warps, key % prm.warps, present[q].second);
-      src += buf;
-    }
+    for (; q < present.size() && present[q].first == key; q++) src += "      P4_CALL(" + present[q].second + ");\n";
     src += "      break;\n";
   }
   src += "    default: break;\n  }\n}\n";

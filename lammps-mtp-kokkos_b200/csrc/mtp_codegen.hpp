@@ -32,12 +32,14 @@ struct P4Params {
   int cache = 56;       // operand values the register cache of a warp may hold
   int acc_max = 16;     // adjoints a warp accumulates at once in the reverse pass
   int fn_cost = 4000;   // term steps per emitted function (bounds ptxas time and register pressure)
+  size_t smem_budget = 0;    // > 0: dynamic shared memory a CTA may use; a program that needs more is cut into rounds
 };
 
 struct P4Info {
   int rows = 0;             // shared-memory rows (m rows of operand nodes + g rows of non-basic operand nodes)
   int m_rows = 0, g_rows = 0;
   int stages = 0;
+  int rounds = 1;           // > 1: the basis functions were dealt to several rounds that reuse the shared-memory rows
   size_t smem_bytes = 0;    // dynamic shared memory of the kernel
   long long terms = 0;      // multiply-add term steps per atom (forward T + reverse 2T, squares merged)
   long long loads = 0;      // shared-memory row loads per chunk summed over warps (after the register cache)

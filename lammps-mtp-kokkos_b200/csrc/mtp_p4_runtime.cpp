@@ -19,12 +19,15 @@ P4Choice p4_choose(const Potential &p, size_t smem_optin, bool latency_shape)
   P4Choice ch;
   if (const char *e = getenv(latency_shape ? "MTP_B200_P4_SMALL" : "MTP_B200_P4")) {
     int na = 0, w = 0, c = 0, acc = 0, mb = 0;
-    if (sscanf(e, "%d,%d,%d,%d,%d", &na, &w, &c, &acc, &mb) == 5) {
+    long budget = 0;
+    const int nf = sscanf(e, "%d,%d,%d,%d,%d,%ld", &na, &w, &c, &acc, &mb, &budget);
+    if (nf >= 5) {
       ch.prm.na = na;
       ch.prm.warps = w;
       ch.prm.cache = c;
       ch.prm.acc_max = acc;
       ch.min_blocks = mb;
+      ch.prm.smem_budget = nf >= 6 ? (size_t) budget : smem_optin;
       const size_t b = p4_smem_bytes(p, ch.prm);
       ch.ok = b > 0 && b <= smem_optin;
       return ch;
@@ -34,9 +37,8 @@ P4Choice p4_choose(const Potential &p, size_t smem_optin, bool latency_shape)
   const size_t two_ctas = (smem_optin + 1024) / 2 - 1024;
   // The emitted code is straight-line and executed once per chunk, so it streams through the instruction cache:
   // measured on B200 it issues ~0.5 instructions/clk/SM whatever the warp count (instruction-fetch bound, ~8 B/clk/SM).
-  // What matters is therefore atoms per instruction: the throughput shape is only worth it with a full warp of atoms
-  // per row (32 per CTA); potentials whose tables do not fit that (levels >= 20) keep the interpreting kernels, whose
-  // loop stays in the instruction cache.  The latency shape (mtp/small/kk: few atoms, every SM must get a chunk) takes
+  // What matters is therefore atoms per instruction: the throughput shape always takes a full warp of atoms per row
+  // (32 per CTA).  The latency shape (mtp/small/kk: few atoms, every SM must get a chunk) takes
   // 8 atoms per CTA and 8 warps: the chunk's critical path is what counts there.
   // Latency shape: a chunk streams the whole program through one SM whatever its width, so the widest chunk that fits
   // (16 atoms, else 8) halves the number of chunks per SM; 8 warps shorten the chunk's critical path.
@@ -45,9 +47,9 @@ P4Choice p4_choose(const Potential &p, size_t smem_optin, bool latency_shape)
     P4Params prm;
     prm.na = nas[t];
     prm.warps = latency_shape ? 8 : 4;
-    size_t b = p4_smem_bytes(p, prm);
-    if (b == 0) return ch;    // structure not supported
-    if (b <= two_ctas) {      // two CTAs per SM: their instruction streams overlap
+    size_t b = p4_smem_bytes(p, prm);    // smem_budget = 0: the whole program in one round
+    if (b == 0) return ch;               // structure not supported
+    if (b <= two_ctas) {                 // two CTAs per SM: their instruction streams overlap
       ch.prm = prm;
       ch.min_blocks = 2;
       ch.ok = true;
@@ -61,6 +63,18 @@ P4Choice p4_choose(const Potential &p, size_t smem_optin, bool latency_shape)
       ch.ok = true;
       return ch;
     }
+  }
+  // Too many rows for one CTA (levels >= 20): the basis functions are dealt to rounds that reuse the rows (mtp_codegen.cpp,
+  // make_rounds); a full warp of atoms per row for the throughput shape, 16 for the latency shape.
+  P4Params prm;
+  prm.na = latency_shape ? 16 : 32;
+  prm.warps = 8;
+  prm.smem_budget = smem_optin;
+  const size_t b = p4_smem_bytes(p, prm);
+  if (b > 0 && b <= smem_optin) {
+    ch.prm = prm;
+    ch.min_blocks = 1;
+    ch.ok = true;
   }
   return ch;
 }
@@ -82,7 +96,7 @@ namespace {
 std::string cache_file(const P4Info &info, const P4Choice &ch)
 {
   char name[96];
-  snprintf(name, sizeof(name), "/p4_%016llx_b%d.cubin", info.hash, ch.min_blocks);
+  snprintf(name, sizeof(name), "/p4_%016llx_b%d%s.cubin", info.hash, ch.min_blocks, getenv("MTP_B200_P4_LINEINFO") ? "_li" : "");
   return p4_cache_dir() + name;
 }
 
@@ -117,8 +131,9 @@ std::vector<char> nvrtc_compile(const std::string &src, int min_blocks)
   if (nvrtcCreateProgram(&prog, src.c_str(), "mtp_program_p4.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
     throw std::runtime_error("nvrtcCreateProgram failed");
   const std::string minb = "-DP4_MINB=" + std::to_string(min_blocks);
-  const char *opts[] = {"-arch=sm_100a", "-std=c++17", "-lineinfo", minb.c_str()};
-  const nvrtcResult rc = nvrtcCompileProgram(prog, 4, opts);
+  // (-lineinfo triples the size of these cubins; MTP_B200_P4_LINEINFO=1 adds it for an ncu source view)
+  const char *opts[] = {"-arch=sm_100a", "-std=c++17", minb.c_str(), "-lineinfo"};
+  const nvrtcResult rc = nvrtcCompileProgram(prog, getenv("MTP_B200_P4_LINEINFO") ? 4 : 3, opts);
   if (rc != NVRTC_SUCCESS) {
     size_t n = 0;
     nvrtcGetProgramLogSize(prog, &n);

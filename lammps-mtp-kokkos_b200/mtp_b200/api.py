@@ -361,14 +361,14 @@ def program_check(path: str, atoms_per_cta: int = 32) -> float:
 
 
 CODEGEN_INFO = ("atoms_per_cta", "warps", "ctas_per_sm", "rows", "stages", "smem_bytes", "terms", "loads", "stores",
-                "critical_terms", "nslots", "hash")
+                "critical_terms", "nslots", "hash", "rounds")
 
 
 def codegen_source(path: str, latency_shape: bool = False):
     """Source of the generated contraction-program kernel for a potential file + generator statistics (no device)."""
     lib = load_library()
     need = C.c_longlong(0)
-    info = (C.c_longlong * 12)()
+    info = (C.c_longlong * 13)()
     _check(lib, lib.mtp_codegen_source(os.fsencode(path), int(latency_shape), None, 0, C.byref(need), info))
     buf = C.create_string_buffer(need.value)
     _check(lib, lib.mtp_codegen_source(os.fsencode(path), int(latency_shape), buf, need.value, C.byref(need), info))

@@ -60,6 +60,7 @@ struct P4Ctx {
 #define SPLAT(u) t2((u), (u))
 #define ZERO t2(0.0, 0.0)
 #define GBST(slot, v) do { const T_ v_ = (v); x.gb[(long long) (slot) * x.ld] = v_.x; x.gb[(long long) (slot) * x.ld + 1] = v_.y; } while (0)
+#define GBACC(slot, v) do { const T_ v_ = (v); x.gb[(long long) (slot) * x.ld] += v_.x; x.gb[(long long) (slot) * x.ld + 1] += v_.y; } while (0)
 #define ESC(s, v) do { const T_ v_ = (v); x.e = FMAK(x.lin[s], v_, x.e); \
     if (x.grade) { x.cand[s] = v_.x; x.cand[x.cand_ld + (s)] = v_.y; } } while (0)
 #else
@@ -75,6 +76,7 @@ struct P4Ctx {
 #define SPLAT(u) (u)
 #define ZERO 0.0
 #define GBST(slot, v) (x.gb[(long long) (slot) * x.ld] = (v))
+#define GBACC(slot, v) (x.gb[(long long) (slot) * x.ld] += (v))
 #define ESC(s, v) do { x.e = std::fma(x.lin[s], (v), x.e); if (x.grade) x.cand[s] = (v); } while (0)
 #endif
 #define LIN(s) (x.lin[s])

@@ -49,7 +49,7 @@ def _host_check(tmp_path, pot_path, pot, latency, env=None):
 
 
 @pytest.mark.parametrize("level,species,latency", [(8, 1, False), (10, 2, False), (12, 3, False), (16, 2, False),
-                                                   (20, 1, True)])
+                                                   (20, 1, True), (22, 1, True)])
 def test_generated_program_matches_the_sequential_program(tmp_path, level, species, latency):
     path, pot = util.write_potential(tmp_path, level, species)
     info = _host_check(tmp_path, path, pot, latency)
@@ -58,12 +58,23 @@ def test_generated_program_matches_the_sequential_program(tmp_path, level, speci
     assert info["loads"] < info["terms"] or level <= 10            # the register cache removes most operand loads
 
 
-def test_throughput_shape_is_refused_when_a_warp_of_atoms_does_not_fit(tmp_path):
-    """Levels >= 20 keep the interpreting kernels for the throughput shape (see p4_choose): the generator says so."""
-    path, _ = util.write_potential(tmp_path, 20, 1)
-    with pytest.raises(api.MTPError, match="outside the generator's range"):
-        api.codegen_source(path, False)
+def test_program_too_large_for_one_cta_is_evaluated_in_rounds(tmp_path):
+    """Level 20: the rows of the whole program exceed a CTA's shared memory at 32 atoms per row, so the basis functions
+    are dealt to rounds that reuse the rows; the emulation checks the sum of the rounds against the sequential program."""
+    path, pot = util.write_potential(tmp_path, 20, 1)
+    info = _host_check(tmp_path, path, pot, False)
+    assert info["atoms_per_cta"] == 32 and info["rounds"] > 1 and info["smem_bytes"] <= 232448
+    tb = mtp_basis.build_mtp_tables(20)
+    assert info["terms"] <= 1.2 * 3 * len(tb.alpha_index_times)      # shared intermediates recomputed: < 20 % extra work
     assert api.codegen_source(path, True)[1]["atoms_per_cta"] == 16
+
+
+def test_rounds_on_a_small_program(tmp_path):
+    path, pot = util.write_potential(tmp_path, 12, 2)
+    info = _host_check(tmp_path, path, pot, False, env={"MTP_B200_P4": "32,4,24,8,2,18000"})
+    assert info["rounds"] >= 3
+    info = _host_check(tmp_path, path, pot, False, env={"MTP_B200_P4": "64,8,24,8,1,36000"})
+    assert info["rounds"] >= 3 and info["atoms_per_cta"] == 64
 
 
 def test_latency_shape_and_two_atoms_per_lane(tmp_path):
