@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -592,12 +593,39 @@ bool make_plan(const Potential &p, const P4Params &prm, Plan &pl, std::string &w
         for (const RevPair &rp : an.out[n]) c += (int) rp.terms.size() + 1;
         tasks.push_back({1, n, c});
       }
-    long long total = 0;
-    for (const Task &t : tasks) total += t.cost;
+    // contiguous runs of the task order (locality: the components of one contraction stay in one warp) with the
+    // smallest possible maximum load: binary search on the load, greedy feasibility check
+    long long total = 0, biggest = 0;
+    for (const Task &t : tasks) {
+      total += t.cost;
+      biggest = std::max<long long>(biggest, t.cost);
+    }
+    auto parts_needed = [&](long long cap) {
+      int parts = 1;
+      long long run = 0;
+      for (const Task &t : tasks) {
+        if (run + t.cost > cap && run > 0) {
+          parts++;
+          run = 0;
+        }
+        run += t.cost;
+      }
+      return parts;
+    };
+    long long lo = std::max(biggest, (total + prm.warps - 1) / prm.warps), hi = std::max(total, 1LL);
+    while (lo < hi) {
+      const long long mid = (lo + hi) / 2;
+      if (parts_needed(mid) <= prm.warps) hi = mid;
+      else
+        lo = mid + 1;
+    }
+    int w = 0;
     long long run = 0;
-    for (const Task &t : tasks) {    // contiguous runs of (almost) equal cost
-      int w = total > 0 ? (int) ((run + t.cost / 2) * prm.warps / total) : 0;
-      w = std::min(w, prm.warps - 1);
+    for (const Task &t : tasks) {
+      if (run + t.cost > lo && run > 0 && w + 1 < prm.warps) {
+        w++;
+        run = 0;
+      }
       pl.work[st][w].push_back(t);
       run += t.cost;
     }
@@ -861,6 +889,15 @@ bool p4_generate(const Potential &p, const P4Params &prm, const short *slot_of_k
         }
       }
       info.crit_terms += crit;
+      if (getenv("MTP_B200_P4_VERBOSE")) {
+        long long tot = 0, big = 0;
+        for (int w = 0; w < prm.warps; w++)
+          for (const Task &t : pl.work[st][w]) {
+            tot += t.cost;
+            big = std::max<long long>(big, t.cost);
+          }
+        fprintf(stderr, "round %d stage %d: max warp load %lld, mean %lld, biggest task %lld\n", r, st, crit, tot / prm.warps, big);
+      }
     }
     stage0 += an.nstages;
   }
