@@ -189,6 +189,9 @@ mtp_gather_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
     long long row0;
     double x0, x1, x2;
   };
+  double *const fld0 = pb.fld;
+  int *const pj0 = pb.pj, *const pjt0 = pb.pjt;
+  const long long cap = pb.cap;
   // every warp walks a CONTIGUOUS run of the list: consecutive centres share most of their neighbors (the list is in
   // spatial order after LAMMPS's atom sort), so the gathered records of a run stay in L1 (the kernel asks for a large
   // L1 carve-out) and only ~10 % of the gathers go to L2
@@ -272,17 +275,18 @@ mtp_gather_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
           }
         }
         const long long s = slot0 + done + lane;
-        pb.fld[s] = r0 * invd;
-        pb.fld[pb.cap + s] = r1 * invd;
-        pb.fld[2 * pb.cap + s] = r2 * invd;
-        pb.fld[3 * pb.cap + s] = dist;
+        double *rec = fld0 + s;    // field f of this record: rec[f * cap]
+        rec[0] = r0 * invd;
+        rec[cap] = r1 * invd;
+        rec[2 * cap] = r2 * invd;
+        rec[3 * cap] = dist;
 #pragma unroll
         for (int mu = 0; mu < R; mu++) {
-          pb.fld[(4 + mu) * pb.cap + s] = F[mu];
-          pb.fld[(4 + R + mu) * pb.cap + s] = Fd[mu];
+          rec[(4 + mu) * cap] = F[mu];
+          rec[(4 + R + mu) * cap] = Fd[mu];
         }
-        pb.pj[s] = jj.x;
-        pb.pjt[s] = jt | (at.itype << 16);    // neighbor species | centre species
+        pj0[s] = jj.x;
+        pjt0[s] = jt | (at.itype << 16);    // neighbor species | centre species
       }
       __syncwarp();
       head = (head + n) & (V2_RING - 1);
