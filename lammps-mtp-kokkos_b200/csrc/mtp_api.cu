@@ -569,7 +569,7 @@ void upload_potential(mtp_handle *h)
       CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) h->v2_radial, 256, h->v2_smem_g));
       h->v2_grid_r = std::max(1, per_sm) * h->sm_count;
       h->v2_grid_g = h->v2_grid_r;
-      h->v2_smem_m = (size_t) 2 * V2_NT * (3 + E.R) * 33 * 8;
+      h->v2_smem_m = (size_t) 2 * 32 * ((3 + E.R) * V2_NT + 4) * 8;
       ok = h->v2_smem_m <= max_dynamic_smem((const void *) E.moments, smem_max);
       if (ok) {
         allow_max_dynamic_smem((const void *) E.moments, smem_max);

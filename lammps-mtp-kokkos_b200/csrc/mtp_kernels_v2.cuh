@@ -392,7 +392,12 @@ __device__ __forceinline__ void v2_moments_body(const SiteArgs &a, const PairBuf
                                                 double *tiles)
 {
   using Sh = V2Shape<D0>;
-  constexpr int R = Sh::R, NF = Sh::NF, NTH = 32 * Sh::NP, TILE = V2_NT * NF * 33;
+  // A tile holds V2_NT pair records of each of the 32 atoms of a block, atom-major: row al = [field][pair], ROW doubles
+  // long.  It is filled by straight 16-byte copies (two pairs of one field are contiguous in the pair buffer and in the
+  // row).  Lane al reads its row; it takes the pairs of every aligned group of four in the order n ^ ((al >> 2) & 3):
+  // with ROW = 4 (mod 16) the 16 lanes of a half warp then hit 16 different 8-byte bank pairs (4 (al & 3) + (n ^ q)).
+  constexpr int R = Sh::R, NF = Sh::NF, NTH = 32 * Sh::NP, ROW = NF * V2_NT + 4, TILE = 32 * ROW;
+  static_assert(V2_NT % 4 == 0 && (NF * V2_NT) % 16 == 0, "tile shape");
   const int lane = threadIdx.x & 31;
   const int nblk = (a.inum + 31) >> 5;
 
@@ -405,20 +410,24 @@ __device__ __forceinline__ void v2_moments_body(const SiteArgs &a, const PairBuf
   // stage tile (blk, n0) into buffer buf; cnt_l = this lane's pair count for atom `lane` of blk
   auto stage = [&](int buf, int blk, int n0, int cnt_l) {
     double *tile = tiles + (size_t) buf * TILE;
-    // warps split the atoms; lanes cover (field, pair) with the pair index fastest: 128-byte runs per field
+    // warps split the atoms; the lanes cover the NF x V2_NT / 2 16-byte chunks of an atom's row
+    constexpr int CH = V2_NT / 2;
     const int warp = threadIdx.x >> 5;
+#pragma unroll 1
     for (int al = warp; al < 32; al += Sh::NP) {
       const int cnt_al = __shfl_sync(FULL, cnt_l, al);
       const double *abase = pb.fld + (size_t) (blk * 32 + al) * pb.ncap + n0;
-      double *trow = tile + al;
+      const unsigned trow = (unsigned) __cvta_generic_to_shared(tile + al * ROW);
 #pragma unroll
-      for (int r0 = 0; r0 < V2_NT * NF; r0 += 32) {
-        const int r = r0 + lane;
-        const int fi = r / V2_NT, n = r % V2_NT;    // V2_NT is a power of two
-        if (r < V2_NT * NF) {
+      for (int c0 = 0; c0 < NF * CH; c0 += 32) {
+        const int c = c0 + lane;
+        if (c < NF * CH) {
+          const int fi = c / CH, ch = c % CH;       // CH is a power of two
           const int gf = fi < 3 ? fi : fi + 1;      // skip the distance field
-          const bool live = n0 + n < cnt_al;
-          cp_async8_zfill(trow + (n * NF + fi) * 33, abase + (size_t) gf * pb.cap + (live ? n : 0), live ? 8 : 0);
+          const int live = min(2, max(0, cnt_al - (n0 + 2 * ch)));
+          const double *src = abase + (size_t) gf * pb.cap + (live ? 2 * ch : 0);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(trow + (unsigned) (fi * V2_NT + 2 * ch) * 8u), "l"(src),
+                       "r"(live * 8));
         }
       }
     }
@@ -451,15 +460,15 @@ __device__ __forceinline__ void v2_moments_body(const SiteArgs &a, const PairBuf
       cp_async_wait<0>();
     __syncthreads();
     {
-      const double *tile = tiles + (size_t) buf * TILE;
-      const int nt = min(V2_NT, nmax - n0);
+      const double *row = tiles + (size_t) buf * TILE + lane * ROW;
+      const int nt = (min(V2_NT, nmax - n0) + 3) & ~3, q = (lane >> 2) & 3;
       for (int n = 0; n < nt; n++) {
-        const double *rec = tile + (size_t) n * NF * 33 + lane;
-        const double ux = rec[0], uy = rec[33], uz = rec[66];
+        const double *rec = row + (n ^ q);
+        const double ux = rec[0], uy = rec[V2_NT], uz = rec[2 * V2_NT];
         double f[R];
 #pragma unroll
-        for (int mu = 0; mu < R; mu++) f[mu] = rec[(3 + mu) * 33];
-        v2_fwd_accumulate<D0, P>(ux, uy, uz, f, acc);    // padded records have f = 0
+        for (int mu = 0; mu < R; mu++) f[mu] = rec[(3 + mu) * V2_NT];
+        v2_fwd_accumulate<D0, P>(ux, uy, uz, f, acc);    // padded records are all zero
       }
     }
     if (last_tile) {
@@ -508,7 +517,7 @@ template <int D0>
 __global__ void __launch_bounds__(32 * V2Shape<D0>::NP, V2MomentsBounds<D0>::MINB)
 mtp_moments_v2(SiteArgs a, PairBuf pb, double *__restrict__ mb, int ld)
 {
-  extern __shared__ __align__(16) unsigned char smem[];    // two tiles of V2_NT x NF x 33 doubles
+  extern __shared__ __align__(16) unsigned char smem[];    // two tiles of 32 x (NF x V2_NT + 4) doubles
   V2PassDispatch<D0, 0>::run(threadIdx.x >> 5, a, pb, mb, ld, reinterpret_cast<double *>(smem));
 }
 
