@@ -336,12 +336,13 @@ typedef void (*V2ForcesKernel)(SiteArgs, PairBuf, const double *, int, double *)
 constexpr int v2_ab_for(int kf) { return 3 * kf * 64 * 8 <= 110 * 1024 ? 64 : 3 * kf * 32 * 8 <= 110 * 1024 ? 32 : 3 * kf * 16 * 8 <= 110 * 1024 ? 16 : 8; }
 struct V2Entry {
   int d0, R, KF, NP, AB;
-  V2GatherKernel radial_v[3];    // {resident CTAs per SM, batches of 32 neighbors in flight}: {2, 3}, {3, 1}, {3, 2}
+  V2GatherKernel radial_v[3];    // [0] 8 radial basis functions, unit row stride, no mask output; [1] 8 functions; [2] general
   V2MomentsKernel moments;
   V2ForcesKernel forces[2];    // [grade step]
 };
 #define V2_ENTRY(D)                                                                                                    \
-  {D, V2Shape<D>::R, V2Shape<D>::KF, V2Shape<D>::NP, v2_ab_for(V2Shape<D>::KF), {mtp_gather_radial_kernel<V2Shape<D>::R, 2, 3>, mtp_gather_radial_kernel<V2Shape<D>::R, 3, 1>, mtp_gather_radial_kernel<V2Shape<D>::R, 3, 2>}, \
+  {D, V2Shape<D>::R, V2Shape<D>::KF, V2Shape<D>::NP, v2_ab_for(V2Shape<D>::KF), {mtp_gather_radial_kernel<V2Shape<D>::R, 2, 3, true, true>, mtp_gather_radial_kernel<V2Shape<D>::R, 2, 3, true, false>, \
+    mtp_gather_radial_kernel<V2Shape<D>::R, 2, 3, false, false>},                                                       \
    mtp_moments_v2<D>,                                                                                                  \
    {mtp_forces_v2<D, v2_ab_for(V2Shape<D>::KF), false>, mtp_forces_v2<D, v2_ab_for(V2Shape<D>::KF), true>}}
 const V2Entry kV2[] = {V2_ENTRY(0), V2_ENTRY(1), V2_ENTRY(2), V2_ENTRY(3), V2_ENTRY(4), V2_ENTRY(5),
@@ -549,18 +550,17 @@ void upload_potential(mtp_handle *h)
     h->v2_smem_g = (size_t) ((nrad + 1) & ~1) * 8 + (size_t) 8 * V2_RING * 4 * 8;    // coefficients + one ring per warp
     // resident CTAs per SM the gather kernel is compiled for: the gather is bound by the latency of its L2 gathers, so
     // resident warps count more than registers (the radial phase spills a few values at 48 registers)
-    int gv = 0;
-    if (const char *e = getenv("MTP_B200_GR_VARIANT")) gv = std::max(0, std::min(2, atoi(e)));
-    h->v2_radial = E.radial_v[gv];
+    h->v2_radial = E.radial_v[d.B == 8 ? 1 : 2];
     bool ok = h->v2_smem_g <= max_dynamic_smem((const void *) h->v2_radial, smem_max);
     if (ok) {
-      allow_max_dynamic_smem((const void *) h->v2_radial, smem_max);
+      for (int gv = 0; gv < 3; gv++) allow_max_dynamic_smem((const void *) E.radial_v[gv], smem_max);
       if (!getenv("MTP_B200_NO_CARVEOUT")) {
         // the gather lives on its L1 hit rate (see the kernel): it asks for the smallest shared-memory carve-out that holds
         // its rings, unlike the other kernels of the pipeline, which all ask for the maximum
         int carve = 25;
         if (const char *e = getenv("MTP_B200_GR_CARVEOUT")) carve = atoi(e);
-        CUDA_CHECK(cudaFuncSetAttribute((const void *) h->v2_radial, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        for (int gv = 0; gv < 3; gv++)
+          CUDA_CHECK(cudaFuncSetAttribute((const void *) E.radial_v[gv], cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         CUDA_CHECK(cudaFuncSetAttribute((const void *) E.moments, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         for (int gq = 0; gq < 2; gq++)
           CUDA_CHECK(cudaFuncSetAttribute((const void *) E.forces[gq], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1021,7 +1021,9 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
       {
         ProfSpan sp(h, MTP_PROF_GATHER, ls);
         const int gr = std::max(1, std::min(h->v2_grid_r, (n + 7) / 8));
-        h->v2_radial<<<gr, 256, h->v2_smem_g, ls>>>(d, s, pb);
+        // the plain instance when the call allows it (unit stride within a row, no cutoff-mask output)
+        V2GatherFn gk = (d.B == 8 && s.stride_jj == 1 && !s.within) ? E.radial_v[0] : h->v2_radial;
+        gk<<<gr, 256, h->v2_smem_g, ls>>>(d, s, pb);
       }
       {
         ProfSpan sp(h, MTP_PROF_MOMENTS, ls);

@@ -124,21 +124,35 @@ constexpr int V2_NT = MTP_V2_NT;      // pairs per staged tile of the moment ker
 // pair (pair_mtp.cpp:139-151), fully unrolled.  ct = coefficient table in shared memory, element (ri, mu) of species
 // pair pt at ct[(ri * R + mu) * SP + pt]: the lanes of a warp that differ in their species pair read adjacent words
 // (no bank conflict), lanes with the same pair read one word (broadcast).
+struct RadialConsts {
+  double rmax, ka, kb, mult, scaling;    // xi = ka d + kb,  mult = d xi / d d
+};
+__device__ __forceinline__ RadialConsts radial_consts(const DevPotential &pot)
+{
+  RadialConsts c;
+  const double inv = 1.0 / (pot.rmax - pot.rmin);    // one division per thread instead of one per pair
+  c.rmax = pot.rmax;
+  c.ka = 2.0 * inv;
+  c.kb = -(pot.rmin + pot.rmax) * inv;
+  c.mult = 2.0 * inv;
+  c.scaling = pot.scaling;
+  return c;
+}
 template <int R, int B>
-__device__ __forceinline__ void radial_unrolled(const DevPotential &pot, const double *__restrict__ ct, int SP, double d,
+__device__ __forceinline__ void radial_unrolled(const RadialConsts &rc, const double *__restrict__ ct, int SP, double d,
                                                 double (&F)[R], double (&Fd)[R])
 {
-  const double t = d - pot.rmax;
-  const double ksi = (2 * d - (pot.rmin + pot.rmax)) / (pot.rmax - pot.rmin);
-  const double mult = 2.0 / (pot.rmax - pot.rmin);
-  double v_prev = pot.scaling * (1 * t * t), d_prev = pot.scaling * 2 * t;
+  const double t = d - rc.rmax;
+  const double ksi = fma(d, rc.ka, rc.kb);
+  const double mult = rc.mult;
+  double v_prev = rc.scaling * (1 * t * t), d_prev = rc.scaling * 2 * t;
 #pragma unroll
   for (int mu = 0; mu < R; mu++) {
     F[mu] = ct[mu * SP] * v_prev;
     Fd[mu] = ct[mu * SP] * d_prev;
   }
   if (B == 1) return;
-  double v_cur = pot.scaling * (ksi * t * t), d_cur = pot.scaling * (mult * t * t + 2 * ksi * t);
+  double v_cur = rc.scaling * (ksi * t * t), d_cur = rc.scaling * (mult * t * t + 2 * ksi * t);
 #pragma unroll
   for (int ri = 1; ri < B; ri++) {
     if (ri > 1) {
@@ -166,7 +180,9 @@ __device__ __forceinline__ void radial_unrolled(const DevPotential &pot, const d
 // The displacement never travels through global memory, every lane of the radial phase is busy, and the FP64 work of
 // one warp runs under the gather latency of the others.
 constexpr int V2_RING = 64;
-template <int R, int MINB, int V2_GB>
+// B8: the radial basis has 8 functions (every MLIP template) -> fully unrolled recurrence; PLAIN: unit stride within a
+// neighbor row and no cutoff-mask output (what a force evaluation inside an MD run asks for)
+template <int R, int MINB, int V2_GB, bool B8, bool PLAIN>
 __global__ void __launch_bounds__(256, MINB)
 mtp_gather_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
 {
@@ -192,6 +208,8 @@ mtp_gather_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
   double *const fld0 = pb.fld;
   int *const pj0 = pb.pj, *const pjt0 = pb.pjt;
   const long long cap = pb.cap;
+  const RadialConsts rc = radial_consts(pot);
+  const long long stride_jj = PLAIN ? 1 : a.stride_jj;
   // every warp walks a CONTIGUOUS run of the list: consecutive centres share most of their neighbors (the list is in
   // spatial order after LAMMPS's atom sort), so the gathered records of a run stay in L1 (the kernel asks for a large
   // L1 carve-out) and only ~10 % of the gathers go to L2
@@ -244,7 +262,7 @@ mtp_gather_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
         const double dist = rsq * invd;
         double F[R], Fd[R];
         const double *ct = s_ct + (at.itype * pot.S + jt);
-        if (pot.B == 8) radial_unrolled<R, 8>(pot, ct, SS, dist, F, Fd);
+        if (B8) radial_unrolled<R, 8>(rc, ct, SS, dist, F, Fd);
         else {    // any other basis size: same recurrence with a run-time trip count
           const double t = dist - pot.rmax;
           const double ksi = (2 * dist - (pot.rmin + pot.rmax)) / (pot.rmax - pot.rmin);
@@ -299,7 +317,7 @@ mtp_gather_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
 #pragma unroll
       for (int b = 0; b < V2_GB; b++) {
         const int jj = base0 + 32 * b + lane;
-        jv[b] = jj < at.jnum ? (a.neighbors[at.row0 + (long long) jj * a.stride_jj] & a.neighmask) : at.i;
+        jv[b] = jj < at.jnum ? (a.neighbors[at.row0 + (long long) jj * stride_jj] & a.neighmask) : at.i;
       }
 #pragma unroll
       for (int b = 0; b < V2_GB; b++)
@@ -322,7 +340,7 @@ mtp_gather_radial_kernel(DevPotential pot, SiteArgs a, PairBuf pb)
             atomicOr(a.status, 1);
             within = false;
           }
-          if (a.within) a.within[at.row0 + (long long) jj * a.stride_jj] = within ? 1 : 0;
+          if (!PLAIN && a.within) a.within[at.row0 + (long long) jj * stride_jj] = within ? 1 : 0;
         }
         const unsigned bal = __ballot_sync(FULL, within);
         if (within) {
