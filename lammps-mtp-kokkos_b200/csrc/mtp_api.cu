@@ -665,7 +665,7 @@ void upload_potential(mtp_handle *h)
       try {
         const P4Choice ch = p4_choose(p, smem_max, shape == 1);
         if (!ch.ok) throw std::runtime_error("potential structure or size outside the generator's range");
-        if (shape == 1 && h->p4[0].loaded() && ch.prm.na == h->p4[0].choice.prm.na) continue;    // same kernel
+        if (shape == 1 && h->p4[0].loaded() && ch.prm.na == h->p4[0].choice.prm.na && ch.prm.groups == h->p4[0].choice.prm.groups) continue;    // same kernel
         P4Module &m = h->p4[shape];
         const std::vector<char> cubin = p4_cubin(p, ch, h->slot_of_k.data(), h->p4_nslots, m.info);
         m.choice = ch;
@@ -743,7 +743,7 @@ int plan_chunk(const mtp_handle *h, int inum, bool grade)
         return x / a * y;
       };
       const long long um = (long long) h->v2_grid_m * 32, uf = (long long) h->v2_grid_fg[grade ? 1 : 0] * h->v2_ab;
-      const long long up = h->p4[0].loaded() ? (long long) h->p4[0].grid_cap * h->p4[0].choice.prm.na
+      const long long up = h->p4[0].loaded() ? (long long) h->p4[0].grid_cap * h->p4[0].choice.atoms_per_cta()
                                              : (long long) h->sm_count * (h->p3_na ? h->p3_na : std::max(1, h->pl_na[0]));
       long long unit = 0;
       if (um > 0 && uf > 0) {
@@ -936,7 +936,7 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
     p4m = (small_p4 && h->p4[1].loaded()) ? &h->p4[1] : (h->p4[0].loaded() ? &h->p4[0] : nullptr);
     if (p4m) {
       p3 = nullptr;
-      na = p4m->choice.prm.na;
+      na = p4m->choice.atoms_per_cta();
       grid_p_cap = p4m->grid_cap;
     }
   }
@@ -1240,7 +1240,7 @@ int mtp_codegen_source(const char *path, int latency_shape, char *buf, long long
     *needed = (long long) src.size() + 1;
     if (buf && cap >= *needed) memcpy(buf, src.c_str(), src.size() + 1);
     if (info_out) {
-      const long long v[13] = {ch.prm.na, ch.prm.warps, ch.min_blocks, info.rows, info.stages, (long long) info.smem_bytes, info.terms,
+      const long long v[13] = {ch.atoms_per_cta(), ch.prm.warps, ch.min_blocks, info.rows, info.stages, (long long) info.smem_bytes, info.terms,
                                info.loads, info.stores, info.crit_terms, nslots, (long long) info.hash, info.rounds};
       memcpy(info_out, v, sizeof(v));
     }

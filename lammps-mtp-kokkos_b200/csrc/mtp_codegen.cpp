@@ -40,7 +40,7 @@ struct Analysis {
 // active (optional, [A]): the basis functions this round evaluates; the program is then restricted to their ancestors,
 // and the other basis functions that are ancestors themselves count as plain intermediates (adjoint seed 0)
 bool analyse(const Potential &p, Analysis &an, std::string &why, const std::vector<char> *active = nullptr,
-             bool first_round = true)
+             bool first_round = true, bool sparse_basics = false)
 {
   an.K = p.alpha_index_basic_count;
   an.M = p.alpha_moment_count;
@@ -109,7 +109,8 @@ bool analyse(const Potential &p, Analysis &an, std::string &why, const std::vect
   an.mrow.assign(M, -1);
   an.grow.assign(M, -1);
   int r = 0;
-  for (int n = 0; n < K; n++) an.mrow[n] = r++;
+  for (int n = 0; n < K; n++)    // sparse: only the basic moments this round reads (as a factor or as a basis function)
+    if (!sparse_basics || an.operand[n] || an.scalar[n] >= 0) an.mrow[n] = r++;
   for (int n = K; n < M; n++)
     if (an.operand[n]) an.mrow[n] = r++;
   an.m_rows = r;
@@ -374,7 +375,7 @@ unsigned long long fnv(unsigned long long h, const void *data, size_t n)
   return h;
 }
 
-const char *kGeneratorVersion = "p4-r2-07";
+const char *kGeneratorVersion = "p4-r2-09";
 
 // ---- fixed text: device prelude and kernel skeleton ------------------------------------------------------
 const char *kDevicePrelude = R"P4(
@@ -407,6 +408,25 @@ struct T_ {
   double x, y;
 };
 #endif
+#ifdef P4_SPARSE
+struct P4Ctx {           // one context for the P4_G atom groups of the CTA iteration; group g: rows at sb + g * P4_GROUP_BYTES
+  unsigned sb, lb;
+  double *gb, *cand;
+  long long ld, cand_ld;
+  int na, al, fbase;     // atoms of this iteration, first atom of the lane within a group, bit 2: grade step, bit 3: owner lane
+  T_ e[P4_G];
+};
+#define P4_GROUP_BYTES (P4_ROWS * P4_NA * 8)
+// every emitted function runs P4_G times in a row, once per atom group: the second to last executions find it in the
+// instruction cache
+#define P4_GCALL(f) \
+  _Pragma("unroll") for (int g_ = 0; g_ < P4_G; g_++) { \
+    const int c_ = g_ * P4_NA + x.al; \
+    const int fl_ = (x.fbase & 4) | (((x.fbase & 8) && c_ < x.na) ? 1 : 0) | ((P4_APL == 2 && (x.fbase & 8) && c_ + 1 < x.na) ? 2 : 0); \
+    x.e[g_] = f(x.sb + g_ * P4_GROUP_BYTES, x.lb, x.gb + g_ * P4_NA, x.ld, \
+                x.cand ? x.cand + (long long) g_ * P4_NA * x.cand_ld : x.cand, x.cand_ld, fl_, x.e[g_]); \
+  }
+#else
 struct P4Ctx {
   unsigned sb, lb;       // shared-window byte addresses: rows + this lane's atom offset, linear coefficients
   double *gb, *cand;
@@ -414,6 +434,7 @@ struct P4Ctx {
   int flags;             // bit 0: first atom of the lane is a listed centre, bit 1: second atom, bit 2: grade step
   T_ e;
 };
+#endif
 #define P4_PARAMS const unsigned sb, const unsigned lb, double *const gb, const long long ld, double *const cand, \
                   const long long cand_ld, const int flags, T_ e
 #define P4_RET T_
@@ -425,6 +446,7 @@ template <int OFF> P4_FN double p4_lds1(unsigned a)
   asm("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF));
   return v;
 }
+P4_FN void p4_red(double *q, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(q), "d"(v) : "memory"); }
 #define LIN(s) p4_lds1<(s) * 8>(lb)
 #if P4_APL == 1
 template <int OFF> P4_FN void p4_sts(unsigned a, double v) { asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "d"(v) : "memory"); }
@@ -440,7 +462,9 @@ template <int OFF> P4_FN void p4_sts(unsigned a, double v) { asm volatile("st.sh
 #define SPLAT(u) (u)
 #define ZERO 0.0
 #define GBST(slot, v) do { if (flags & 1) __stcg(gb + (long long) (slot) * ld, (v)); } while (0)
-#define GBACC(slot, v) do { if (flags & 1) { double *q_ = gb + (long long) (slot) * ld; __stcg(q_, __ldcg(q_) + (v)); } } while (0)
+// later rounds ADD their share: a reduction without return value (RED.ADD.F64), so the round never waits for the old value;
+// one lane owns an address and its updates are issued in program order, so the sum has a fixed order
+#define GBACC(slot, v) do { if (flags & 1) p4_red(gb + (long long) (slot) * ld, (v)); } while (0)
 #define ESC(s, v) do { e = fma(LIN(s), (v), e); if ((flags & 5) == 5) cand[s] = (v); } while (0)
 #else
 template <int OFF> P4_FN T_ p4_lds2(unsigned a)
@@ -472,8 +496,8 @@ P4_FN T_ p4_splat(double u) { T_ r; r.x = u; r.y = u; return r; }
 #define ZERO p4_splat(0.0)
 #define GBST(slot, v) do { const T_ v_ = (v); double *q_ = gb + (long long) (slot) * ld; \
     if (flags & 2) __stcg(reinterpret_cast<double2 *>(q_), make_double2(v_.x, v_.y)); else if (flags & 1) __stcg(q_, v_.x); } while (0)
-#define GBACC(slot, v) do { const T_ v_ = (v); double *q_ = gb + (long long) (slot) * ld; \\
-    if (flags & 1) __stcg(q_, __ldcg(q_) + v_.x); if (flags & 2) __stcg(q_ + 1, __ldcg(q_ + 1) + v_.y); } while (0)
+#define GBACC(slot, v) do { const T_ v_ = (v); double *q_ = gb + (long long) (slot) * ld; \
+    if (flags & 1) p4_red(q_, v_.x); if (flags & 2) p4_red(q_ + 1, v_.y); } while (0)
 #define ESC(s, v) do { const T_ v_ = (v); e = p4_fmau(LIN(s), v_, e); \
     if (flags & 4) { if (flags & 1) cand[s] = v_.x; if (flags & 2) cand[cand_ld + (s)] = v_.y; } } while (0)
 #endif
@@ -564,6 +588,105 @@ extern "C" __global__ void __launch_bounds__(P4_W * 32, P4_MINB) mtp_program_p4(
 #endif
 )P4";
 
+// Sparse / grouped form: a CTA iteration takes P4_G groups of P4_NA atoms; the rows of group g start at
+// S + g * P4_ROWS * P4_NA; at the first stage of a round the basic moments that round reads are staged for all groups.
+const char *kKernelSparse = R"P4(
+#ifndef P4_HOST
+extern "C" __global__ void __launch_bounds__(P4_W * 32, P4_MINB) mtp_program_p4(const P4Args a)
+{
+  extern __shared__ __align__(16) double S[];
+  constexpr int NAC = P4_NA * P4_G;    // atoms per CTA iteration
+  double *s_lin = S + (size_t) P4_ROWS * NAC;
+  double *epart = s_lin + ((P4_A + 1) & ~1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int t = tid; t < P4_A; t += P4_W * 32) s_lin[t] = a.lin[t];
+  const int al = (P4_APL * lane) % P4_NA;        // first atom of this lane within a group
+  const bool owner = P4_APL * lane < P4_NA;      // lanes beyond the group width repeat the work of another lane, never write
+  double e_thread = 0.0;
+  __syncthreads();
+  for (int chunk0 = blockIdx.x * NAC; chunk0 < a.inum; chunk0 += gridDim.x * NAC) {
+    const int na = min(NAC, a.inum - chunk0);
+    P4Ctx x;
+    x.sb = (unsigned) __cvta_generic_to_shared(S + al);
+    x.lb = (unsigned) __cvta_generic_to_shared(s_lin);
+    x.ld = a.ld;
+    x.gb = a.gb + chunk0 + al;
+    x.cand_ld = a.cand_ld;
+    x.cand = a.grade ? a.cand_rows + (long long) (chunk0 + al) * a.cand_ld + a.cand_col0 : nullptr;
+    x.na = na;
+    x.al = al;
+    x.fbase = (owner ? 8 : 0) | (a.grade ? 4 : 0);
+#pragma unroll
+    for (int g = 0; g < P4_G; g++) {
+#if P4_APL == 2
+      x.e[g].x = x.e[g].y = 0.0;
+#else
+      x.e[g] = 0.0;
+#endif
+    }
+    int round = 0;
+#pragma unroll 1
+    for (int st = 0; st < P4_NSTAGE; st++) {
+      if (st == p4_round_stage0[round]) {    // basic moments this round reads -> their rows, every group (16-byte cp.async, zero fill past the end)
+        const int i0 = p4_stage_off[round], nrow = p4_stage_off[round + 1] - i0;
+        for (int t = tid; t < nrow * (NAC / 2); t += P4_W * 32) {
+          const int i = i0 + t / (NAC / 2), c = (t % (NAC / 2)) * 2;
+          const int nb = max(0, min(2, na - c)) * 8;
+          const unsigned dst = (unsigned) __cvta_generic_to_shared(S + ((size_t) (c / P4_NA) * P4_ROWS + p4_stage_row[i]) * P4_NA + c % P4_NA);
+          const double *src = a.mb + (long long) p4_stage_slot[i] * a.ld + chunk0 + (nb ? c : 0);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(nb));
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();
+        round++;
+      }
+      p4_run_stage(st, warp, x);
+      __syncthreads();
+    }
+    for (int t = tid; t < P4_NZERO * NAC; t += P4_W * 32) {    // rows of gb that no basic moment owns
+      const int c = t % NAC;
+      if (c < na) a.gb[(long long) p4_zero_slot[t / NAC] * a.ld + chunk0 + c] = 0.0;
+    }
+    if (a.eflag_global || a.eflag_atom) {    // fixed-order sum over the warps, species term (pair_mtp.cpp:204-212)
+      if (owner) {
+#pragma unroll
+        for (int g = 0; g < P4_G; g++) {
+#if P4_APL == 2
+          epart[(warp * P4_G + g) * P4_NA + al] = x.e[g].x;
+          epart[(warp * P4_G + g) * P4_NA + al + 1] = x.e[g].y;
+#else
+          epart[(warp * P4_G + g) * P4_NA + al] = x.e[g];
+#endif
+        }
+      }
+      __syncthreads();
+      for (int c = tid; c < na; c += P4_W * 32) {
+        const int i = a.ilist ? a.ilist[a.first_ii + chunk0 + c] : a.first_ii + chunk0 + c;
+        int itype = (int) *reinterpret_cast<const long long *>(reinterpret_cast<const char *>(a.xt) + 32 * (size_t) i + 24);
+        if (itype < 0 || itype >= a.S) itype = 0;
+        double es = 0.0;
+        for (int w = 0; w < P4_W; w++) es += epart[(w * P4_G + c / P4_NA) * P4_NA + c % P4_NA];
+        es += a.species[itype];
+        if (a.eflag_atom) a.eatom[i] = es;
+        if (a.eflag_global) e_thread += es;
+      }
+      __syncthreads();
+    }
+  }
+  // per-CTA energy partial, fixed order
+  epart[tid] = e_thread;
+  __syncthreads();
+  if (tid < 8) {
+    double s = 0.0;
+    if (tid == 0)
+      for (int t = 0; t < P4_W * 32; t++) s += epart[t];
+    a.partials[(size_t) blockIdx.x * 8 + tid] = s;
+  }
+}
+#endif
+)P4";
+
 struct Plan {
   Analysis an;
   std::vector<std::vector<std::vector<Task>>> work;    // [stage][warp] -> tasks in order
@@ -576,7 +699,7 @@ bool make_plan(const Potential &p, const P4Params &prm, Plan &pl, std::string &w
     why = "bad generator parameters";
     return false;
   }
-  if (!analyse(p, pl.an, why, active, first_round)) return false;
+  if (!analyse(p, pl.an, why, active, first_round, prm.sparse != 0)) return false;
   const Analysis &an = pl.an;
   pl.work.assign(an.nstages, std::vector<std::vector<Task>>(prm.warps));
   for (int st = 0; st < an.nstages; st++) {
@@ -635,7 +758,8 @@ bool make_plan(const Potential &p, const P4Params &prm, Plan &pl, std::string &w
 
 size_t smem_of_rows(int rows, int A, const P4Params &prm)
 {
-  return ((size_t) rows * prm.na + (size_t) ((A + 1) & ~1) + (size_t) prm.warps * prm.na) * 8;
+  const size_t g = (size_t) std::max(1, prm.groups);
+  return ((size_t) rows * prm.na * g + (size_t) ((A + 1) & ~1) + (size_t) prm.warps * prm.na * g) * 8;
 }
 
 // Rounds.  When the rows of the whole program (moments of every operand node + adjoints of the non-basic ones) do not
@@ -646,12 +770,13 @@ size_t smem_of_rows(int rows, int A, const P4Params &prm)
 bool make_rounds(const Potential &p, const P4Params &prm, std::vector<std::vector<char>> &rounds, std::string &why)
 {
   Analysis all;
-  if (!analyse(p, all, why)) return false;
+  if (!analyse(p, all, why, nullptr, true, prm.sparse != 0)) return false;
   rounds.clear();
   if (prm.smem_budget == 0 || smem_of_rows(all.m_rows + all.g_rows, all.A, prm) <= prm.smem_budget) return true;    // one round
   const int K = all.K, M = all.M, T = all.T, A = all.A;
   const long long fixed = (long long) smem_of_rows(0, A, prm);
-  const long long row_budget = ((long long) prm.smem_budget - fixed) / ((long long) prm.na * 8);
+  const long long row_budget = ((long long) prm.smem_budget - fixed) / ((long long) prm.na * std::max(1, prm.groups) * 8);
+  const bool sparse = prm.sparse != 0;
   const int *tm = p.alpha_index_times.data();
   // proper non-basic ancestors of every basis function (bit sets): exactly the nodes that need a moment row and an
   // adjoint row in the round that evaluates it
@@ -674,13 +799,25 @@ bool make_rounds(const Potential &p, const P4Params &prm, std::vector<std::vecto
   for (int n = 0; n < M; n++) anc[n].assign(W64, 0ULL);
   for (int t : order)    // a target's factors were completed before its first product (topological file order)
     for (int o : in_ops[t]) {
-      if (o >= K) anc[t][o >> 6] |= 1ULL << (o & 63);
+      if (o >= K || sparse) anc[t][o >> 6] |= 1ULL << (o & 63);    // sparse: basic factors cost a row too
       for (int w = 0; w < W64; w++) anc[t][w] |= anc[o][w];
     }
-  auto popcount = [&](const std::vector<unsigned long long> &v) {
-    long long c = 0;
-    for (unsigned long long x : v) c += __builtin_popcountll(x);
-    return c;
+  if (sparse)    // a basic moment that is a basis function itself is read by its round
+    for (int sc = 0; sc < A; sc++) {
+      const int n = p.alpha_moment_mapping[sc];
+      if (n < K) anc[n][n >> 6] |= 1ULL << (n & 63);
+    }
+  // rows a set of nodes costs: one per basic moment (all K when not sparse), moment + adjoint per other node
+  std::vector<unsigned long long> basic_mask(W64, 0ULL);
+  for (int n = 0; n < K; n++) basic_mask[n >> 6] |= 1ULL << (n & 63);
+  auto rows_of = [&](const std::vector<unsigned long long> &a, const std::vector<unsigned long long> *b) {
+    long long nb = 0, no = 0;
+    for (int w = 0; w < W64; w++) {
+      const unsigned long long v = a[w] | (b ? (*b)[w] : 0ULL);
+      nb += __builtin_popcountll(v & basic_mask[w]);
+      no += __builtin_popcountll(v & ~basic_mask[w]);
+    }
+    return (sparse ? nb : (long long) K) + 2 * no;
   };
   std::vector<char> assigned(A, 0);
   int left = A;
@@ -695,11 +832,9 @@ bool make_rounds(const Potential &p, const P4Params &prm, std::vector<std::vecto
       for (int sc = 0; sc < A; sc++) {
         if (assigned[sc]) continue;
         const std::vector<unsigned long long> &as = anc[p.alpha_moment_mapping[sc]];
-        long long add = 0, size = 0;
-        for (int w = 0; w < W64; w++) {
-          add += __builtin_popcountll(as[w] & ~cur[w]);
-          size += __builtin_popcountll(as[w]);
-        }
+        long long size = 0;
+        for (int w = 0; w < W64; w++) size += __builtin_popcountll(as[w]);
+        const long long add = rows_of(cur, &as) - rows_of(cur, nullptr);
         const bool better = in_cur == 0 ? size > best_size : (best < 0 || add < best_add || (add == best_add && size > best_size));
         if (better) {
           best = sc;
@@ -708,7 +843,7 @@ bool make_rounds(const Potential &p, const P4Params &prm, std::vector<std::vecto
         }
       }
       if (best < 0) break;
-      if (K + 2 * (popcount(cur) + best_add) > row_budget) {
+      if (rows_of(cur, &anc[p.alpha_moment_mapping[best]]) > row_budget) {
         if (in_cur == 0) {
           why = "one basis function alone needs more shared-memory rows than a CTA has";
           return false;
@@ -733,30 +868,47 @@ bool make_rounds(const Potential &p, const P4Params &prm, std::vector<std::vecto
 
 }    // namespace
 
-size_t p4_smem_bytes(const Potential &p, const P4Params &prm)
+namespace {
+P4Params normalised(P4Params prm)
 {
+  prm.groups = std::max(1, prm.groups);
+  if (prm.groups > 1) prm.sparse = 1;
+  return prm;
+}
+}    // namespace
+
+size_t p4_smem_bytes(const Potential &p, const P4Params &prm_in, int *rounds_out)
+{
+  if (rounds_out) *rounds_out = 1;
+  const P4Params prm = normalised(prm_in);
   std::vector<std::vector<char>> rounds;
   std::string why;
   if (!make_rounds(p, prm, rounds, why)) return 0;
   int rows = 0, A = 0;
   if (rounds.empty()) {
     Analysis an;
-    if (!analyse(p, an, why)) return 0;
+    if (!analyse(p, an, why, nullptr, true, prm.sparse != 0)) return 0;
     rows = an.m_rows + an.g_rows;
     A = an.A;
   } else
     for (size_t r = 0; r < rounds.size(); r++) {
       Analysis an;
-      if (!analyse(p, an, why, &rounds[r], r == 0)) return 0;
+      if (!analyse(p, an, why, &rounds[r], r == 0, prm.sparse != 0)) return 0;
       rows = std::max(rows, an.m_rows + an.g_rows);
       A = an.A;
     }
+  if (rounds_out && !rounds.empty()) *rounds_out = (int) rounds.size();
   return smem_of_rows(rows, A, prm);
 }
 
-bool p4_generate(const Potential &p, const P4Params &prm, const short *slot_of_k, int nslots, std::string &src, P4Info &info,
+bool p4_generate(const Potential &p, const P4Params &prm_in, const short *slot_of_k, int nslots, std::string &src, P4Info &info,
                  std::string &why)
 {
+  const P4Params prm = normalised(prm_in);
+  if (prm.groups > 8) {
+    why = "bad generator parameters";
+    return false;
+  }
   std::vector<std::vector<char>> rounds;
   if (!make_rounds(p, prm, rounds, why)) return false;
   const int nrounds = std::max<int>(1, (int) rounds.size());
@@ -782,11 +934,12 @@ bool p4_generate(const Potential &p, const P4Params &prm, const short *slot_of_k
   info.smem_bytes = smem_of_rows(rows, an0.A, prm);
   info.terms = terms;
   info.threads = prm.warps * 32;
+  info.groups = prm.groups;
 
   unsigned long long h = 1469598103934665603ULL;
   h = fnv(h, kGeneratorVersion, strlen(kGeneratorVersion));
-  const long long hdr[11] = {K, an0.M, an0.T, an0.A, prm.na, prm.warps, prm.cache, prm.acc_max, nslots, prm.fn_cost,
-                             (long long) prm.smem_budget};
+  const long long hdr[13] = {K, an0.M, an0.T, an0.A, prm.na, prm.warps, prm.cache, prm.acc_max, nslots, prm.fn_cost,
+                             (long long) prm.smem_budget, prm.groups, prm.sparse};
   h = fnv(h, hdr, sizeof(hdr));
   h = fnv(h, p.alpha_index_times.data(), p.alpha_index_times.size() * sizeof(int));
   h = fnv(h, p.alpha_moment_mapping.data(), p.alpha_moment_mapping.size() * sizeof(int));
@@ -802,6 +955,8 @@ bool p4_generate(const Potential &p, const P4Params &prm, const short *slot_of_k
            "#define P4_NA %d\n#define P4_APL %d\n#define P4_W %d\n#define P4_ROWS %d\n#define P4_MROWS %d\n#define P4_K %d\n"
            "#define P4_A %d\n#define P4_M %d\n#define P4_NSTAGE %d\n#define P4_NSLOTS %d\n#ifndef P4_MINB\n#define P4_MINB 1\n#endif\n",
            kGeneratorVersion, K, an0.M, an0.T, an0.A, nrounds, prm.na, apl, prm.warps, rows, m_rows, K, an0.A, an0.M, nstages, nslots);
+  src += buf;
+  snprintf(buf, sizeof(buf), "#define P4_G %d\n#define P4_NROUND %d\n%s", prm.groups, nrounds, prm.sparse ? "#define P4_SPARSE 1\n" : "");
   src += buf;
   src += kDevicePrelude;
   // tables
@@ -823,6 +978,27 @@ bool p4_generate(const Potential &p, const P4Params &prm, const short *slot_of_k
   src += "#define P4_NZERO " + std::to_string(zero.size()) + "\nP4_TABLE short p4_zero_slot[P4_NZERO + 1] = {";
   for (int s : zero) src += std::to_string(s) + ",";
   src += "0};\n";
+  if (prm.sparse) {    // per round: the basic moments it reads -> (row of mb, shared-memory row), and its first stage
+    std::string off = "P4_TABLE short p4_stage_off[P4_NROUND + 1] = {0", slot = "P4_TABLE short p4_stage_slot[] = {",
+                row = "P4_TABLE short p4_stage_row[] = {", st0 = "P4_TABLE short p4_round_stage0[P4_NROUND + 1] = {";
+    int count = 0, stage = 0;
+    for (const Plan &pl : plans) {
+      for (int k = 0; k < K; k++)
+        if (pl.an.mrow[k] >= 0) {
+          slot += std::to_string(slot_of_k ? (int) slot_of_k[k] : k) + ",";
+          row += std::to_string(pl.an.mrow[k]) + ",";
+          count++;
+        }
+      off += "," + std::to_string(count);
+      st0 += std::to_string(stage) + ",";
+      stage += pl.an.nstages;
+    }
+    if (count > 32767) {
+      why = "too many staged rows";
+      return false;
+    }
+    src += off + "};\n" + slot + "0};\n" + row + "0};\n" + st0 + "-1};\n";
+  }
   // m-row of every node in the LAST round (host harness: lets the checker read back the stored moments); -1 = not stored
   src += "#ifdef P4_HOST\nstatic const int p4_mrow[P4_M] = {";
   for (int n = 0; n < an0.M; n++) src += std::to_string(plans.back().an.mrow[n]) + (n + 1 < an0.M ? "," : "");
@@ -905,11 +1081,12 @@ bool p4_generate(const Potential &p, const P4Params &prm, const short *slot_of_k
   for (size_t q = 0; q < present.size();) {
     const int key = present[q].first;
     src += "    case " + std::to_string(key) + ":\n";
-    for (; q < present.size() && present[q].first == key; q++) src += "      P4_CALL(" + present[q].second + ");\n";
+    for (; q < present.size() && present[q].first == key; q++)
+      src += std::string(prm.sparse ? "      P4_GCALL(" : "      P4_CALL(") + present[q].second + ");\n";
     src += "      break;\n";
   }
   src += "    default: break;\n  }\n}\n";
-  src += kKernel;
+  src += prm.sparse ? kKernelSparse : kKernel;
   return true;
 }
 

@@ -33,6 +33,10 @@ struct P4Params {
   int acc_max = 16;     // adjoints a warp accumulates at once in the reverse pass
   int fn_cost = 4000;   // term steps per emitted function (bounds ptxas time and register pressure)
   size_t smem_budget = 0;    // > 0: dynamic shared memory a CTA may use; a program that needs more is cut into rounds
+  int groups = 1;       // atom groups per CTA: every emitted function is executed `groups` times in a row, once per group
+                        // of `na` atoms, so that an instruction fetched once serves groups * na atoms (the code is
+                        // straight-line and otherwise never reused; small functions stay in the instruction cache)
+  int sparse = 0;       // 1: a round keeps only the basic moments it reads in shared memory (implied by groups > 1)
 };
 
 struct P4Info {
@@ -46,11 +50,13 @@ struct P4Info {
   long long stores = 0;
   long long crit_terms = 0; // sum over stages of the most loaded warp's term steps
   int threads = 0;
+  int groups = 1;           // atom groups per CTA (atoms per CTA iteration = groups * na)
   unsigned long long hash = 0;
 };
 
 // shared-memory bytes the kernel needs for (p, prm) without generating it; 0 = structure not supported
-size_t p4_smem_bytes(const Potential &p, const P4Params &prm);
+// (rounds_out, optional: number of rounds the program is cut into)
+size_t p4_smem_bytes(const Potential &p, const P4Params &prm, int *rounds_out = nullptr);
 
 // Emits the kernel source for potential p.  slot_of_k maps basic moment k to its row of mb / gb (NULL = identity),
 // nslots = rows of mb / gb.  Returns false (and a reason) when the table's structure is outside what the generator

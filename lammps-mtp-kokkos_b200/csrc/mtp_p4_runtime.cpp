@@ -20,14 +20,18 @@ P4Choice p4_choose(const Potential &p, size_t smem_optin, bool latency_shape)
   if (const char *e = getenv(latency_shape ? "MTP_B200_P4_SMALL" : "MTP_B200_P4")) {
     int na = 0, w = 0, c = 0, acc = 0, mb = 0;
     long budget = 0;
-    const int nf = sscanf(e, "%d,%d,%d,%d,%d,%ld", &na, &w, &c, &acc, &mb, &budget);
+    int groups = 1, fn_cost = 0, sparse = 0;
+    const int nf = sscanf(e, "%d,%d,%d,%d,%d,%ld,%d,%d,%d", &na, &w, &c, &acc, &mb, &budget, &groups, &fn_cost, &sparse);
     if (nf >= 5) {
+      if (nf >= 7) ch.prm.groups = groups;
+      if (nf >= 8 && fn_cost > 0) ch.prm.fn_cost = fn_cost;
+      if (nf >= 9) ch.prm.sparse = sparse;
       ch.prm.na = na;
       ch.prm.warps = w;
       ch.prm.cache = c;
       ch.prm.acc_max = acc;
       ch.min_blocks = mb;
-      ch.prm.smem_budget = nf >= 6 ? (size_t) budget : smem_optin;
+      ch.prm.smem_budget = (nf >= 6 && budget > 0) ? (size_t) budget : smem_optin;
       const size_t b = p4_smem_bytes(p, ch.prm);
       ch.ok = b > 0 && b <= smem_optin;
       return ch;
@@ -42,6 +46,37 @@ P4Choice p4_choose(const Potential &p, size_t smem_optin, bool latency_shape)
   // 8 atoms per CTA and 8 warps: the chunk's critical path is what counts there.
   // Latency shape: a chunk streams the whole program through one SM whatever its width, so the widest chunk that fits
   // (16 atoms, else 8) halves the number of chunks per SM; 8 warps shorten the chunk's critical path.
+  // Throughput shape (measured on B200, profiles/r2_p4_shapes.txt): what the kernel waits for is instruction fetch
+  // (straight-line code, every CTA streams it), the barriers between stages and the latency of its own global traffic,
+  // so MORE RESIDENT CTAs beat bigger CTAs: each keeps only the basic moments its current round reads (sparse rounds),
+  // which lets four 4-warp CTAs (level <= 16 or so) or two 8-warp CTAs (levels 20-24) share an SM.
+  if (!latency_shape && !getenv("MTP_B200_P4_DENSE")) {
+    const size_t four_ctas = (smem_optin + 1024) / 4 - 1024;
+    P4Params prm;
+    prm.na = 32;
+    prm.cache = 40;    // 128 registers per thread at these occupancies
+    prm.acc_max = 12;
+    prm.sparse = 1;
+    int rounds = 0;
+    prm.warps = 4;
+    prm.smem_budget = four_ctas;
+    size_t b = p4_smem_bytes(p, prm, &rounds);
+    if (b > 0 && b <= four_ctas && rounds <= 4) {
+      ch.prm = prm;
+      ch.min_blocks = 4;
+      ch.ok = true;
+      return ch;
+    }
+    prm.warps = 8;
+    prm.smem_budget = two_ctas;
+    b = p4_smem_bytes(p, prm, &rounds);
+    if (b > 0 && b <= two_ctas && rounds <= 24) {
+      ch.prm = prm;
+      ch.min_blocks = 2;
+      ch.ok = true;
+      return ch;
+    }
+  }
   const int nas[2] = {latency_shape ? 16 : 32, latency_shape ? 8 : 32};
   for (int t = 0; t < (latency_shape ? 2 : 1); t++) {
     P4Params prm;

@@ -17,9 +17,11 @@ struct P4Choice {
   P4Params prm;
   int min_blocks = 1;    // CTAs per SM the kernel is compiled for (__launch_bounds__)
   bool ok = false;
+  int atoms_per_cta() const { return prm.na * (prm.groups > 1 ? prm.groups : 1); }    // per CTA iteration
 };
 
-// atoms per CTA / warps for potential p given the shared-memory limit; override: MTP_B200_P4="na,warps,cache,acc,minb"
+// atoms per CTA / warps for potential p given the shared-memory limit;
+// override: MTP_B200_P4="na,warps,cache,acc,minb[,smem_budget[,groups[,fn_cost[,sparse]]]]"
 P4Choice p4_choose(const Potential &p, size_t smem_optin, bool latency_shape);
 
 // directory of the cubin cache: $MTP_B200_KCACHE, else <directory of this shared library>/kcache

@@ -321,7 +321,7 @@ class MTPB200:
         """Which kernels the last compute launched (mtp_last_kernel_path)."""
         v = int(self.lib.mtp_last_kernel_path(self.h))
         return {"family": v & 15, "program_v3": bool(v & 16), "program_generated": bool(v & 32),
-                "program_atoms_per_cta": (v >> 8) & 255}
+                "program_atoms_per_cta": (v >> 8) & 4095}
 
     def program_kernel_note(self, latency_shape: bool = False) -> str:
         """Empty when the generated contraction-program kernel serves this handle, else why it does not."""

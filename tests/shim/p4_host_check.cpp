@@ -21,6 +21,7 @@
 #define P4_RET void
 #define P4_RETURN return
 #define P4_CALL(f) f(x)
+#define P4_GCALL(f) f(x)    // sparse / grouped form: the harness plays ONE atom group (the group loop is kernel plumbing)
 
 #ifdef P4_TWO
 struct T_ {
@@ -134,13 +135,28 @@ int main(int argc, char **argv)
   }
   // ---- generated program, scheduled like the kernel ----
   std::vector<double> S((size_t) P4_ROWS * NA, 1e300), Snext;    // poison: reading a row that was never written is visible
+#ifndef P4_SPARSE
   for (int k = 0; k < K; k++)
     for (int at = 0; at < NA; at++) S[(size_t) k * NA + at] = basic[(size_t) k * NA + at];
+#endif
   Snext = S;
   std::vector<double> gb((size_t) P4_NSLOTS * ld, 1e300), cand((size_t) NA * A, 1e300);
   std::vector<T_> e((size_t) P4_W * 32, ZERO);
   const int lanes = NA / P4_APL;
+  int round = 0;
   for (int st = 0; st < P4_NSTAGE; st++) {
+#ifdef P4_SPARSE
+    if (st == p4_round_stage0[round]) {    // a round starts: every row is stale, then the basic moments it reads are staged
+      S.assign(S.size(), 1e300);
+      std::vector<int> slot2k(P4_NSLOTS, -1);
+      for (int k = 0; k < K; k++) slot2k[p4_slot_of_k[k]] = k;
+      for (int i = p4_stage_off[round]; i < p4_stage_off[round + 1]; i++)
+        for (int at = 0; at < NA; at++) S[(size_t) p4_stage_row[i] * NA + at] = basic[(size_t) slot2k[p4_stage_slot[i]] * NA + at];
+      Snext = S;
+      round++;
+    }
+#endif
+    (void) round;
     for (int w = 0; w < P4_W; w++)
       for (int lane = 0; lane < lanes; lane++) {
         const int al = lane * P4_APL;

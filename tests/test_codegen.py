@@ -41,7 +41,7 @@ def _host_check(tmp_path, pot_path, pot, latency, env=None):
     tables = os.path.join(str(tmp_path), "tables.txt")
     _write_tables(tables, pot)
     exe = os.path.join(str(tmp_path), "p4_host_check")
-    two = ["-DP4_TWO"] if info["atoms_per_cta"] == 64 else []
+    two = ["-DP4_TWO"] if "#define P4_APL 2" in src else []    # two atoms per lane
     subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", f'-DP4_SOURCE="{gen}"'] + two + ["-o", exe, HARNESS], check=True)
     r = subprocess.run([exe, tables], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
