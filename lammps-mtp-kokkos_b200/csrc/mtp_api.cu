@@ -860,7 +860,12 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
   const int nsuper = (int) chunks.size();
   // grade scratch is not per lane; a program kernel that needs (nearly) all the shared memory of an SM cannot share it
   // with the kernels of another lane and only gets in their way (level 22: 215 ms serialised, 269 ms on three lanes)
-  const bool sm_filling_program = h->p4[0].loaded() && h->p4[0].info.smem_bytes > 160 * 1024 && !getenv("MTP_B200_FORCE_LANES");
+  // (measured again with two 115 KB CTAs per SM at level 22: 8.7 ms on one lane, 12.1 ms on three; at level 16 the four
+  // 57 KB CTAs are a fifth of the step and the lanes still gain 5 %: the rule looks at the program's share of the work too)
+  const P4Module &pm0 = h->p4[0];
+  const size_t p4_per_sm = pm0.loaded() ? pm0.info.smem_bytes * (size_t) std::max(1, pm0.grid_cap / std::max(1, h->sm_count)) : 0;
+  const bool sm_filling_program = pm0.loaded() && !getenv("MTP_B200_FORCE_LANES") &&
+                                  (pm0.info.smem_bytes > 160 * 1024 || (p4_per_sm > 200 * 1024 && pm0.info.terms >= 8000));
   const int nlanes = (use_v2 && !grade && !sm_filling_program) ? std::max(1, std::min(h->nlanes, nsuper)) : 1;
   if (use_v2) {
     const V2Entry &E = kV2[h->v2_entry];

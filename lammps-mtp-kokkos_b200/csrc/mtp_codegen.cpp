@@ -375,7 +375,7 @@ unsigned long long fnv(unsigned long long h, const void *data, size_t n)
   return h;
 }
 
-const char *kGeneratorVersion = "p4-r2-09";
+const char *kGeneratorVersion = "p4-r2-10";
 
 // ---- fixed text: device prelude and kernel skeleton ------------------------------------------------------
 const char *kDevicePrelude = R"P4(
@@ -414,17 +414,23 @@ struct P4Ctx {           // one context for the P4_G atom groups of the CTA iter
   double *gb, *cand;
   long long ld, cand_ld;
   int na, al, fbase;     // atoms of this iteration, first atom of the lane within a group, bit 2: grade step, bit 3: owner lane
-  T_ e[P4_G];
+  int grp;               // side-by-side groups: the group of this warp
+  T_ e[P4_GE];
 };
 #define P4_GROUP_BYTES (P4_ROWS * P4_NA * 8)
 // every emitted function runs P4_G times in a row, once per atom group: the second to last executions find it in the
 // instruction cache
+#if P4_SPATIAL
+#define P4_GLOOP for (int g_ = x.grp, e_ = 0; e_ < 1; e_++)
+#else
+#define P4_GLOOP _Pragma("unroll") for (int g_ = 0, e_ = 0; g_ < P4_G; g_++, e_++)
+#endif
 #define P4_GCALL(f) \
-  _Pragma("unroll") for (int g_ = 0; g_ < P4_G; g_++) { \
+  P4_GLOOP { \
     const int c_ = g_ * P4_NA + x.al; \
     const int fl_ = (x.fbase & 4) | (((x.fbase & 8) && c_ < x.na) ? 1 : 0) | ((P4_APL == 2 && (x.fbase & 8) && c_ + 1 < x.na) ? 2 : 0); \
-    x.e[g_] = f(x.sb + g_ * P4_GROUP_BYTES, x.lb, x.gb + g_ * P4_NA, x.ld, \
-                x.cand ? x.cand + (long long) g_ * P4_NA * x.cand_ld : x.cand, x.cand_ld, fl_, x.e[g_]); \
+    x.e[e_] = f(x.sb + g_ * P4_GROUP_BYTES, x.lb, x.gb + g_ * P4_NA, x.ld, \
+                x.cand ? x.cand + (long long) g_ * P4_NA * x.cand_ld : x.cand, x.cand_ld, fl_, x.e[e_]); \
   }
 #else
 struct P4Ctx {
@@ -592,14 +598,19 @@ extern "C" __global__ void __launch_bounds__(P4_W * 32, P4_MINB) mtp_program_p4(
 // S + g * P4_ROWS * P4_NA; at the first stage of a round the basic moments that round reads are staged for all groups.
 const char *kKernelSparse = R"P4(
 #ifndef P4_HOST
-extern "C" __global__ void __launch_bounds__(P4_W * 32, P4_MINB) mtp_program_p4(const P4Args a)
+extern "C" __global__ void __launch_bounds__(P4_NT, P4_MINB) mtp_program_p4(const P4Args a)
 {
   extern __shared__ __align__(16) double S[];
   constexpr int NAC = P4_NA * P4_G;    // atoms per CTA iteration
   double *s_lin = S + (size_t) P4_ROWS * NAC;
   double *epart = s_lin + ((P4_A + 1) & ~1);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int t = tid; t < P4_A; t += P4_W * 32) s_lin[t] = a.lin[t];
+  const int tid = threadIdx.x, lane = tid & 31;
+#if P4_SPATIAL
+  const int warp = (tid >> 5) % P4_W, grp = (tid >> 5) / P4_W;    // warp = which share of a stage, grp = whose atoms
+#else
+  const int warp = tid >> 5, grp = 0;
+#endif
+  for (int t = tid; t < P4_A; t += P4_NT) s_lin[t] = a.lin[t];
   const int al = (P4_APL * lane) % P4_NA;        // first atom of this lane within a group
   const bool owner = P4_APL * lane < P4_NA;      // lanes beyond the group width repeat the work of another lane, never write
   double e_thread = 0.0;
@@ -616,8 +627,9 @@ extern "C" __global__ void __launch_bounds__(P4_W * 32, P4_MINB) mtp_program_p4(
     x.na = na;
     x.al = al;
     x.fbase = (owner ? 8 : 0) | (a.grade ? 4 : 0);
+    x.grp = grp;
 #pragma unroll
-    for (int g = 0; g < P4_G; g++) {
+    for (int g = 0; g < P4_GE; g++) {
 #if P4_APL == 2
       x.e[g].x = x.e[g].y = 0.0;
 #else
@@ -629,7 +641,7 @@ extern "C" __global__ void __launch_bounds__(P4_W * 32, P4_MINB) mtp_program_p4(
     for (int st = 0; st < P4_NSTAGE; st++) {
       if (st == p4_round_stage0[round]) {    // basic moments this round reads -> their rows, every group (16-byte cp.async, zero fill past the end)
         const int i0 = p4_stage_off[round], nrow = p4_stage_off[round + 1] - i0;
-        for (int t = tid; t < nrow * (NAC / 2); t += P4_W * 32) {
+        for (int t = tid; t < nrow * (NAC / 2); t += P4_NT) {
           const int i = i0 + t / (NAC / 2), c = (t % (NAC / 2)) * 2;
           const int nb = max(0, min(2, na - c)) * 8;
           const unsigned dst = (unsigned) __cvta_generic_to_shared(S + ((size_t) (c / P4_NA) * P4_ROWS + p4_stage_row[i]) * P4_NA + c % P4_NA);
@@ -644,24 +656,25 @@ extern "C" __global__ void __launch_bounds__(P4_W * 32, P4_MINB) mtp_program_p4(
       p4_run_stage(st, warp, x);
       __syncthreads();
     }
-    for (int t = tid; t < P4_NZERO * NAC; t += P4_W * 32) {    // rows of gb that no basic moment owns
+    for (int t = tid; t < P4_NZERO * NAC; t += P4_NT) {    // rows of gb that no basic moment owns
       const int c = t % NAC;
       if (c < na) a.gb[(long long) p4_zero_slot[t / NAC] * a.ld + chunk0 + c] = 0.0;
     }
     if (a.eflag_global || a.eflag_atom) {    // fixed-order sum over the warps, species term (pair_mtp.cpp:204-212)
       if (owner) {
 #pragma unroll
-        for (int g = 0; g < P4_G; g++) {
+        for (int ge = 0; ge < P4_GE; ge++) {
+          const int g = P4_SPATIAL ? grp : ge;
 #if P4_APL == 2
-          epart[(warp * P4_G + g) * P4_NA + al] = x.e[g].x;
-          epart[(warp * P4_G + g) * P4_NA + al + 1] = x.e[g].y;
+          epart[(warp * P4_G + g) * P4_NA + al] = x.e[ge].x;
+          epart[(warp * P4_G + g) * P4_NA + al + 1] = x.e[ge].y;
 #else
-          epart[(warp * P4_G + g) * P4_NA + al] = x.e[g];
+          epart[(warp * P4_G + g) * P4_NA + al] = x.e[ge];
 #endif
         }
       }
       __syncthreads();
-      for (int c = tid; c < na; c += P4_W * 32) {
+      for (int c = tid; c < na; c += P4_NT) {
         const int i = a.ilist ? a.ilist[a.first_ii + chunk0 + c] : a.first_ii + chunk0 + c;
         int itype = (int) *reinterpret_cast<const long long *>(reinterpret_cast<const char *>(a.xt) + 32 * (size_t) i + 24);
         if (itype < 0 || itype >= a.S) itype = 0;
@@ -680,7 +693,7 @@ extern "C" __global__ void __launch_bounds__(P4_W * 32, P4_MINB) mtp_program_p4(
   if (tid < 8) {
     double s = 0.0;
     if (tid == 0)
-      for (int t = 0; t < P4_W * 32; t++) s += epart[t];
+      for (int t = 0; t < P4_NT; t++) s += epart[t];
     a.partials[(size_t) blockIdx.x * 8 + tid] = s;
   }
 }
@@ -873,6 +886,8 @@ P4Params normalised(P4Params prm)
 {
   prm.groups = std::max(1, prm.groups);
   if (prm.groups > 1) prm.sparse = 1;
+  else
+    prm.spatial = 0;
   return prm;
 }
 }    // namespace
@@ -933,13 +948,13 @@ bool p4_generate(const Potential &p, const P4Params &prm_in, const short *slot_o
   info.rounds = nrounds;
   info.smem_bytes = smem_of_rows(rows, an0.A, prm);
   info.terms = terms;
-  info.threads = prm.warps * 32;
+  info.threads = prm.warps * 32 * (prm.spatial ? prm.groups : 1);
   info.groups = prm.groups;
 
   unsigned long long h = 1469598103934665603ULL;
   h = fnv(h, kGeneratorVersion, strlen(kGeneratorVersion));
-  const long long hdr[13] = {K, an0.M, an0.T, an0.A, prm.na, prm.warps, prm.cache, prm.acc_max, nslots, prm.fn_cost,
-                             (long long) prm.smem_budget, prm.groups, prm.sparse};
+  const long long hdr[14] = {K, an0.M, an0.T, an0.A, prm.na, prm.warps, prm.cache, prm.acc_max, nslots, prm.fn_cost,
+                             (long long) prm.smem_budget, prm.groups, prm.sparse, prm.spatial};
   h = fnv(h, hdr, sizeof(hdr));
   h = fnv(h, p.alpha_index_times.data(), p.alpha_index_times.size() * sizeof(int));
   h = fnv(h, p.alpha_moment_mapping.data(), p.alpha_moment_mapping.size() * sizeof(int));
@@ -956,7 +971,8 @@ bool p4_generate(const Potential &p, const P4Params &prm_in, const short *slot_o
            "#define P4_A %d\n#define P4_M %d\n#define P4_NSTAGE %d\n#define P4_NSLOTS %d\n#ifndef P4_MINB\n#define P4_MINB 1\n#endif\n",
            kGeneratorVersion, K, an0.M, an0.T, an0.A, nrounds, prm.na, apl, prm.warps, rows, m_rows, K, an0.A, an0.M, nstages, nslots);
   src += buf;
-  snprintf(buf, sizeof(buf), "#define P4_G %d\n#define P4_NROUND %d\n%s", prm.groups, nrounds, prm.sparse ? "#define P4_SPARSE 1\n" : "");
+  snprintf(buf, sizeof(buf), "#define P4_G %d\n#define P4_NROUND %d\n#define P4_SPATIAL %d\n#define P4_GE %d\n#define P4_NT %d\n%s",
+           prm.groups, nrounds, prm.spatial ? 1 : 0, prm.spatial ? 1 : prm.groups, info.threads, prm.sparse ? "#define P4_SPARSE 1\n" : "");
   src += buf;
   src += kDevicePrelude;
   // tables

@@ -37,6 +37,9 @@ struct P4Params {
                         // of `na` atoms, so that an instruction fetched once serves groups * na atoms (the code is
                         // straight-line and otherwise never reused; small functions stay in the instruction cache)
   int sparse = 0;       // 1: a round keeps only the basic moments it reads in shared memory (implied by groups > 1)
+  int spatial = 0;      // 1 (with groups > 1): the groups run SIDE BY SIDE on `groups` sets of `warps` warps instead of one
+                        // after the other: warp w of every set executes the same function at the same time (the stage
+                        // barriers keep them together), so one instruction stream feeds `groups` warps
 };
 
 struct P4Info {

@@ -20,12 +20,13 @@ P4Choice p4_choose(const Potential &p, size_t smem_optin, bool latency_shape)
   if (const char *e = getenv(latency_shape ? "MTP_B200_P4_SMALL" : "MTP_B200_P4")) {
     int na = 0, w = 0, c = 0, acc = 0, mb = 0;
     long budget = 0;
-    int groups = 1, fn_cost = 0, sparse = 0;
-    const int nf = sscanf(e, "%d,%d,%d,%d,%d,%ld,%d,%d,%d", &na, &w, &c, &acc, &mb, &budget, &groups, &fn_cost, &sparse);
+    int groups = 1, fn_cost = 0, sparse = 0, spatial = 0;
+    const int nf = sscanf(e, "%d,%d,%d,%d,%d,%ld,%d,%d,%d,%d", &na, &w, &c, &acc, &mb, &budget, &groups, &fn_cost, &sparse, &spatial);
     if (nf >= 5) {
       if (nf >= 7) ch.prm.groups = groups;
       if (nf >= 8 && fn_cost > 0) ch.prm.fn_cost = fn_cost;
       if (nf >= 9) ch.prm.sparse = sparse;
+      if (nf >= 10) ch.prm.spatial = spatial;
       ch.prm.na = na;
       ch.prm.warps = w;
       ch.prm.cache = c;

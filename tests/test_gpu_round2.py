@@ -40,6 +40,33 @@ def test_other_kernel_families_match_the_oracle(tmp_path, built, monkeypatch, en
     mtp.close()
 
 
+@pytest.mark.parametrize("spec,atoms", [("32,4,40,12,4,18000,1,4000,1", 32),        # sparse rounds, later rounds RED.ADD their adjoints
+                                        ("32,4,24,8,2,30000,2", 64),                # two atom groups, one after the other
+                                        ("32,4,24,8,1,60000,4,60,1,1", 128),        # four groups side by side
+                                        ("64,8,24,8,1,60000,2", 128)])              # two atoms per lane x two groups
+@pytest.mark.parametrize("grade", [False, True])
+def test_generated_program_shapes_match_the_oracle(tmp_path, built, monkeypatch, spec, atoms, grade):
+    """Every form of the generated contraction-program kernel the generator can emit (sparse rounds, atom groups in time
+    or side by side, two atoms per lane), forced on a level-12 potential and compared with the oracle; the list is ragged
+    (a tail chunk shorter than a group) and long enough that a CTA iterates."""
+    from mtp_b200.api import MTPB200
+    from oracle_py import OracleMTP
+    monkeypatch.setenv("MTP_B200_P4", spec)
+    monkeypatch.setenv("MTP_B200_P4_SMALL", spec)     # a small system would otherwise take the latency shape
+    monkeypatch.setenv("MTP_B200_P4_REQUIRE", "1")
+    monkeypatch.setenv("MTP_B200_KCACHE", str(tmp_path / "kcache"))
+    path, pot = util.write_potential(tmp_path, 12, 2, active_set=grade)
+    sysm = util.small_system("bcc", 3.165, (7, 7, 7), 2, seed=5)
+    ilist = sysm.ilist[: sysm.nlocal - 7]
+    ref = OracleMTP(pot).compute(sysm.x, sysm.type, ilist, sysm.numneigh, sysm.neigh, sysm.offsets, grade=grade)
+    mtp = MTPB200(path, selection_state=grade)
+    gpu = mtp.compute_host(sysm.x, sysm.type, ilist, sysm.numneigh, sysm.neigh, sysm.offsets, grade=grade)
+    used = mtp.last_kernel_path()
+    assert used["program_generated"] and used["program_atoms_per_cta"] == atoms, (used, mtp.program_kernel_note())
+    _cmp(gpu, ref, ilist, grade)
+    mtp.close()
+
+
 def _permuted(tmp_path, level, species, truncate=False):
     """The same potential with its basic moments renumbered at random and the products of every dependency wave
     shuffled, as a file from another generator may order them; truncate: drop the last basic moment nobody multiplies
