@@ -155,6 +155,17 @@ def pinned_like(a):
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
+def cpu_model():
+    """Host CPU model string (so that two rounds' reference arms can be compared)."""
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def run_reference(args, cfg, pot_path, pot):
     """The reference's own CPU `mtp` (oracle/_ref, unmodified sources) on all host cores; falls back to
     the C restatement (kind "port") only if the prebuilt reference library did not travel."""
@@ -284,7 +295,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "sample": r["sample"]},
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
-                                 "sample": r["sample"]},
+                                 "sample": r["sample"], "cpu_model": cpu_model()},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         emit(line)
@@ -751,7 +762,8 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         r = run_reference(argparse.Namespace(**{**vars(args), "steps": 8, "warmup": 1}), cfg, pot_path, pot)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+               "cpu_model": cpu_model()}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",

@@ -224,6 +224,7 @@ struct mtp_handle {
   int grid_cap[2] = {0, 0};
   // three-kernel pipeline (register-resident family)
   DevBuf<double> d_mb, d_gb;      // [K][ld] basic moments / their adjoints of the current super-chunk
+  DevBuf<double> d_esite;         // rounds in parallel + eflag_atom: [lane][round][ld] site-energy shares
   int pl_na_fit = 0;              // largest atoms-per-CTA of the program kernel that fits shared memory
   int pl_grid_m = 0, pl_grid_p = 0, pl_grid_f[2] = {0, 0};
   size_t pl_smem_m = 0, pl_smem_f[2] = {0, 0};
@@ -946,7 +947,8 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
     }
   }
   h->last_path = (use_v2 ? 2 : pipeline ? 1 : 0) | (p3 ? 16 : 0) | (p4m ? 32 : 0) | (na << 8);
-  const int rows_per_super = pipeline ? grid_p_cap + std::max(h->pl_grid_f[gi], h->v2_grid_f) : h->grid_cap[gi];
+  const int p4_rounds = (p4m && p4m->info.rpar_rounds > 1) ? p4m->info.rpar_rounds : 1;    // rounds in parallel: gridDim.y
+  const int rows_per_super = pipeline ? grid_p_cap * p4_rounds + std::max(h->pl_grid_f[gi], h->v2_grid_f) : h->grid_cap[gi];
   h->d_partials.ensure((size_t) nsuper * rows_per_super * 8);
   int rows_used = 0;
   if (nlanes > 1) {    // fork: the lanes start after everything queued on the caller's stream so far
@@ -954,7 +956,8 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
     for (int l = 0; l < nlanes; l++) CUDA_CHECK(cudaStreamWaitEvent(h->lanes[l].stream, h->ev_fork, 0));
   }
 
-  auto launch_p4 = [&](const SiteArgs &sa, const double *mbp, double *gbp, double *part, int grid, cudaStream_t ls) {
+  // returns the rows of `part` the launch fills
+  auto launch_p4 = [&](const SiteArgs &sa, const double *mbp, double *gbp, double *part, int grid, cudaStream_t ls, int lane) -> int {
     P4Args pa{};
     pa.mb = mbp;
     pa.gb = gbp;
@@ -974,8 +977,20 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
     pa.cand_ld = sa.cand_ld;
     pa.cand_col0 = d.S * d.S * d.R * d.B + d.S;
     pa.partials = part;
+    pa.esite = nullptr;
+    if (p4_rounds > 1) {    // every round ADDS its shares: gb starts at zero; per-atom energies are summed in round order
+      CUDA_CHECK(cudaMemsetAsync(gbp, 0, (size_t) h->p4_nslots * ld * sizeof(double), ls));
+      if (sa.eflag_atom) {
+        h->d_esite.ensure((size_t) mtp_handle::kMaxLanes * p4_rounds * ld);    // one region per lane
+        pa.esite = h->d_esite.p + (size_t) lane * p4_rounds * ld;
+      }
+    }
     void *kargs[] = {&pa};
-    CUDA_CHECK(cudaLaunchKernel((const void *) p4m->kernel, dim3(grid), dim3(p4m->info.threads), kargs, p4m->info.smem_bytes, ls));
+    CUDA_CHECK(cudaLaunchKernel((const void *) p4m->kernel, dim3(grid, p4_rounds), dim3(p4m->info.threads), kargs,
+                                p4m->info.smem_bytes, ls));
+    if (pa.esite && sa.inum > 0)
+      esite_sum_kernel<<<(sa.inum + 255) / 256, 256, 0, ls>>>(sa.inum, sa.first_ii, sa.ilist, pa.esite, ld, p4_rounds, sa.eatom);
+    return grid * p4_rounds;
   };
 
   // a phase is complete when every lane has drained the chunks dealt to it so far
@@ -1037,9 +1052,10 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
       }
       const int gp = std::max(1, std::min(grid_p_cap, (n + na - 1) / na));
       double *part_p = h->d_partials.p + (size_t) rows_used * 8;
+      int rows_p = gp;
       {
         ProfSpan sp(h, MTP_PROF_PROGRAM, ls);
-        if (p4m) launch_p4(s, L.mb.p, L.gb.p, part_p, gp, ls);
+        if (p4m) rows_p = launch_p4(s, L.mb.p, L.gb.p, part_p, gp, ls, sc % nlanes);
         else if (p3)
           p3<<<gp, P3_THREADS, smem_p, ls>>>(d, s, h->f3f, h->f3r, L.mb.p, L.gb.p, ld, part_p);
         else if (grade)
@@ -1047,7 +1063,7 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
         else
           mtp_program_kernel<false><<<gp, PROG_THREADS, smem_p, ls>>>(d, s, L.mb.p, L.gb.p, ld, na, lna, part_p);
       }
-      rows_used += gp;
+      rows_used += rows_p;
       const int ab = h->v2_ab;
       const int gf = std::max(1, std::min(h->v2_grid_fg[gi], (n + ab - 1) / ab));
       double *part_f = h->d_partials.p + (size_t) rows_used * 8;
@@ -1076,9 +1092,10 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
       }
       const int gp = std::max(1, std::min(grid_p_cap, (n + na - 1) / na));
       double *part_p = h->d_partials.p + (size_t) rows_used * 8;
+      int rows_p = gp;
       {
         ProfSpan sp(h, MTP_PROF_PROGRAM, st);
-        if (p4m) launch_p4(s, h->d_mb.p, h->d_gb.p, part_p, gp, st);
+        if (p4m) rows_p = launch_p4(s, h->d_mb.p, h->d_gb.p, part_p, gp, st, 0);
         else if (p3)
           p3<<<gp, P3_THREADS, smem_p, st>>>(d, s, h->f3f, h->f3r, h->d_mb.p, h->d_gb.p, ld, part_p);
         else if (grade)
@@ -1086,7 +1103,7 @@ void launch_site(mtp_handle *h, const mtp_compute_args &a, cudaStream_t st,
         else
           mtp_program_kernel<false><<<gp, PROG_THREADS, smem_p, st>>>(d, s, h->d_mb.p, h->d_gb.p, ld, na, lna, part_p);
       }
-      rows_used += gp;
+      rows_used += rows_p;
       const int gf = std::max(1, std::min(h->pl_grid_f[gi], (n + W - 1) / W));
       double *part_f = h->d_partials.p + (size_t) rows_used * 8;
       {

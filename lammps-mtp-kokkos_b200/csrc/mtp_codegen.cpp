@@ -375,7 +375,7 @@ unsigned long long fnv(unsigned long long h, const void *data, size_t n)
   return h;
 }
 
-const char *kGeneratorVersion = "p4-r2-10";
+const char *kGeneratorVersion = "p4-r2-11";
 
 // ---- fixed text: device prelude and kernel skeleton ------------------------------------------------------
 const char *kDevicePrelude = R"P4(
@@ -395,6 +395,7 @@ struct P4Args {
   long long cand_ld;
   int cand_col0;
   double *partials;
+  double *esite;
 };
 #define P4_FN __device__ __forceinline__
 #define P4_STAGE_FN __device__ __noinline__
@@ -614,6 +615,12 @@ extern "C" __global__ void __launch_bounds__(P4_NT, P4_MINB) mtp_program_p4(cons
   const int al = (P4_APL * lane) % P4_NA;        // first atom of this lane within a group
   const bool owner = P4_APL * lane < P4_NA;      // lanes beyond the group width repeat the work of another lane, never write
   double e_thread = 0.0;
+#if P4_RPAR
+  const int r_only = blockIdx.y;    // rounds in parallel: this CTA evaluates one round (gb was zeroed, every share is a RED.ADD)
+  const int st_begin = p4_round_stage0[r_only], st_end = r_only + 1 < P4_NROUND ? p4_round_stage0[r_only + 1] : P4_NSTAGE;
+#else
+  const int r_only = 0, st_begin = 0, st_end = P4_NSTAGE;
+#endif
   __syncthreads();
   for (int chunk0 = blockIdx.x * NAC; chunk0 < a.inum; chunk0 += gridDim.x * NAC) {
     const int na = min(NAC, a.inum - chunk0);
@@ -636,9 +643,9 @@ extern "C" __global__ void __launch_bounds__(P4_NT, P4_MINB) mtp_program_p4(cons
       x.e[g] = 0.0;
 #endif
     }
-    int round = 0;
+    int round = r_only;
 #pragma unroll 1
-    for (int st = 0; st < P4_NSTAGE; st++) {
+    for (int st = st_begin; st < st_end; st++) {
       if (st == p4_round_stage0[round]) {    // basic moments this round reads -> their rows, every group (16-byte cp.async, zero fill past the end)
         const int i0 = p4_stage_off[round], nrow = p4_stage_off[round + 1] - i0;
         for (int t = tid; t < nrow * (NAC / 2); t += P4_NT) {
@@ -656,7 +663,7 @@ extern "C" __global__ void __launch_bounds__(P4_NT, P4_MINB) mtp_program_p4(cons
       p4_run_stage(st, warp, x);
       __syncthreads();
     }
-    for (int t = tid; t < P4_NZERO * NAC; t += P4_NT) {    // rows of gb that no basic moment owns
+    for (int t = tid; t < (P4_RPAR ? 0 : P4_NZERO * NAC); t += P4_NT) {    // rows of gb that no basic moment owns
       const int c = t % NAC;
       if (c < na) a.gb[(long long) p4_zero_slot[t / NAC] * a.ld + chunk0 + c] = 0.0;
     }
@@ -680,8 +687,13 @@ extern "C" __global__ void __launch_bounds__(P4_NT, P4_MINB) mtp_program_p4(cons
         if (itype < 0 || itype >= a.S) itype = 0;
         double es = 0.0;
         for (int w = 0; w < P4_W; w++) es += epart[(w * P4_G + c / P4_NA) * P4_NA + c % P4_NA];
+#if P4_RPAR
+        if (r_only == 0) es += a.species[itype];
+        if (a.eflag_atom) a.esite[(long long) r_only * a.ld + chunk0 + c] = es;    // summed in round order afterwards
+#else
         es += a.species[itype];
         if (a.eflag_atom) a.eatom[i] = es;
+#endif
         if (a.eflag_global) e_thread += es;
       }
       __syncthreads();
@@ -694,7 +706,7 @@ extern "C" __global__ void __launch_bounds__(P4_NT, P4_MINB) mtp_program_p4(cons
     double s = 0.0;
     if (tid == 0)
       for (int t = 0; t < P4_NT; t++) s += epart[t];
-    a.partials[(size_t) blockIdx.x * 8 + tid] = s;
+    a.partials[((size_t) blockIdx.y * gridDim.x + blockIdx.x) * 8 + tid] = s;
   }
 }
 #endif
@@ -928,8 +940,9 @@ bool p4_generate(const Potential &p, const P4Params &prm_in, const short *slot_o
   if (!make_rounds(p, prm, rounds, why)) return false;
   const int nrounds = std::max<int>(1, (int) rounds.size());
   std::vector<Plan> plans((size_t) nrounds);
+  const bool rpar = prm.rpar && prm.sparse && nrounds > 1;    // rounds in parallel: no round is the first, all of them ADD
   for (int r = 0; r < nrounds; r++)
-    if (!make_plan(p, prm, plans[r], why, rounds.empty() ? nullptr : &rounds[r], r == 0)) return false;
+    if (!make_plan(p, prm, plans[r], why, rounds.empty() ? nullptr : &rounds[r], r == 0 && !rpar)) return false;
   const Analysis &an0 = plans[0].an;
   const int K = an0.K;
   int rows = 0, nstages = 0, m_rows = 0;
@@ -950,11 +963,12 @@ bool p4_generate(const Potential &p, const P4Params &prm_in, const short *slot_o
   info.terms = terms;
   info.threads = prm.warps * 32 * (prm.spatial ? prm.groups : 1);
   info.groups = prm.groups;
+  info.rpar_rounds = rpar ? nrounds : 0;
 
   unsigned long long h = 1469598103934665603ULL;
   h = fnv(h, kGeneratorVersion, strlen(kGeneratorVersion));
   const long long hdr[14] = {K, an0.M, an0.T, an0.A, prm.na, prm.warps, prm.cache, prm.acc_max, nslots, prm.fn_cost,
-                             (long long) prm.smem_budget, prm.groups, prm.sparse, prm.spatial};
+                             (long long) prm.smem_budget, prm.groups, prm.sparse, prm.spatial + 2 * (rpar ? 1 : 0)};
   h = fnv(h, hdr, sizeof(hdr));
   h = fnv(h, p.alpha_index_times.data(), p.alpha_index_times.size() * sizeof(int));
   h = fnv(h, p.alpha_moment_mapping.data(), p.alpha_moment_mapping.size() * sizeof(int));
@@ -971,8 +985,9 @@ bool p4_generate(const Potential &p, const P4Params &prm_in, const short *slot_o
            "#define P4_A %d\n#define P4_M %d\n#define P4_NSTAGE %d\n#define P4_NSLOTS %d\n#ifndef P4_MINB\n#define P4_MINB 1\n#endif\n",
            kGeneratorVersion, K, an0.M, an0.T, an0.A, nrounds, prm.na, apl, prm.warps, rows, m_rows, K, an0.A, an0.M, nstages, nslots);
   src += buf;
-  snprintf(buf, sizeof(buf), "#define P4_G %d\n#define P4_NROUND %d\n#define P4_SPATIAL %d\n#define P4_GE %d\n#define P4_NT %d\n%s",
-           prm.groups, nrounds, prm.spatial ? 1 : 0, prm.spatial ? 1 : prm.groups, info.threads, prm.sparse ? "#define P4_SPARSE 1\n" : "");
+  snprintf(buf, sizeof(buf), "#define P4_G %d\n#define P4_NROUND %d\n#define P4_SPATIAL %d\n#define P4_GE %d\n#define P4_NT %d\n#define P4_RPAR %d\n%s",
+           prm.groups, nrounds, prm.spatial ? 1 : 0, prm.spatial ? 1 : prm.groups, info.threads, rpar ? 1 : 0,
+           prm.sparse ? "#define P4_SPARSE 1\n" : "");
   src += buf;
   src += kDevicePrelude;
   // tables

@@ -40,6 +40,9 @@ struct P4Params {
   int spatial = 0;      // 1 (with groups > 1): the groups run SIDE BY SIDE on `groups` sets of `warps` warps instead of one
                         // after the other: warp w of every set executes the same function at the same time (the stage
                         // barriers keep them together), so one instruction stream feeds `groups` warps
+  int rpar = 0;         // 1 (sparse, more than one round): ROUNDS IN PARALLEL -- blockIdx.y selects the round a CTA
+                        // evaluates; every round adds its adjoint shares to a zeroed gb with RED.ADD.  For small systems
+                        // (mtp/small/kk): the critical path of a chunk is one round instead of the whole program
 };
 
 struct P4Info {
@@ -54,6 +57,7 @@ struct P4Info {
   long long crit_terms = 0; // sum over stages of the most loaded warp's term steps
   int threads = 0;
   int groups = 1;           // atom groups per CTA (atoms per CTA iteration = groups * na)
+  int rpar_rounds = 0;      // > 0: rounds run in parallel, launch with gridDim.y = rpar_rounds on a zeroed gb
   unsigned long long hash = 0;
 };
 
@@ -82,7 +86,8 @@ struct P4Args {
   double *cand_rows;
   long long cand_ld;
   int cand_col0;           // first column of the linear block of the candidate vector
-  double *partials;        // [gridDim.x][8]
+  double *partials;        // [gridDim.y * gridDim.x][8]
+  double *esite;           // rounds in parallel, eflag_atom: [round][ld] site-energy shares (summed by esite_sum_kernel)
 };
 
 }    // namespace mtpb200

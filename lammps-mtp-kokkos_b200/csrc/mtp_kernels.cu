@@ -504,6 +504,17 @@ __global__ void finalize_ev_kernel(const double *partials, int nrows, double *ev
   if (lane == 0) ev[c] = (accumulate ? ev[c] : 0.0) + s;
 }
 
+// rounds in parallel (generated program kernel, latency shape): eatom[i] = sum over rounds of the round's share, in round order
+__global__ void esite_sum_kernel(int inum, int first_ii, const int *__restrict__ ilist, const double *__restrict__ esite, int ld,
+                                 int rounds, double *__restrict__ eatom)
+{
+  const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ii >= inum) return;
+  double s = 0.0;
+  for (int r = 0; r < rounds; r++) s += esite[(size_t) r * ld + ii];
+  eatom[ilist ? ilist[first_ii + ii] : first_ii + ii] = s;
+}
+
 }    // namespace mtpb200
 #include "mtp_kernels_v1.cuh"
 #include "mtp_kernels_v2.cuh"

@@ -20,13 +20,15 @@ P4Choice p4_choose(const Potential &p, size_t smem_optin, bool latency_shape)
   if (const char *e = getenv(latency_shape ? "MTP_B200_P4_SMALL" : "MTP_B200_P4")) {
     int na = 0, w = 0, c = 0, acc = 0, mb = 0;
     long budget = 0;
-    int groups = 1, fn_cost = 0, sparse = 0, spatial = 0;
-    const int nf = sscanf(e, "%d,%d,%d,%d,%d,%ld,%d,%d,%d,%d", &na, &w, &c, &acc, &mb, &budget, &groups, &fn_cost, &sparse, &spatial);
+    int groups = 1, fn_cost = 0, sparse = 0, spatial = 0, rpar = 0;
+    const int nf = sscanf(e, "%d,%d,%d,%d,%d,%ld,%d,%d,%d,%d,%d", &na, &w, &c, &acc, &mb, &budget, &groups, &fn_cost, &sparse, &spatial,
+                          &rpar);
     if (nf >= 5) {
       if (nf >= 7) ch.prm.groups = groups;
       if (nf >= 8 && fn_cost > 0) ch.prm.fn_cost = fn_cost;
       if (nf >= 9) ch.prm.sparse = sparse;
       if (nf >= 10) ch.prm.spatial = spatial;
+      if (nf >= 11) ch.prm.rpar = rpar;
       ch.prm.na = na;
       ch.prm.warps = w;
       ch.prm.cache = c;
@@ -74,6 +76,28 @@ P4Choice p4_choose(const Potential &p, size_t smem_optin, bool latency_shape)
     if (b > 0 && b <= two_ctas && rounds <= 24) {
       ch.prm = prm;
       ch.min_blocks = 2;
+      ch.ok = true;
+      return ch;
+    }
+  }
+  // Latency shape, large programs: ROUNDS IN PARALLEL.  A chunk's critical path is the whole program streamed through one
+  // SM; cutting the basis functions into 2-16 sparse rounds that run as separate CTAs (gridDim.y = rounds, shares added to a
+  // zeroed gb by RED.ADD) divides that path by the number of rounds and fills the SMs a small system leaves idle.
+  if (latency_shape && !getenv("MTP_B200_P4_NO_RPAR")) {
+    const size_t four_ctas = (smem_optin + 1024) / 4 - 1024;
+    P4Params prm;
+    prm.na = 16;
+    prm.warps = 4;
+    prm.cache = 40;
+    prm.acc_max = 12;
+    prm.sparse = 1;
+    prm.rpar = 1;
+    prm.smem_budget = four_ctas;
+    int rounds = 0;
+    const size_t b = p4_smem_bytes(p, prm, &rounds);
+    if (b > 0 && b <= four_ctas && rounds >= 2 && rounds <= 16) {
+      ch.prm = prm;
+      ch.min_blocks = 4;
       ch.ok = true;
       return ch;
     }

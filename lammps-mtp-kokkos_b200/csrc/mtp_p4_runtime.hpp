@@ -21,7 +21,7 @@ struct P4Choice {
 };
 
 // atoms per CTA / warps for potential p given the shared-memory limit;
-// override: MTP_B200_P4="na,warps,cache,acc,minb[,smem_budget[,groups[,fn_cost[,sparse]]]]"
+// override: MTP_B200_P4="na,warps,cache,acc,minb[,smem_budget[,groups[,fn_cost[,sparse[,spatial[,rpar]]]]]]"
 P4Choice p4_choose(const Potential &p, size_t smem_optin, bool latency_shape);
 
 // directory of the cubin cache: $MTP_B200_KCACHE, else <directory of this shared library>/kcache

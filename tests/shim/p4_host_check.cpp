@@ -140,7 +140,12 @@ int main(int argc, char **argv)
     for (int at = 0; at < NA; at++) S[(size_t) k * NA + at] = basic[(size_t) k * NA + at];
 #endif
   Snext = S;
-  std::vector<double> gb((size_t) P4_NSLOTS * ld, 1e300), cand((size_t) NA * A, 1e300);
+#if defined(P4_RPAR) && P4_RPAR
+  const double gb0 = 0.0;      // rounds in parallel: every round ADDS to a zeroed gb (the rounds are played in order here)
+#else
+  const double gb0 = 1e300;    // poison: the first round must write every row
+#endif
+  std::vector<double> gb((size_t) P4_NSLOTS * ld, gb0), cand((size_t) NA * A, 1e300);
   std::vector<T_> e((size_t) P4_W * 32, ZERO);
   const int lanes = NA / P4_APL;
   int round = 0;

@@ -93,6 +93,20 @@ def test_sparse_rounds_and_atom_groups(tmp_path):
     assert info["atoms_per_cta"] == 128 and info["warps"] == 8
 
 
+def test_rounds_in_parallel_for_the_latency_shape(tmp_path):
+    """mtp/small/kk: the rounds of a large program run as separate CTAs (gridDim.y = rounds); every round ADDS its adjoint
+    shares to a zeroed gb, none of them is "the first" (the emulation plays the rounds in order on a zeroed gb)."""
+    path, pot = util.write_potential(tmp_path, 12, 2)
+    info = _host_check(tmp_path, path, pot, False, env={"MTP_B200_P4": "16,4,24,8,4,9000,1,4000,1,0,1"})
+    assert info["rounds"] >= 2 and info["atoms_per_cta"] == 16
+    path, pot = util.write_potential(tmp_path, 20, 1)
+    src, info = api.codegen_source(path, True)                     # the library's own choice for config 3
+    assert "#define P4_RPAR 1" in src and 2 <= info["rounds"] <= 16 and info["atoms_per_cta"] == 16
+    assert "\n  GBST(" not in src and "\n  GBACC(" in src           # no plain adjoint store in any stage function
+    src, _ = api.codegen_source(path, False)
+    assert "#define P4_RPAR 0" in src                              # the throughput shape keeps its rounds in sequence
+
+
 def test_throughput_shape_prefers_resident_ctas(tmp_path):
     """Level 16 (config 2): four 4-warp CTAs per SM in sparse rounds; level 22 (config 5): two 8-warp CTAs per SM."""
     path, pot = util.write_potential(tmp_path, 16, 2)
