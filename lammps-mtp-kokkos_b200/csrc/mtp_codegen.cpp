@@ -784,7 +784,8 @@ bool make_plan(const Potential &p, const P4Params &prm, Plan &pl, std::string &w
 size_t smem_of_rows(int rows, int A, const P4Params &prm)
 {
   const size_t g = (size_t) std::max(1, prm.groups);
-  return ((size_t) rows * prm.na * g + (size_t) ((A + 1) & ~1) + (size_t) prm.warps * prm.na * g) * 8;
+  // rows, linear coefficients, energy partials: [warp][atom] per iteration, and one entry per THREAD for the CTA's sum
+  return ((size_t) rows * prm.na * g + (size_t) ((A + 1) & ~1) + (size_t) prm.warps * std::max(prm.na, 32) * g) * 8;
 }
 
 // Rounds.  When the rows of the whole program (moments of every operand node + adjoints of the non-basic ones) do not

@@ -81,9 +81,12 @@ P4Choice p4_choose(const Potential &p, size_t smem_optin, bool latency_shape)
     }
   }
   // Latency shape, large programs: ROUNDS IN PARALLEL.  A chunk's critical path is the whole program streamed through one
-  // SM; cutting the basis functions into 2-16 sparse rounds that run as separate CTAs (gridDim.y = rounds, shares added to a
+  // SM; cutting the basis functions into 2-8 sparse rounds that run as separate CTAs (gridDim.y = rounds, shares added to a
   // zeroed gb by RED.ADD) divides that path by the number of rounds and fills the SMs a small system leaves idle.
-  if (latency_shape && !getenv("MTP_B200_P4_NO_RPAR")) {
+  // MEASURED (config 3, 2,000 atoms, level 20): 66 us against 54 us for the single-CTA-per-chunk shape -- the rounds of all
+  // chunks stream more distinct code through the GPC instruction caches, which is what bounds the kernel, and the zeroing
+  // of gb is on the path.  Not the default; MTP_B200_P4_RPAR=1 selects it (levels 18-20 parity-tested on the GPU).
+  if (latency_shape && getenv("MTP_B200_P4_RPAR")) {
     const size_t four_ctas = (smem_optin + 1024) / 4 - 1024;
     P4Params prm;
     prm.na = 16;
@@ -95,7 +98,7 @@ P4Choice p4_choose(const Potential &p, size_t smem_optin, bool latency_shape)
     prm.smem_budget = four_ctas;
     int rounds = 0;
     const size_t b = p4_smem_bytes(p, prm, &rounds);
-    if (b > 0 && b <= four_ctas && rounds >= 2 && rounds <= 16) {
+    if (b > 0 && b <= four_ctas && rounds >= 2 && rounds <= 8) {
       ch.prm = prm;
       ch.min_blocks = 4;
       ch.ok = true;

@@ -100,11 +100,17 @@ def test_rounds_in_parallel_for_the_latency_shape(tmp_path):
     info = _host_check(tmp_path, path, pot, False, env={"MTP_B200_P4": "16,4,24,8,4,9000,1,4000,1,0,1"})
     assert info["rounds"] >= 2 and info["atoms_per_cta"] == 16
     path, pot = util.write_potential(tmp_path, 20, 1)
-    src, info = api.codegen_source(path, True)                     # the library's own choice for config 3
-    assert "#define P4_RPAR 1" in src and 2 <= info["rounds"] <= 16 and info["atoms_per_cta"] == 16
+    os.environ["MTP_B200_P4_RPAR"] = "1"                            # opt-in: measured slower than one CTA per chunk
+    try:
+        src, info = api.codegen_source(path, True)
+    finally:
+        del os.environ["MTP_B200_P4_RPAR"]
+    assert "#define P4_RPAR 1" in src and 2 <= info["rounds"] <= 8 and info["atoms_per_cta"] == 16
     assert "\n  GBST(" not in src and "\n  GBACC(" in src           # no plain adjoint store in any stage function
     src, _ = api.codegen_source(path, False)
     assert "#define P4_RPAR 0" in src                              # the throughput shape keeps its rounds in sequence
+    src, info = api.codegen_source(path, True)
+    assert "P4_RPAR 1" not in src and info["rounds"] == 1          # the default latency shape: one CTA per chunk, one round
 
 
 def test_throughput_shape_prefers_resident_ctas(tmp_path):
