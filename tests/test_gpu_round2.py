@@ -67,6 +67,36 @@ def test_generated_program_shapes_match_the_oracle(tmp_path, built, monkeypatch,
     mtp.close()
 
 
+@pytest.mark.parametrize("level,species", [(20, 1), (22, 3)])
+def test_sparse_round_throughput_shape_of_large_programs(tmp_path, built, level, species):
+    """Levels 20 / 22 (config 5) in the THROUGHPUT shape of the generated kernel -- two 8-warp CTAs per SM, sparse rounds,
+    RED.ADD adjoint shares -- against the oracle: the system gives every SM more than one 32-atom chunk, so this shape
+    (not the latency one the small goldens take) is the one that runs; one lane and three lanes, ragged tail."""
+    import torch
+    from mtp_b200 import api
+    from mtp_b200.api import MTPB200
+    from oracle_py import OracleMTP
+    path, pot = util.write_potential(tmp_path, level, species)
+    sysm = util.small_system("fcc", 3.56, (11, 11, 11), species, seed=5)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    ilist = sysm.ilist[: sysm.nlocal - 5]
+    assert len(ilist) >= 32 * sms
+    info = api.codegen_source(path, False)[1]
+    assert info["rounds"] > 1 and info["ctas_per_sm"] == 2 and info["atoms_per_cta"] == 32
+    ref = OracleMTP(pot).compute(sysm.x, sysm.type, ilist, sysm.numneigh, sysm.neigh, sysm.offsets)
+    mtp = MTPB200(path)
+    for lanes, chunk in ((1, 1 << 30), (3, 2048)):
+        mtp.set_lanes(lanes)
+        mtp.set_chunksize(chunk)
+        gpu = mtp.compute_host(sysm.x, sysm.type, ilist, sysm.numneigh, sysm.neigh, sysm.offsets)
+        used = mtp.last_kernel_path()
+        assert used["program_generated"], (used, mtp.program_kernel_note())
+        if lanes == 1:    # (super-chunks of 2,048 atoms are small systems again: they take the latency shape)
+            assert used["program_atoms_per_cta"] == 32, used
+        _cmp(gpu, ref, ilist)
+    mtp.close()
+
+
 def _permuted(tmp_path, level, species, truncate=False):
     """The same potential with its basic moments renumbered at random and the products of every dependency wave
     shuffled, as a file from another generator may order them; truncate: drop the last basic moment nobody multiplies
